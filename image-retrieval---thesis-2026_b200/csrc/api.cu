@@ -1,0 +1,157 @@
+// C-ABI entry points: argument validation, work decomposition, workspace carving, launches.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace knn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    cudaGetLastError();
+    return 148;  // B200
+  }
+  return sms;
+}
+
+// Work decomposition: a unit = (128-query block, gallery split).  Splits are contiguous gallery ranges,
+// multiples of the column tile; their number fills the 148 SMs for a few waves while keeping every unit
+// at least a handful of tiles long.  Query block is the fast grid index so concurrently resident CTAs
+// walk the SAME gallery range (L2 reuse of the gallery stream).
+static SearchGeom make_geom(int64_t nq, int64_t ng, int dtype, int k) {
+  SearchGeom g;
+  g.kp = kpad_for(k);
+  g.L = 2 * g.kp;
+  g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
+  if (g.qblocks < 1) g.qblocks = 1;
+  const int tile = dtype == KNN_BF16 ? bf16_tile_cols() : 128;
+  const int64_t ntiles = (ng + tile - 1) / tile;
+  const int sms = sm_count();
+  const int per_sm = dtype == KNN_BF16 ? 1 : 2;
+  int64_t want = ((int64_t)4 * sms * per_sm + g.qblocks - 1) / g.qblocks;   // ~4 waves
+  const int64_t fill = ((int64_t)sms * per_sm + g.qblocks - 1) / g.qblocks;  // one full wave
+  int64_t by_len = ntiles / 8;                                               // >= 8 tiles per unit
+  if (by_len < fill) by_len = fill;
+  if (want > by_len) want = by_len;
+  if (want > ntiles) want = ntiles;
+  if (want > 2048) want = 2048;
+  if (want < 1) want = 1;
+  const int64_t tiles_per_split = ntiles > 0 ? (ntiles + want - 1) / want : 1;
+  g.split_len = tiles_per_split * tile;
+  g.splits = ntiles > 0 ? (int)((ntiles + tiles_per_split - 1) / tiles_per_split) : 0;
+  return g;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace knn
+
+using namespace knn;
+
+extern "C" int knn_version(void) { return KNN_ABI_VERSION; }
+extern "C" const char* knn_last_error(void) { return g_err; }
+
+extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
+  (void)d;
+  if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
+  const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, dtype, k);
+  const size_t tau = align_up((size_t)g.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
+  const size_t lists = (size_t)(g.splits > 0 ? g.splits : 1) * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
+  return tau + lists;
+}
+
+static int check_common(const void* q, const void* g, const float* qs, const float* gs, int64_t nq, int64_t ng,
+                        int d, int dtype, int metric, int self_mode) {
+  KNN_REQUIRE(nq >= 0 && ng >= 0 && d >= 1, "bad shape nq=%lld ng=%lld d=%d", (long long)nq, (long long)ng, d);
+  KNN_REQUIRE(ng < 0xFFFFFFFEll, "gallery shard too large for 32-bit local rows: %lld", (long long)ng);
+  KNN_REQUIRE(dtype == KNN_F32 || dtype == KNN_BF16, "bad dtype %d", dtype);
+  KNN_REQUIRE(metric == KNN_COSINE || metric == KNN_IP || metric == KNN_L2, "bad metric %d", metric);
+  KNN_REQUIRE(self_mode >= KNN_SELF_KEEP && self_mode <= KNN_SELF_MINUS1, "bad self_mode %d", self_mode);
+  KNN_REQUIRE(!(metric == KNN_L2 && self_mode == KNN_SELF_MINUS1), "KNN_SELF_MINUS1 is a similarity convention");
+  if (nq > 0 && ng > 0) {
+    KNN_REQUIRE(q && g, "null q/g pointer");
+    KNN_REQUIRE(metric != KNN_L2 || (qs && gs), "KNN_L2 needs q_sqnorm and g_sqnorm");
+  }
+  return KNN_OK;
+}
+
+extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm, int64_t nq,
+                          int64_t ng, int d, int dtype, int k, int metric, int self_mode, int64_t self_offset,
+                          int64_t index_base, float* out_val, int64_t* out_idx, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
+  if (rc != KNN_OK) return rc;
+  KNN_REQUIRE(k >= 1, "k must be >= 1, got %d", k);
+  if (k > kMaxFusedK) {
+    set_error("knn_search: k=%d exceeds the fused limit %d; use knn_scores_dense + knn_rank_rows", k, kMaxFusedK);
+    return KNN_E_UNSUPPORTED;
+  }
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(out_val && out_idx, "null output pointer");
+  const size_t need = knn_search_workspace(nq, ng, d, dtype, k);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("knn_search: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return KNN_E_WORKSPACE;
+  }
+  KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const SearchGeom geo = make_geom(nq, ng, dtype, k);
+
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.g = g; p.qsq = q_sqnorm; p.gsq = g_sqnorm;
+  p.nq = nq; p.ng = ng; p.d = d; p.k = k; p.kp = geo.kp;
+  p.metric = metric; p.self_mode = self_mode;
+  p.self_offset = self_offset - index_base;
+  p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks;
+  const size_t tau_bytes = align_up((size_t)geo.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
+  p.tau_global = reinterpret_cast<uint32_t*>(workspace);
+  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + tau_bytes);
+  p.dense_out = nullptr;
+
+  if (geo.splits > 0) {
+    KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
+    rc = (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
+    if (rc != KNN_OK) return rc;
+  }
+  return launch_merge_units(p, index_base, out_val, out_idx, s);
+}
+
+extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
+                                int64_t nq, int64_t ng, int d, int dtype, int metric, int self_mode,
+                                int64_t self_offset, float* out, void* stream) {
+  int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
+  if (rc != KNN_OK) return rc;
+  if (dtype != KNN_F32) {
+    set_error("knn_scores_dense: fp32 inputs only (upcast bf16 rows first; the cast is exact)");
+    return KNN_E_UNSUPPORTED;
+  }
+  if (nq == 0 || ng == 0) return KNN_OK;
+  KNN_REQUIRE(out, "null output pointer");
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.g = g; p.qsq = q_sqnorm; p.gsq = g_sqnorm;
+  p.nq = nq; p.ng = ng; p.d = d; p.k = 1; p.kp = 32;
+  p.metric = metric; p.self_mode = self_mode; p.self_offset = self_offset;
+  p.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
+  const int64_t ntiles = (ng + 127) / 128;
+  int64_t want = ((int64_t)2 * sm_count() + p.qblocks - 1) / p.qblocks;
+  if (want > ntiles) want = ntiles;
+  if (want < 1) want = 1;
+  const int64_t tps = (ntiles + want - 1) / want;
+  p.split_len = tps * 128;
+  p.splits = (int)((ntiles + tps - 1) / tps);
+  p.dense_out = out;
+  return launch_search_f32(p, true, (cudaStream_t)stream);
+}

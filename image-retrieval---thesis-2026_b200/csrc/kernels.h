@@ -1,0 +1,35 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace knn {
+
+struct SearchParams {
+  const void* q;
+  const void* g;
+  const float* qsq;   // |q|^2 (L2 only)
+  const float* gsq;   // |g|^2 (L2 only)
+  int64_t nq, ng;
+  int d;
+  int k, kp;
+  int metric;
+  int self_mode;
+  int64_t self_offset;  // LOCAL gallery row of query 0 (query i is local row self_offset + i)
+  int64_t split_len;    // gallery rows per split
+  int splits;
+  int qblocks;
+  uint64_t* lists;       // [splits][qblocks][128][2*kp] candidate keys
+  uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
+  float* dense_out;      // dense mode only
+};
+
+int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream);
+int launch_search_bf16(const SearchParams& p, cudaStream_t stream);
+int bf16_tile_cols();  // gallery rows per tile of the tcgen05 kernel
+
+int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
+                       cudaStream_t stream);
+
+}  // namespace knn

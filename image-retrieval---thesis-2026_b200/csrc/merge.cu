@@ -1,0 +1,266 @@
+// Final selection over per-unit candidate lists, k-way merge of per-shard results, and full row ranking.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace knn {
+
+namespace {
+
+constexpr int kSortCap = 4096;      // keys sorted per shared-memory block
+constexpr int kSortThreads = 512;
+
+// In-shared-memory bitonic sort, descending overall; `gbase` is the global position of s[0] so the
+// same routine serves as the local stage of a larger network (direction depends on global position).
+__device__ __forceinline__ void smem_bitonic(uint64_t* s, int n, int size_from, int size_to, int stride_cap,
+                                             int64_t gbase) {
+  for (int size = size_from; size <= size_to; size <<= 1) {
+    int stride = size >> 1;
+    if (stride > stride_cap) stride = stride_cap;
+    for (; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int pos = ((i / stride) * (stride << 1)) + (i % stride);
+        const bool desc = (((gbase + pos) & (int64_t)size) == 0);
+        uint64_t a = s[pos], b = s[pos + stride];
+        const bool swap = desc ? (a < b) : (a > b);
+        if (swap) { s[pos] = b; s[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int pow2_ge(int x) {
+  int p = 2;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// One CTA per query row: gather the best-KP prefix of every gallery split's list, sort, emit top-k.
+__global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams p, int64_t index_base,
+                                                                 float* __restrict__ out_val,
+                                                                 int64_t* __restrict__ out_idx) {
+  __shared__ uint64_t s[kSortCap];
+  const int64_t r = blockIdx.x;
+  const int qb = (int)(r / kRowsPerUnit), lr = (int)(r % kRowsPerUnit);
+  const int kp = p.kp, L = 2 * p.kp;
+  const int64_t M = (int64_t)p.splits * kp;
+  const bool l2 = p.metric == KNN_L2;
+
+  for (int i = threadIdx.x; i < kp; i += blockDim.x) s[i] = 0ull;
+  int64_t consumed = 0;
+  do {
+    const int64_t left = M - consumed;
+    const int take = (int)(left < (kSortCap - kp) ? left : (kSortCap - kp));
+    const int n = pow2_ge(kp + take);
+    for (int i = threadIdx.x; i < n - kp; i += blockDim.x) {
+      uint64_t key = 0ull;
+      if (i < take) {
+        const int64_t c = consumed + i;
+        const int sp = (int)(c / kp), j = (int)(c % kp);
+        key = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
+      }
+      s[kp + i] = key;
+    }
+    __syncthreads();
+    smem_bitonic(s, n, 2, n, n, 0);
+    consumed += take;
+  } while (consumed < M);
+
+  for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+    const uint64_t key = s[j];
+    float v; int64_t id;
+    if (key == 0ull) {
+      v = l2 ? INFINITY : -INFINITY;
+      id = -1;
+    } else {
+      const float sc = key_score(key);
+      v = l2 ? (0.0f - sc) : sc;
+      id = (int64_t)key_row(key) + index_base;
+    }
+    out_val[r * p.k + j] = v;
+    out_idx[r * p.k + j] = id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k-way merge of `parts` sorted candidate lists per query by rank counting (no sort): the output slot
+// of candidate (part, j) is j + sum over the other parts of the number of their entries that precede
+// it in the total order (score best-first, then ascending gallery index, then part).
+// ------------------------------------------------------------------------------------------------
+struct Cand { uint32_t o; int64_t id; };
+
+__device__ __forceinline__ bool precedes(const Cand& x, int px, const Cand& a, int pa) {
+  if (x.o != a.o) return x.o > a.o;
+  if (x.id != a.id) return x.id < a.id;
+  return px < pa;
+}
+
+__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ vals,
+                                                        const int64_t* __restrict__ idx, int parts, int64_t nq,
+                                                        int k, int l2, float* __restrict__ out_val,
+                                                        int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  int64_t* sid = reinterpret_cast<int64_t*>(sm);                 // [parts*k]
+  uint32_t* so = reinterpret_cast<uint32_t*>(sid + parts * k);   // [parts*k]
+  const int64_t r = blockIdx.x;
+  const int n = parts * k;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const int pp = c / k, j = c % k;
+    const int64_t off = ((int64_t)pp * nq + r) * k + j;
+    const int64_t id = idx[off];
+    const float v = vals[off];
+    if (id < 0) { so[c] = 0u; sid[c] = INT64_MAX; }
+    else { so[c] = f2ord((l2 ? -v : v) + 0.0f); sid[c] = id; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    const int pa = c / k, j = c % k;
+    const Cand a{so[c], sid[c]};
+    int rank = j;
+    for (int px = 0; px < parts; ++px) {
+      if (px == pa) continue;
+      int lo = 0, hi = k;  // number of entries of list px preceding a
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const Cand x{so[px * k + mid], sid[px * k + mid]};
+        if (precedes(x, px, a, pa)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      const int64_t off = ((int64_t)pa * nq + r) * k + j;
+      out_val[r * k + rank] = vals[off];
+      out_idx[r * k + rank] = idx[off];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full ranking of every row: one CTA per row, bitonic network over Npad = pow2 >= ng keys, the
+// sub-networks of span <= 4096 run in shared memory, the wider strides in the global workspace.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) rank_rows_kernel(const float* __restrict__ scores, int64_t nq,
+                                                               int64_t ng, int largest_first, int64_t npad,
+                                                               uint64_t* __restrict__ ws,
+                                                               int64_t* __restrict__ ranks) {
+  __shared__ uint64_t s[kSortCap];
+  const int64_t r = blockIdx.x;
+  const float* srow = scores + r * ng;
+  uint64_t* wrow = ws + r * npad;
+  const int64_t nblocks = (npad + kSortCap - 1) / kSortCap;
+  const int bn = (int)(npad < kSortCap ? npad : kSortCap);
+
+  // phase A: sort every block of <= 4096 keys in shared memory (directions follow the global network)
+  for (int64_t b = 0; b < nblocks; ++b) {
+    const int64_t g0 = b * kSortCap;
+    for (int i = threadIdx.x; i < bn; i += blockDim.x) {
+      const int64_t c = g0 + i;
+      uint64_t key = 0ull;
+      if (c < ng) {
+        float v = srow[c];
+        v = largest_first ? v : -v;
+        key = ((uint64_t)f2ord(v + 0.0f) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)c);
+      }
+      s[i] = key;
+    }
+    __syncthreads();
+    smem_bitonic(s, bn, 2, bn, bn, g0);
+    if (nblocks == 1) {
+      for (int i = threadIdx.x; i < ng; i += blockDim.x) ranks[r * ng + i] = (int64_t)key_row(s[i]);
+      return;
+    }
+    for (int i = threadIdx.x; i < bn; i += blockDim.x) wrow[g0 + i] = s[i];
+    __syncthreads();
+  }
+  // phase B: wider sub-networks
+  for (int64_t size = 2 * (int64_t)kSortCap; size <= npad; size <<= 1) {
+    for (int64_t stride = size >> 1; stride >= kSortCap; stride >>= 1) {
+      for (int64_t i = threadIdx.x; i < (npad >> 1); i += blockDim.x) {
+        const int64_t pos = ((i / stride) * (stride << 1)) + (i % stride);
+        const bool desc = ((pos & size) == 0);
+        uint64_t a = wrow[pos], b = wrow[pos + stride];
+        const bool swap = desc ? (a < b) : (a > b);
+        if (swap) { wrow[pos] = b; wrow[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+    for (int64_t b = 0; b < nblocks; ++b) {
+      const int64_t g0 = b * kSortCap;
+      for (int i = threadIdx.x; i < kSortCap; i += blockDim.x) s[i] = wrow[g0 + i];
+      __syncthreads();
+      // remaining strides (< 4096) of this `size`: direction bit comes from the global position
+      int stride = kSortCap >> 1;
+      for (; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < (kSortCap >> 1); i += blockDim.x) {
+          const int pos = ((i / stride) * (stride << 1)) + (i % stride);
+          const bool desc = (((g0 + pos) & size) == 0);
+          uint64_t a = s[pos], bb = s[pos + stride];
+          const bool swap = desc ? (a < bb) : (a > bb);
+          if (swap) { s[pos] = bb; s[pos + stride] = a; }
+        }
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < kSortCap; i += blockDim.x) wrow[g0 + i] = s[i];
+      __syncthreads();
+    }
+  }
+  for (int64_t i = threadIdx.x; i < ng; i += blockDim.x) ranks[r * ng + i] = (int64_t)key_row(wrow[i]);
+}
+
+}  // namespace
+
+int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
+                       cudaStream_t stream) {
+  if (p.nq == 0) return KNN_OK;
+  merge_units_kernel<<<(unsigned)p.nq, kSortThreads, 0, stream>>>(p, index_base, out_val, out_idx);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+}  // namespace knn
+
+using namespace knn;
+
+extern "C" int knn_merge_topk(const float* vals, const int64_t* idx, int parts, int64_t nq, int k, int metric,
+                              float* out_val, int64_t* out_idx, void* stream) {
+  KNN_REQUIRE(vals && idx && out_val && out_idx, "knn_merge_topk: null pointer");
+  KNN_REQUIRE(parts >= 1 && k >= 1 && nq >= 0, "knn_merge_topk: bad sizes parts=%d k=%d nq=%lld", parts, k,
+              (long long)nq);
+  const size_t smem = (size_t)parts * k * 12;
+  KNN_REQUIRE(smem <= 200 * 1024, "knn_merge_topk: parts*k=%d too large (max %d)", parts * k, 200 * 1024 / 12);
+  if (nq == 0) return KNN_OK;
+  KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(vals, idx, parts, nq, k,
+                                                                     metric == KNN_L2 ? 1 : 0, out_val, out_idx);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+static int64_t rank_npad(int64_t ng) {
+  int64_t p = 2;
+  while (p < ng) p <<= 1;
+  return p;
+}
+
+extern "C" size_t knn_rank_rows_workspace(int64_t nq, int64_t ng) {
+  if (nq <= 0 || ng <= 0) return 0;
+  const int64_t npad = rank_npad(ng);
+  if (npad <= kSortCap) return 0;
+  return (size_t)nq * (size_t)npad * sizeof(uint64_t);
+}
+
+extern "C" int knn_rank_rows(const float* scores, int64_t nq, int64_t ng, int largest_first, int64_t* ranks,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  KNN_REQUIRE(nq >= 0 && ng >= 0 && ng < 0xFFFFFFFFll, "knn_rank_rows: bad sizes");
+  if (nq == 0 || ng == 0) return KNN_OK;
+  KNN_REQUIRE(scores && ranks, "knn_rank_rows: null pointer");
+  const size_t need = knn_rank_rows_workspace(nq, ng);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+    set_error("knn_rank_rows: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return KNN_E_WORKSPACE;
+  }
+  rank_rows_kernel<<<(unsigned)nq, kSortThreads, 0, (cudaStream_t)stream>>>(
+      scores, nq, ng, largest_first, rank_npad(ng), reinterpret_cast<uint64_t*>(workspace), ranks);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}

@@ -1,0 +1,242 @@
+// Exact-fp32 distance + fused top-k (the parity path).
+//
+// Arithmetic definition (restated bit-for-bit by oracle/knn_oracle.c):
+//   dot(q,g) = fmaf chain over d = 0..D-1 in ascending order starting from +0.0f (one FFMA per term,
+//              no split-K, no reassociation), i.e. plain fp32 accumulation like the reference's
+//              torch.mm / `@` (test.py:1006, train.py:405; MKL's summation order is unspecified).
+//   L2:  d = sqrt(max(rn(rn(|q|^2 + |g|^2) - 2*dot), 0))   (GEMM form of torch.cdist, test_ath.py:87)
+// Tile: 128 query rows x 128 gallery rows per CTA, BK = 16, 256 threads, 8x8 register micro-tile,
+// double-buffered shared memory.  Scores never leave the SM: the tile goes through shared memory to the
+// 128 row-owner threads which run the selection of select.cuh.
+#include "select.cuh"
+#include "kernels.h"
+
+namespace knn {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int LDA = BM + 4;   // padded leading dimension of the transposed operand tiles
+constexpr int LDS = BN + 1;   // padded leading dimension of the score tile
+constexpr int kThreads = 256;
+
+struct Frag { float4 v[2]; };
+
+template <bool kVec>
+__device__ __forceinline__ void load_tile(const float* __restrict__ X, int64_t r0, int64_t nrows, int d, int k0,
+                                          int tid, Frag& f) {
+  const int kq = (tid & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int64_t r = r0 + (tid >> 2) + h * 64;
+    if (r >= nrows) r = nrows - 1;  // clamp: results of padded rows are discarded later
+    const float* p = X + r * (int64_t)d + k0 + kq;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kVec) {
+      if (k0 + kq < d) v = __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+      if (k0 + kq + 0 < d) v.x = __ldg(p + 0);
+      if (k0 + kq + 1 < d) v.y = __ldg(p + 1);
+      if (k0 + kq + 2 < d) v.z = __ldg(p + 2);
+      if (k0 + kq + 3 < d) v.w = __ldg(p + 3);
+    }
+    f.v[h] = v;
+  }
+}
+
+__device__ __forceinline__ void store_tile(float* __restrict__ T, int tid, const Frag& f) {
+  const int kq = (tid & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = (tid >> 2) + h * 64;
+    T[(kq + 0) * LDA + r] = f.v[h].x;
+    T[(kq + 1) * LDA + r] = f.v[h].y;
+    T[(kq + 2) * LDA + r] = f.v[h].z;
+    T[(kq + 3) * LDA + r] = f.v[h].w;
+  }
+}
+
+template <int E, bool kL2, bool kDense, bool kVec>
+__global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                     // [2][BK][LDA]
+  float* Bs = As + 2 * BK * LDA;        // [2][BK][LDA]
+  float* Ss = Bs + 2 * BK * LDA;        // [BM][LDS]
+  float* gs = Ss + BM * LDS;            // [BN]
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int qb = blockIdx.x, sp = blockIdx.y;
+  const int64_t row0 = (int64_t)qb * BM;
+  const int64_t c_begin = (int64_t)sp * p.split_len;
+  const int64_t c_end = (c_begin + p.split_len < p.ng) ? c_begin + p.split_len : p.ng;
+  const float* __restrict__ Q = reinterpret_cast<const float*>(p.q);
+  const float* __restrict__ G = reinterpret_cast<const float*>(p.g);
+  const int ntk = (p.d + BK - 1) / BK;
+
+  // selection state of the row owners (threads 0..127 own query row row0 + tid)
+  constexpr int L = 32 * E;
+  RowState st;
+  const bool owner = tid < BM;
+  const bool row_valid = owner && (row0 + tid < p.nq);
+  uint32_t self_row = 0xFFFFFFFFu;
+  float qn = 0.f;
+  uint32_t* tau_row = nullptr;
+  if (!kDense && owner) {
+    const int64_t unit = (int64_t)sp * p.qblocks + qb;
+    rowstate_init(st, p.lists + ((unit * BM + tid) * (int64_t)L));
+    if (row_valid) {
+      const int64_t sr = p.self_offset + row0 + tid;
+      if (p.self_mode != KNN_SELF_KEEP && sr >= 0 && sr < p.ng) self_row = (uint32_t)sr;
+      if (kL2) qn = __ldg(p.qsq + row0 + tid);
+      tau_row = p.tau_global + row0 + tid;
+    }
+  }
+
+  for (int64_t col0 = c_begin; col0 < c_end; col0 += BN) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    Frag fa, fb;
+    load_tile<kVec>(Q, row0, p.nq, p.d, 0, tid, fa);
+    load_tile<kVec>(G, col0, p.ng, p.d, 0, tid, fb);
+    __syncthreads();  // previous tile's readers of As/Bs/Ss are done
+    store_tile(As, tid, fa);
+    store_tile(Bs, tid, fb);
+    __syncthreads();
+
+    for (int kt = 0; kt < ntk; ++kt) {
+      const int buf = kt & 1;
+      if (kt + 1 < ntk) {
+        load_tile<kVec>(Q, row0, p.nq, p.d, (kt + 1) * BK, tid, fa);
+        load_tile<kVec>(G, col0, p.ng, p.d, (kt + 1) * BK, tid, fb);
+      }
+      const float* a_s = As + buf * BK * LDA;
+      const float* b_s = Bs + buf * BK * LDA;
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(a_s + kk * LDA + ty * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(a_s + kk * LDA + 64 + ty * 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(b_s + kk * LDA + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(b_s + kk * LDA + 64 + tx * 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      if (kt + 1 < ntk) {
+        store_tile(As + (buf ^ 1) * BK * LDA, tid, fa);
+        store_tile(Bs + (buf ^ 1) * BK * LDA, tid, fb);
+      }
+      __syncthreads();
+    }
+
+    if (kDense) {
+      // write the tile (score definition identical to the selection path)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t r = row0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+        if (r >= p.nq) continue;
+        float qni = 0.f;
+        if (kL2) qni = __ldg(p.qsq + r);
+        const int64_t sr = (p.self_mode != KNN_SELF_KEEP) ? p.self_offset + r : -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t c = col0 + tx * 4 + (j & 3) + (j >> 2) * 64;
+          if (c >= c_end) continue;
+          float v = acc[i][j];
+          if (kL2) {
+            const float x = qni + __ldg(p.gsq + c);
+            v = __fsqrt_rn(fmaxf(-fmaf(2.0f, v, -x), 0.0f));
+          }
+          if (c == sr) {
+            if (p.self_mode == KNN_SELF_EXCLUDE) v = kL2 ? INFINITY : -INFINITY;
+            else if (p.self_mode == KNN_SELF_MINUS1) v = kL2 ? 1.0f : -1.0f;
+          }
+          p.dense_out[r * p.ng + c] = v;
+        }
+      }
+    } else {
+      // stage the score tile for the row owners
+      if (owner) {
+        if (kL2) {
+          int64_t c = col0 + tid;
+          if (c >= p.ng) c = p.ng - 1;
+          gs[tid] = __ldg(p.gsq + c);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = ty * 4 + (i & 3) + (i >> 2) * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = tx * 4 + (j & 3) + (j >> 2) * 64;
+          Ss[r * LDS + c] = acc[i][j];
+        }
+      }
+      __syncthreads();
+      if (owner) {
+        refresh_tau<kL2>(st, tau_row);
+        const float* srow = Ss + tid * LDS;
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+          const int64_t cg = col0 + cb;
+          const int64_t rem = c_end - cg;
+          const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
+          auto fv = [&](int j) -> float {
+            const float dot = srow[cb + j];
+            if (kL2) return fmaf(2.0f, dot, -(qn + gs[cb + j]));
+            return dot;
+          };
+          select_chunk<32, kL2>(st, fv, (uint32_t)cg, nvalid, self_row, p.self_mode, row_valid);
+          warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+        }
+      }
+      // next tile starts with a __syncthreads() before Ss / gs are overwritten
+    }
+  }
+
+  if (!kDense && owner) warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
+}
+
+size_t f32_smem_bytes() { return sizeof(float) * (size_t)(4 * BK * LDA + BM * LDS + BN); }
+
+template <int E, bool kL2, bool kDense, bool kVec>
+int launch_one(const SearchParams& p, cudaStream_t stream) {
+  auto kern = search_f32_kernel<E, kL2, kDense, kVec>;
+  const size_t smem = f32_smem_bytes();
+  KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);
+  kern<<<grid, kThreads, smem, stream>>>(p);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+template <int E, bool kDense>
+int launch_e(const SearchParams& p, bool vec, cudaStream_t stream) {
+  const bool l2 = p.metric == KNN_L2;
+  if (l2) return vec ? launch_one<E, true, kDense, true>(p, stream) : launch_one<E, true, kDense, false>(p, stream);
+  return vec ? launch_one<E, false, kDense, true>(p, stream) : launch_one<E, false, kDense, false>(p, stream);
+}
+
+}  // namespace
+
+int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream) {
+  const bool vec = (p.d % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.q) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.g) & 15) == 0);
+  if (dense) return launch_e<2, true>(p, vec, stream);
+  switch (p.kp) {
+    case 32: return launch_e<2, false>(p, vec, stream);
+    case 64: return launch_e<4, false>(p, vec, stream);
+    case 128: return launch_e<8, false>(p, vec, stream);
+    case 256: return launch_e<16, false>(p, vec, stream);
+    default: set_error("unsupported padded k %d", p.kp); return KNN_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace knn

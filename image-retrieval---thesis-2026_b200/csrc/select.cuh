@@ -1,0 +1,220 @@
+// Fused top-k selection shared by the fp32 (FFMA) and bf16 (tcgen05) distance kernels.
+//
+// Ownership model: inside a CTA every query row is owned by exactly ONE thread (the thread that reads
+// that row's scores: TMEM lane i <-> thread i of the epilogue warps).  The owner keeps, in registers,
+//   cnt  - number of candidates currently in the row's list
+//   tau  - score of the current k-th best candidate (-inf until k candidates were seen)
+// and appends every score that can still enter the top-k to a per-(unit,row) list in the global
+// workspace (L2 resident, capacity L = 2*KP >= 2k).  99.9 % of the scores are rejected by one max +
+// one compare per 32-score chunk.  When a list is about to overflow the WARP compacts it
+// cooperatively (bitonic sort of L 64-bit keys held L/32 per lane), keeps the best k and tightens tau.
+// Thresholds are shared between all CTAs working on the same query row through tau_global
+// (atomicMax of the order-preserving encoding), so late gallery splits start with a tight filter.
+//
+// Exactness: a candidate is dropped only if its score is < tau where tau is the k-th best key of some
+// subset of the gallery, hence <= the final k-th best; every member of the true top-k (ties resolved
+// by ascending gallery row through the key encoding) therefore survives to the final merge.
+#pragma once
+#include "common.cuh"
+
+namespace knn {
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+template <int E>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[E], int lane) {
+  // Bitonic network over n = 32*E keys, element index i = e*32 + lane, final order descending in i.
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int se = stride >> 5;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & se) == 0) {
+            const int i = e * 32 + lane;
+            const bool desc = ((i & size) == 0);
+            uint64_t a = v[e], b = v[e | se];
+            uint64_t hi = a > b ? a : b, lo = a > b ? b : a;
+            v[e] = desc ? hi : lo;
+            v[e | se] = desc ? lo : hi;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int i = e * 32 + lane;
+          const bool desc = ((i & size) == 0);
+          const bool lower = ((lane & stride) == 0);
+          uint64_t a = v[e];
+          uint64_t b = __shfl_xor_sync(kFullMask, a, stride);
+          const bool keep_max = (lower == desc);
+          v[e] = keep_max ? (a > b ? a : b) : (a > b ? b : a);
+        }
+      }
+    }
+  }
+}
+
+// Warp-cooperative compaction of one row's list: sort, keep the best `keep` (k, or KP at unit end),
+// return the new count and (if >= k candidates exist) the new threshold.  All 32 lanes must call.
+template <int E>
+__device__ __forceinline__ void compact_row(uint64_t* __restrict__ list, int cnt, int k, int keep, int lane,
+                                            int& new_cnt, uint64_t& new_taukey) {
+  uint64_t v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    v[e] = (i < cnt) ? __ldcg(list + i) : 0ull;
+  }
+  warp_sort_desc<E>(v, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    if (i < keep) __stcg(list + i, v[e]);
+  }
+  uint64_t kth = 0;
+  const int ke = (k - 1) >> 5, kl = (k - 1) & 31;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    uint64_t t = __shfl_sync(kFullMask, v[e], kl);
+    if (e == ke) kth = t;
+  }
+  new_cnt = cnt < k ? cnt : k;
+  new_taukey = (cnt >= k) ? kth : 0ull;  // 0 = "no threshold yet"
+}
+
+struct RowState {
+  uint64_t* list;   // this row's candidate list (capacity L)
+  int cnt;
+  float tau;        // exact score threshold (larger = better)
+  float ftau;       // threshold in "filter space" (== tau for similarities, -d^2 bound for L2)
+  uint64_t taukey;  // a candidate must have key > taukey (exact, tie-aware form of tau)
+};
+
+__device__ __forceinline__ void rowstate_init(RowState& st, uint64_t* list) {
+  st.list = list;
+  st.cnt = 0;
+  st.tau = -INFINITY;
+  st.ftau = -INFINITY;
+  st.taukey = 0ull;
+}
+
+template <bool kL2>
+__device__ __forceinline__ float filter_tau(float tau) {
+  if (!kL2) return tau;
+  // tau = -d_k.  A candidate qualifies iff d <= d_k with d = rn(sqrt(d2)); conservative bound on d2:
+  // d2 <= d_k^2 * (1 + 4e-6) never rejects a qualifying candidate.
+  if (tau == -INFINITY) return -INFINITY;
+  float dk = -tau;
+  return -(dk * dk * 1.000004f + 1e-37f);
+}
+
+template <bool kL2>
+__device__ __forceinline__ float exact_score(float f) {
+  // f is the filter value: dot for similarities, -(|q|^2+|g|^2-2 q.g) for L2.
+  if (!kL2) return f;
+  return -__fsqrt_rn(fmaxf(-f, 0.0f));
+}
+
+// One chunk of CH filter values owned by this thread (fv(j): value of column col0+j, larger = better).
+// Fast path: one max-reduce + one compare.  Slow path: exact score, self handling, tie-aware key test,
+// append to the row's list.  The caller guarantees cnt <= L - CH on entry.
+template <int CH, bool kL2, class FV>
+__device__ __forceinline__ void select_chunk(RowState& st, FV fv, uint32_t col0, uint32_t ncols_valid,
+                                             uint32_t self_row, int self_mode, bool row_valid) {
+  float m = fv(0);
+#pragma unroll
+  for (int j = 1; j < CH; ++j) m = fmaxf(m, fv(j));
+  if (row_valid && m >= st.ftau) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float f = fv(j);
+      if (f >= st.ftau && (uint32_t)j < ncols_valid) {
+        const uint32_t row = col0 + (uint32_t)j;
+        float s = exact_score<kL2>(f);
+        bool take = true;
+        if (row == self_row) {
+          if (self_mode == KNN_SELF_EXCLUDE) take = false;
+          else if (self_mode == KNN_SELF_MINUS1) s = -1.0f;
+        }
+        const uint64_t key = make_key(s, row);
+        if (take && key > st.taukey) {
+          __stcg(st.list + st.cnt, key);
+          st.cnt++;
+        }
+      }
+    }
+  }
+}
+
+// After a chunk was appended: compact every row of this warp whose list could overflow on the next
+// chunk (cnt > L - CH).  Warp-uniform control flow; `valid` rows only.
+template <int E, int CH, bool kL2>
+__device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int lane,
+                                                       uint32_t* __restrict__ tau_global_row) {
+  constexpr int L = 32 * E;
+  unsigned need = __ballot_sync(kFullMask, st.cnt > L - CH);
+  while (need) {
+    const int r = __ffs(need) - 1;
+    need &= need - 1;
+    uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
+    const int rc = __shfl_sync(kFullMask, st.cnt, r);
+    int nc; uint64_t nk;
+    __syncwarp();
+    compact_row<E>(rl, rc, k, k, lane, nc, nk);
+    if (lane == r) {
+      st.cnt = nc;
+      if (nk > st.taukey) {
+        st.taukey = nk;
+        st.tau = key_score(nk);
+        st.ftau = filter_tau<kL2>(st.tau);
+        if (tau_global_row) atomicMax(tau_global_row, (uint32_t)(nk >> 32));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// End of unit: leave the best KP keys (sorted, zero padded) in list[0..KP) of every row of the warp.
+template <int E, bool kL2>
+__device__ __forceinline__ void warp_finalize(RowState& st, int k, int kp, int lane,
+                                              uint32_t* __restrict__ tau_global_row, bool row_valid) {
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
+    const int rc = __shfl_sync(kFullMask, st.cnt, r);
+    const int rv = __shfl_sync(kFullMask, (int)row_valid, r);
+    if (!rv) continue;
+    int nc; uint64_t nk;
+    compact_row<E>(rl, rc, k, kp, lane, nc, nk);
+    if (lane == r) {
+      st.cnt = nc;
+      if (nk > st.taukey) {
+        st.taukey = nk;
+        st.tau = key_score(nk);
+        if (tau_global_row) atomicMax(tau_global_row, (uint32_t)(nk >> 32));
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Pull the shared threshold (other CTAs working on the same query row may have tightened it).
+template <bool kL2>
+__device__ __forceinline__ void refresh_tau(RowState& st, const uint32_t* __restrict__ tau_global_row) {
+  if (!tau_global_row) return;
+  uint32_t o = __ldcg(tau_global_row);
+  // The shared value is a SCORE bound only: any key with that score may still qualify, so the key
+  // form is (ord << 32) | 0 (the worst key of that score); only adopt it when strictly tighter.
+  if (o != 0u && ord2f(o) > st.tau) {
+    st.tau = ord2f(o);
+    st.ftau = filter_tau<kL2>(st.tau);
+    st.taukey = (uint64_t)o << 32;
+  }
+}
+
+}  // namespace knn

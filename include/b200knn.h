@@ -1,0 +1,164 @@
+/*
+ * b200knn.h -- C ABI of the B200-native exact k-NN retrieval + retrieval-metrics engine.
+ *
+ * This library replaces ONE hot path of CrispyChillies/Image-Retrieval---Thesis-2026:
+ *   L2-normalise -> cosine / inner-product / L2 distance -> top-k ranking -> retrieval metrics.
+ * The reference has no FFI for this path (it is inline torch/numpy); each entry point below cites the
+ * reference call it stands in for (paths relative to the reference repo root).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`
+ *   - return 0 on success, a negative KNN_E_* code otherwise; knn_last_error() gives a thread-local message
+ *   - no allocation / ownership transfer inside the library: the caller passes outputs and a workspace
+ *     sized by the matching *_workspace() query
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*), no hidden syncs
+ *   - no global mutable state except the thread-local error string
+ */
+#ifndef B200KNN_H_
+#define B200KNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KNN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define KNN_API __attribute__((visibility("default")))
+#else
+#define KNN_API
+#endif
+
+/* error codes */
+#define KNN_OK              0
+#define KNN_E_INVALID      -1   /* bad argument (shape, dtype, k, alignment) */
+#define KNN_E_WORKSPACE    -2   /* workspace too small / null */
+#define KNN_E_CUDA         -3   /* a CUDA runtime / driver call failed */
+#define KNN_E_UNSUPPORTED  -4   /* combination not implemented */
+
+/* element types */
+#define KNN_F32   0
+#define KNN_BF16  1
+
+/* metrics: score ordering is always "best first" in the outputs */
+#define KNN_COSINE 0   /* inner product of (already normalised) rows, larger = better (test.py:1006, train.py:405) */
+#define KNN_IP     1   /* inner product, larger = better (test.py:296 `embeds @ embeds.t()`)                         */
+#define KNN_L2     2   /* Euclidean distance sqrt(max(|q|^2+|g|^2-2q.g,0)), smaller = better (test_ath.py:87)         */
+
+/* eps modes of the three normalisation conventions on the path */
+#define KNN_EPS_CLAMP 0  /* x / max(||x||, eps)   F.normalize, test.py:1005, fusion_eval/fuse.py:11-15 */
+#define KNN_EPS_NONE  1  /* x / ||x||             test.py:251 (zero row -> NaN, reproduced)             */
+#define KNN_EPS_ADD   2  /* x / (||x|| + eps)     test.py:444                                           */
+#define KNN_CAST_ONLY 3  /* y = x (cast to out_dtype only; rows already normalised by the model, model.py:38) */
+
+/* self handling of self-retrieval (query i is gallery row self_offset+i) */
+#define KNN_SELF_KEEP    0
+#define KNN_SELF_EXCLUDE 1  /* fill_diagonal_(-inf): test.py:1081, train.py:406 -- the row never appears in top-k */
+#define KNN_SELF_MINUS1  2  /* fill_diagonal_(-1):   nih_multilabel_training.py:86 -- row kept with score -1        */
+
+KNN_API int         knn_version(void);
+KNN_API const char* knn_last_error(void);
+
+/* Row-wise L2 normalisation fused with the cast to the search dtype.
+ * Replaces F.normalize(x, p=2, dim=1) (test.py:1005; train.py:404,450; nih_multilabel_training.py:83;
+ * milvus/milvus_retrieval.py:63), `x / x.norm(dim=-1, keepdim=True)` (test.py:251) and l2_normalize
+ * (fusion_eval/fuse.py:11-15).  x: [n,d] in_dtype; y: [n,d] out_dtype (must not alias x);
+ * sqnorm (nullable): [n] fp32, squared norm of the OUTPUT row as stored (used by the L2 metric). */
+KNN_API int knn_normalize(const void* x, void* y, float* sqnorm, int64_t n, int d,
+                  int in_dtype, int out_dtype, float eps, int eps_mode, void* stream);
+
+/* Squared row norms of a stored matrix (fp32 accumulate): the |g|^2 term of torch.cdist's GEMM form. */
+KNN_API int knn_row_sqnorm(const void* x, float* sqnorm, int64_t n, int d, int dtype, void* stream);
+
+/* Fused distance + top-k.  Replaces `S = q @ g.T` / `-torch.cdist(q, g)` followed by
+ * `S.topk(k, 1, True, True)` (test.py:44,1080; train.py:405-409) / `torch.argsort(dist, dim=1)[:, :k]`
+ * (test_ath.py:100-114) / a Milvus FLAT `collection.search(limit=k)` (milvus/milvus_retrieval.py:80-86)
+ * without materialising the Q x N matrix.
+ *   q [nq,d], g [ng,d]: row-major, same dtype (KNN_F32 exact FFMA path, KNN_BF16 tcgen05 path)
+ *   q_sqnorm [nq], g_sqnorm [ng]: fp32 squared norms, required for KNN_L2, ignored otherwise
+ *   self_mode / self_offset: query i is gallery row (self_offset + i - index_base) of this shard
+ *   index_base: added to the local gallery row index in out_idx (row-sharded galleries)
+ *   out_val [nq,k] fp32: cosine/ip similarity (descending) or L2 distance (ascending)
+ *   out_idx [nq,k] int64: gallery row (+index_base); ties broken by ascending gallery row;
+ *                         if fewer than k candidates exist the tail is (-inf | +inf, -1)
+ */
+KNN_API int knn_search(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
+               int64_t nq, int64_t ng, int d, int dtype, int k, int metric,
+               int self_mode, int64_t self_offset, int64_t index_base,
+               float* out_val, int64_t* out_idx,
+               void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k);
+
+/* Dense score matrix (small problems only; compatibility with callers that want the full `dists`
+ * matrix of test.py:1080 / fusion_eval/metrics.py:15).  out [nq,ng] fp32, same score definition and
+ * self handling as knn_search (KNN_SELF_EXCLUDE writes -inf for similarity, +inf for L2). */
+KNN_API int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
+                     int64_t nq, int64_t ng, int d, int dtype, int metric,
+                     int self_mode, int64_t self_offset, float* out, void* stream);
+
+/* Full ranking of every row of a dense score matrix: stable order (score best-first, then ascending
+ * column).  Replaces torch.argsort(dists, dim=1, descending=True) (test.py:1018) and the column-wise
+ * variant of test.py:1090 when called on the transposed matrix.  scores [nq,ng] fp32; ranks [nq,ng] int64.
+ * largest_first=1 for similarities, 0 for distances. */
+KNN_API int    knn_rank_rows(const float* scores, int64_t nq, int64_t ng, int largest_first,
+                     int64_t* ranks, void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_rank_rows_workspace(int64_t nq, int64_t ng);
+
+/* k-way merge of `parts` per-shard candidate lists (after the all-gather of row-sharded search results).
+ * vals [parts,nq,k], idx [parts,nq,k] (global indices, -1 = empty) -> out [nq,k]; order as knn_search. */
+KNN_API int knn_merge_topk(const float* vals, const int64_t* idx, int parts, int64_t nq, int k, int metric,
+                   float* out_val, int64_t* out_idx, void* stream);
+
+/* Single-label relevance of retrieved lists: rel[i,j] = (glab[idx[i,j]] == qlab[i]), 0 for idx < 0.
+ * Building block of retrieval_accuracy (test.py:38-54), compute_metrics (test_ath.py:90-172),
+ * _compute_single_label_retrieval_metrics (train.py:399-441), fusion_eval/metrics.py:41-94. */
+KNN_API int knn_relevance_single(const int64_t* idx, int64_t nq, int k, const int64_t* qlab, const int64_t* glab,
+                         int64_t ng, uint8_t* rel, int64_t* retrieved_lab, void* stream);
+
+/* Multi-label relevance with labels packed to 64-bit masks: Jaccard (intersection / (union + 1e-8)) in
+ * the reference's own arithmetic -- arith 0: fp32 tensors, threshold rounded to fp32 (train.py:462-466,
+ * nih_multilabel_training.py:90-93, test.py:956-965); arith 1: Python doubles (evaluate_nih_zilliz.py:12-17)
+ * -- and the "shares >= 1 label" match of test.py:1045.  rel_jaccard / rel_any: [nq,k] uint8 (nullable). */
+KNN_API int knn_relevance_multilabel(const int64_t* idx, int64_t nq, int k, const uint64_t* qmask,
+                             const uint64_t* gmask, int64_t ng, double jaccard_thr, int arith,
+                             uint8_t* rel_jaccard, uint8_t* rel_any, void* stream);
+
+/* Per-query ranked-list statistics from a relevance matrix rel [nq,k] at cut-off kk <= k:
+ *   hits[i]      int32  number of relevant items in the first kk
+ *   first[i]     int32  1-based rank of the first relevant item (0 = none)
+ *   ap_topk[i]   f64    sum_{hits}(cum/rank) / hits             (test_ath.py:138-151; 0 when no hit)
+ *   prec_sum[i]  f64    sum_{hits}(cum/rank)  (caller divides by the relevant count: train.py:431-433,
+ *                       fusion_eval/metrics.py:78-83, test.py:974-981)
+ * All in IEEE double with the reference's operation order (no FMA contraction). */
+KNN_API int knn_ranked_stats(const uint8_t* rel, int64_t nq, int k, int kk,
+                     int32_t* hits, int32_t* first, double* ap_topk, double* prec_sum, void* stream);
+
+/* Majority vote over the first kk retrieved labels (lab [nq,k] int64).
+ * tie_mode 0: first label reaching the max count in rank order (collections.Counter.most_common,
+ *             test.py:149-161, test_ath.py:153);  tie_mode 1: smallest label (torch.mode train_ath.py:208,
+ *             np.unique+argmax evaluate_medsiglip.py:156-157). vote [nq] int64. */
+KNN_API int knn_majority_vote(const int64_t* lab, int64_t nq, int k, int kk, int tie_mode, int64_t* vote,
+                      void* stream);
+
+/* Trapezoidal AP of compute_ap/compute_map (test.py:58-146) from a full ranking.
+ * ranks [nq,ng] int64 row-major = for query i the gallery rows best-first (the reference passes the
+ * transposed [ng,nq] layout; the Python wrapper transposes).  Positives of query i are all j with
+ * glab[j] == qlab[i] (the query itself included when it is part of the gallery).
+ * ap [nq] f64, prs [nq,nkappa] f64 (precision at kappas, test.py:137-140), npos [nq] int32. */
+KNN_API int knn_map_full(const int64_t* ranks, int64_t nq, int64_t ng, const int64_t* qlab, const int64_t* glab,
+                 const int32_t* kappas, int nkappa, double* ap, double* prs, int32_t* npos, void* stream);
+
+/* sklearn.metrics.average_precision_score over a ranked list (scores descending, tied scores grouped;
+ * evaluate_nih_zilliz.py:50, train.py:473-475, nih_multilabel_training.py:95).  val [nq,k] fp32 scores
+ * (best first), rel [nq,k]; ap [nq] f64 (NaN when the list has no relevant item). */
+KNN_API int    knn_ap_sklearn(const float* val, const uint8_t* rel, int64_t nq, int k, double* ap,
+                      void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_ap_sklearn_workspace(int64_t nq, int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KNN_H_ */
