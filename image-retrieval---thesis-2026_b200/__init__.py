@@ -1,0 +1,15 @@
+"""b200knn: B200-native exact k-NN retrieval + retrieval metrics.
+
+Drop-in for the query x gallery similarity-search hot path of CrispyChillies/Image-Retrieval---Thesis-2026
+(L2-normalise -> cosine / L2 -> top-k -> R@K / P@K / mAP / multilabel hit-rate).  The package directory is
+``image-retrieval---thesis-2026_b200/``; it is importable as ``b200knn`` through the shim next to it.
+"""
+from ._lib import KnnError, LIB_PATH, load as load_library
+from .search import FlatIndex, merge_topk, normalize, rank_rows, row_sqnorm, scores_dense, search
+from . import metrics
+from .sharded import ShardedFlatIndex
+
+__all__ = [
+    "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
+    "rank_rows", "row_sqnorm", "scores_dense", "search", "metrics",
+]

@@ -1,0 +1,78 @@
+"""ctypes binding of libb200knn.so (the C ABI declared in include/b200knn.h).
+
+There is deliberately NO fallback: if the shared library is missing or a kernel call fails, the caller
+gets an exception.  Nothing in this package computes a distance, a ranking or a metric in torch/numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200knn.so")
+
+# constants mirrored from include/b200knn.h
+KNN_F32, KNN_BF16 = 0, 1
+KNN_COSINE, KNN_IP, KNN_L2 = 0, 1, 2
+KNN_EPS_CLAMP, KNN_EPS_NONE, KNN_EPS_ADD, KNN_CAST_ONLY = 0, 1, 2, 3
+KNN_SELF_KEEP, KNN_SELF_EXCLUDE, KNN_SELF_MINUS1 = 0, 1, 2
+MAX_FUSED_K = 256
+
+_p, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
+
+# name -> (restype, argtypes); every symbol include/b200knn.h declares (tests/test_abi.py checks the two agree)
+SIGNATURES = {
+    "knn_version": (_i, []),
+    "knn_last_error": (C.c_char_p, []),
+    "knn_normalize": (_i, [_p, _p, _p, _i64, _i, _i, _i, _f, _i, _p]),
+    "knn_row_sqnorm": (_i, [_p, _p, _i64, _i, _i, _p]),
+    "knn_search": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "knn_search_workspace": (_sz, [_i64, _i64, _i, _i, _i]),
+    "knn_scores_dense": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p]),
+    "knn_rank_rows": (_i, [_p, _i64, _i64, _i, _p, _p, _sz, _p]),
+    "knn_rank_rows_workspace": (_sz, [_i64, _i64]),
+    "knn_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
+    "knn_relevance_single": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
+    "knn_relevance_multilabel": (_i, [_p, _i64, _i, _p, _p, _i64, _d, _i, _p, _p, _p]),
+    "knn_ranked_stats": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
+    "knn_majority_vote": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
+    "knn_map_full": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "knn_ap_sklearn": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
+    "knn_ap_sklearn_workspace": (_sz, [_i64, _i]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class KnnError(RuntimeError):
+    """A b200knn C-ABI call returned a negative status."""
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise KnnError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                "(nvcc, sm_100a). b200knn has no CPU / torch fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().knn_last_error()
+        raise KnnError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

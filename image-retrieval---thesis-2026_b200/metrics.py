@@ -1,0 +1,433 @@
+"""Retrieval metrics with the reference's names, signatures and return types, computed on the GPU.
+
+Per-query work (label gather, relevance, hit counts, AP, majority vote, trapezoidal AP over a full ranking)
+runs in the kernels of csrc/metrics.cu with the reference's own operation order in IEEE double; the Python
+layer only shapes results into the reference's dicts and takes the final mean over the per-query array the
+way the reference does (``np.mean`` / a sequential Python ``+=``), which keeps those numbers bit-identical.
+
+Two entry styles per metric family:
+  * the reference signature (dense ``dists`` / ``ranks`` matrices) for small problems, and
+  * an embeddings-in / top-k-in variant that never materialises N x N.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .search import _ptr, _require_cuda, _stream, rank_rows, search
+
+_NAN = float("nan")
+
+
+# --------------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI
+# --------------------------------------------------------------------------------------------------
+def _dev_i64(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int64).contiguous()
+    return torch.as_tensor(np.asarray(x), dtype=torch.int64, device=device).contiguous()
+
+
+def relevance_single(indices: torch.Tensor, qlabels, glabels) -> Tuple[torch.Tensor, torch.Tensor]:
+    """rel[i,j] = glabels[indices[i,j]] == qlabels[i]  and the retrieved labels.  -> (uint8 [Q,k], int64 [Q,k])"""
+    _require_cuda(indices)
+    idx = indices.contiguous().long()
+    nq, k = idx.shape
+    ql, gl = _dev_i64(qlabels, idx.device).view(-1), _dev_i64(glabels, idx.device).view(-1)
+    rel = torch.empty((nq, k), dtype=torch.uint8, device=idx.device)
+    lab = torch.empty((nq, k), dtype=torch.int64, device=idx.device)
+    with torch.cuda.device(idx.device):
+        rc = L.load().knn_relevance_single(_ptr(idx), nq, k, _ptr(ql), _ptr(gl), gl.numel(), _ptr(rel), _ptr(lab),
+                                           _stream(idx))
+    L.check(rc, "knn_relevance_single")
+    return rel, lab
+
+
+def pack_multihot(labels: torch.Tensor) -> torch.Tensor:
+    """[N,C] multi-hot (C <= 64) -> int64 bitmask per row (bit c set iff labels[:,c] != 0)."""
+    if labels.dim() != 2 or labels.shape[1] > 64:
+        raise ValueError("multi-hot labels must be [N, C] with C <= 64")
+    bits = (labels != 0).to(torch.int64)
+    weights = (torch.ones((), dtype=torch.int64, device=labels.device) << torch.arange(labels.shape[1],
+                                                                                   device=labels.device))
+    return (bits * weights).sum(dim=1)
+
+
+def relevance_multilabel(indices: torch.Tensor, qmask: torch.Tensor, gmask: torch.Tensor, jaccard_threshold: float,
+                         arith: str = "fp32") -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (rel_jaccard uint8 [Q,k], rel_any uint8 [Q,k]); arith 'fp32' = torch/numpy fp32 tensors
+    (train.py:462-466), 'fp64' = Python floats (evaluate_nih_zilliz.py:12-17)."""
+    _require_cuda(indices)
+    idx = indices.contiguous().long()
+    nq, k = idx.shape
+    qm, gm = _dev_i64(qmask, idx.device), _dev_i64(gmask, idx.device)
+    rj = torch.empty((nq, k), dtype=torch.uint8, device=idx.device)
+    ra = torch.empty((nq, k), dtype=torch.uint8, device=idx.device)
+    with torch.cuda.device(idx.device):
+        rc = L.load().knn_relevance_multilabel(_ptr(idx), nq, k, _ptr(qm), _ptr(gm), gm.numel(),
+                                               float(jaccard_threshold), 0 if arith == "fp32" else 1, _ptr(rj),
+                                               _ptr(ra), _stream(idx))
+    L.check(rc, "knn_relevance_multilabel")
+    return rj, ra
+
+
+def ranked_stats(rel: torch.Tensor, kk: Optional[int] = None):
+    """-> (hits int32 [Q], first int32 [Q] (1-based, 0 = none), ap_topk f64 [Q], prec_sum f64 [Q]) at cut-off kk."""
+    _require_cuda(rel)
+    rel = rel.contiguous()
+    nq, k = rel.shape
+    kk = k if kk is None else min(int(kk), k)
+    dev = rel.device
+    hits = torch.empty((nq,), dtype=torch.int32, device=dev)
+    first = torch.empty((nq,), dtype=torch.int32, device=dev)
+    ap = torch.empty((nq,), dtype=torch.float64, device=dev)
+    ps = torch.empty((nq,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().knn_ranked_stats(_ptr(rel), nq, k, kk, _ptr(hits), _ptr(first), _ptr(ap), _ptr(ps), _stream(rel))
+    L.check(rc, "knn_ranked_stats")
+    return hits, first, ap, ps
+
+
+def majority_vote_labels(retrieved_labels: torch.Tensor, kk: int, tie: str = "first") -> torch.Tensor:
+    """Majority label of the first kk retrieved labels.  tie='first': collections.Counter.most_common
+    (test.py:149-161); tie='smallest': torch.mode / np.unique+argmax (train_ath.py:208)."""
+    _require_cuda(retrieved_labels)
+    lab = retrieved_labels.contiguous().long()
+    nq, k = lab.shape
+    vote = torch.empty((nq,), dtype=torch.int64, device=lab.device)
+    with torch.cuda.device(lab.device):
+        rc = L.load().knn_majority_vote(_ptr(lab), nq, k, min(int(kk), k), 0 if tie == "first" else 1, _ptr(vote),
+                                        _stream(lab))
+    L.check(rc, "knn_majority_vote")
+    return vote
+
+
+def ap_sklearn(vals: torch.Tensor, rel: torch.Tensor) -> torch.Tensor:
+    """sklearn.metrics.average_precision_score per ranked list (tied scores grouped).  NaN = no relevant item."""
+    _require_cuda(vals, rel)
+    vals, rel = vals.contiguous().float(), rel.contiguous()
+    nq, k = vals.shape
+    ap = torch.empty((nq,), dtype=torch.float64, device=vals.device)
+    lib = L.load()
+    with torch.cuda.device(vals.device):
+        nbytes = lib.knn_ap_sklearn_workspace(nq, k)
+        ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=vals.device)
+        rc = lib.knn_ap_sklearn(_ptr(vals), _ptr(rel), nq, k, _ptr(ap), _ptr(ws), ws.numel(), _stream(vals))
+    L.check(rc, "knn_ap_sklearn")
+    return ap
+
+
+def _seq_sum(x: np.ndarray, axis=None):
+    """Left-to-right float64 accumulation: what a Python ``acc = acc + v`` loop does (test.py:134,141)."""
+    if x.size == 0:
+        return 0.0 if axis is None else np.zeros(x.shape[1:])
+    return np.add.accumulate(x, axis=0 if axis is None else axis)[-1]
+
+
+# --------------------------------------------------------------------------------------------------
+# D1  retrieval_accuracy  (test.py:38-54; train.py:560; test_nonclip.py:31; eval_medsiglip.py:16)
+# --------------------------------------------------------------------------------------------------
+def recall_at_k_from_topk(indices: torch.Tensor, qlabels, glabels, topk: Sequence[int] = (1,)) -> List[torch.Tensor]:
+    """R@K from retrieved indices [Q, >=max(topk)]: list of 0-d fp32 tensors, 100 * mean[any label match in top-k]."""
+    rel, _ = relevance_single(indices, qlabels, glabels)
+    _, first, _, _ = ranked_stats(rel)
+    nq = rel.shape[0]
+    res = []
+    for k in topk:
+        correct_k = ((first > 0) & (first <= int(k))).sum(dtype=torch.float32)
+        res.append((correct_k * (100.0 / nq)).cpu())
+    return res
+
+
+def retrieval_accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)) -> List[torch.Tensor]:
+    """Reference signature: ``output`` is the dense [N,N] score matrix (larger = more similar, diagonal already
+    masked), ``target`` the labels.  Row-wise top-maxk with ties broken by ascending column."""
+    _require_cuda(output)
+    maxk = max(topk)
+    pred = rank_rows(output, largest_first=True)[:, :maxk].contiguous()
+    return recall_at_k_from_topk(pred, target, target, topk)
+
+
+# --------------------------------------------------------------------------------------------------
+# D2  compute_ap / compute_map  (test.py:58-146)
+# --------------------------------------------------------------------------------------------------
+def map_full(ranks_rowmajor: torch.Tensor, qlabels, glabels, kappas: Sequence[int] = ()):
+    """Per-query trapezoidal AP + precision@kappas from a full ranking [Q, N] (best first).
+    -> (ap f64 [Q], prs f64 [Q, len(kappas)], npos int32 [Q]) on the device."""
+    _require_cuda(ranks_rowmajor)
+    rk = ranks_rowmajor.contiguous().long()
+    nq, ng = rk.shape
+    dev = rk.device
+    ql, gl = _dev_i64(qlabels, dev).view(-1), _dev_i64(glabels, dev).view(-1)
+    kap = torch.as_tensor(list(kappas), dtype=torch.int32, device=dev)
+    ap = torch.empty((nq,), dtype=torch.float64, device=dev)
+    prs = torch.empty((nq, max(len(kappas), 1)), dtype=torch.float64, device=dev)
+    npos = torch.empty((nq,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().knn_map_full(_ptr(rk), nq, ng, _ptr(ql), _ptr(gl), _ptr(kap), len(kappas), _ptr(ap), _ptr(prs),
+                                   _ptr(npos), _stream(rk))
+    L.check(rc, "knn_map_full")
+    return ap, prs[:, : len(kappas)], npos
+
+
+def compute_map(ranks, gnd, kappas=[]):
+    """Reference signature (test.py:95): ``ranks`` is [db_size, nq] (column i = ranking of query i, best first),
+    ``gnd`` the labels.  -> (mAP, aps [nq], pr [len(kappas)], prs [nq, len(kappas)]) as float64 numpy."""
+    dev = ranks.device if isinstance(ranks, torch.Tensor) and ranks.is_cuda else torch.device("cuda")
+    rk = torch.as_tensor(ranks, device=dev).t().contiguous()
+    gl = _dev_i64(gnd, dev)
+    ap, prs, npos = map_full(rk, gl, gl, kappas)
+    aps = ap.cpu().numpy()
+    prs_np = prs.cpu().numpy().reshape(len(aps), len(kappas))
+    valid = npos.cpu().numpy() > 0
+    nq, nempty = len(aps), int((~valid).sum())
+    mAP = _seq_sum(aps[valid]) / (nq - nempty)
+    pr = _seq_sum(prs_np[valid], axis=0) / (nq - nempty) if len(kappas) else np.zeros(0)
+    return float(mAP), aps, np.asarray(pr, dtype=np.float64), prs_np
+
+
+# --------------------------------------------------------------------------------------------------
+# D3  compute_classification_metrics  (test.py:149-223)
+# --------------------------------------------------------------------------------------------------
+def _prf_from_predictions(true: np.ndarray, pred: np.ndarray) -> Dict[str, float]:
+    """macro / weighted precision, recall, F1 (zero_division=0) and accuracy from the confusion counts, with
+    sklearn's formulas (precision_recall_fscore_support): host math on a C x C matrix."""
+    labels = np.unique(np.concatenate([true, pred]))
+    tp = np.array([np.sum((true == c) & (pred == c)) for c in labels], dtype=np.float64)
+    pred_sum = np.array([np.sum(pred == c) for c in labels], dtype=np.float64)
+    true_sum = np.array([np.sum(true == c) for c in labels], dtype=np.float64)
+
+    def div(a, b):
+        out = np.zeros_like(a)
+        np.divide(a, b, out=out, where=b != 0)
+        return out
+
+    precision, recall = div(tp, pred_sum), div(tp, true_sum)
+    f1 = div(2.0 * tp, true_sum + pred_sum)
+    w = true_sum
+
+    def avg(x, weights=None):
+        return float(np.average(x, weights=weights))
+
+    return {
+        "precision_macro": avg(precision) * 100.0, "recall_macro": avg(recall) * 100.0, "f1_macro": avg(f1) * 100.0,
+        "precision_weighted": avg(precision, w) * 100.0, "recall_weighted": avg(recall, w) * 100.0,
+        "f1_weighted": avg(f1, w) * 100.0,
+        "accuracy": float(np.mean(true == pred)) * 100.0,
+    }
+
+
+def classification_metrics_from_topk(indices: torch.Tensor, qlabels, glabels, k_values=(1, 5, 10, 15, 20),
+                                     tie: str = "first") -> Dict[int, Dict[str, float]]:
+    _, lab = relevance_single(indices, qlabels, glabels)
+    true = _dev_i64(qlabels, indices.device).view(-1).cpu().numpy()
+    out = {}
+    for k in k_values:
+        pred = majority_vote_labels(lab, k, tie).cpu().numpy()
+        out[k] = _prf_from_predictions(true, pred)
+    return out
+
+
+def compute_classification_metrics(labels: torch.Tensor, dists: torch.Tensor, k_values=[1, 5, 10, 15, 20]):
+    """Reference signature (test.py:164): dense ``dists`` (higher = more similar); ranks COLUMNS
+    (``argsort(dists, dim=0)``), ties by ascending row."""
+    _require_cuda(dists)
+    ranks = rank_rows(dists.t().contiguous(), largest_first=True)[:, : max(k_values)].contiguous()
+    return classification_metrics_from_topk(ranks, labels, labels, k_values)
+
+
+# --------------------------------------------------------------------------------------------------
+# D10 compute_metrics  (test_ath.py:90-172): true query x gallery retrieval
+# --------------------------------------------------------------------------------------------------
+def compute_metrics(query_codes, query_labels, gallery_codes, gallery_labels, query_logits=None,
+                    topk_values=(1, 5, 10), binary_codes: bool = False, precision: str = "fp32"):
+    """mHR, mAP@k, mRR, mP@k, R@k and majority-vote accuracy per cut-off, L2 ranking (ascending distance)."""
+    if binary_codes:
+        raise L.KnnError("Hamming ranking is a 'next' row (SURVEY 8(f).4); use L2 codes")
+    _require_cuda(query_codes, gallery_codes)
+    kmax = max(topk_values)
+    _, idx = search(query_codes.float(), gallery_codes.float(), kmax, "l2", precision=precision)
+    dev = idx.device
+    ql, gl = _dev_i64(query_labels, dev).view(-1), _dev_i64(gallery_labels, dev).view(-1)
+    rel, lab = relevance_single(idx, ql, gl)
+    # total relevant items per query (integer counting, exact)
+    uniq, counts = torch.unique(gl, return_counts=True)
+    pos = torch.searchsorted(uniq, ql).clamp(max=uniq.numel() - 1)
+    total_rel = torch.where(uniq[pos] == ql, counts[pos], torch.zeros_like(counts[pos])).cpu().numpy()
+    retrieval = {}
+    for topk in topk_values:
+        hits, first, ap, _ = ranked_stats(rel, topk)
+        hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
+        vote = majority_vote_labels(lab, topk, "first")
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rr = np.where(first_np > 0, 1.0 / np.maximum(first_np, 1), 0.0)
+            rec = np.where(total_rel > 0, hits_np / np.maximum(total_rel, 1), 0.0)
+        retrieval[topk] = {
+            "mhr": float(np.mean((hits_np > 0).astype(np.float64))),
+            "map": float(np.mean(ap.cpu().numpy())),
+            "mrr": float(np.mean(rr)),
+            "mp@k": float(np.mean(hits_np / topk)),
+            "r@k": float(np.mean(rec)),
+            "majority_acc": float(np.mean((vote == ql).cpu().numpy().astype(np.float64))),
+        }
+    classification_acc = None
+    if query_logits is not None:
+        classification_acc = query_logits.argmax(dim=1).eq(ql.to(query_logits.device)).float().mean().item()
+    return {"classification_acc": classification_acc, "retrieval": retrieval}
+
+
+# --------------------------------------------------------------------------------------------------
+# D9  evaluate_results  (evaluate_nih_zilliz.py:34-64) over top-k hit lists, and D5 hit-rate (test.py:1016-1056)
+# --------------------------------------------------------------------------------------------------
+def evaluate_results_from_topk(vals: torch.Tensor, indices: torch.Tensor, qlabels_multihot: torch.Tensor,
+                               glabels_multihot: torch.Tensor, jaccard_threshold: float = 0.4,
+                               ks: Iterable[int] = (1, 5, 10, 20, 50)) -> Dict[str, float]:
+    """``evaluate_results`` on device-resident top-k lists instead of the JSON hit lists."""
+    qm, gm = pack_multihot(qlabels_multihot), pack_multihot(glabels_multihot)
+    rel, _ = relevance_multilabel(indices, qm, gm, jaccard_threshold, arith="fp64")
+    nhits = rel.shape[1]
+    total_pos, _, _, _ = ranked_stats(rel)
+    total_np = total_pos.cpu().numpy().astype(np.int64)
+    ap = ap_sklearn(vals, rel).cpu().numpy()
+    aps = ap[total_np > 0]
+    metrics = {
+        "mAP": float(np.mean(aps) * 100.0) if len(aps) else 0.0,
+        "num_queries": float(rel.shape[0]),
+        "num_valid_ap_queries": float(len(aps)),
+    }
+    for k in ks:
+        kk = min(int(k), nhits)
+        hk = ranked_stats(rel, kk)[0].cpu().numpy().astype(np.float64)
+        # precision_at_k = float(np.mean(relevances[:k])) over float64 0/1 entries: sum is exact, one division
+        p = hk / kk
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = np.where(total_np > 0, hk / np.maximum(total_np, 1), 0.0)
+        metrics[f"P@{k}"] = float(np.mean(p) * 100.0) if len(p) else 0.0
+        metrics[f"R@{k}"] = float(np.mean(r) * 100.0) if len(r) else 0.0
+    return metrics
+
+
+def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch.Tensor,
+                                  glabels_multihot: torch.Tensor, k_values=(1, 5, 10, 15, 20)):
+    """Precision@K (share of the top-K sharing >= 1 label with the query) and Recall@K = hit-rate
+    (test.py:1031-1056).  -> {k: (precision_percent, recall_percent)}"""
+    qm, gm = pack_multihot(qlabels_multihot), pack_multihot(glabels_multihot)
+    _, rel_any = relevance_multilabel(indices, qm, gm, 0.0)
+    nq = rel_any.shape[0]
+    out = {}
+    for k in k_values:
+        hk = ranked_stats(rel_any, k)[0].cpu().numpy()
+        total_precision = _seq_sum(hk.astype(np.float64) / k)   # total_precision += num_matches / k
+        total_recall = int((hk > 0).sum())
+        out[k] = (float(total_precision / nq * 100), float(total_recall / nq * 100))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# D6 / D11 / D13: embeddings-in single-label evaluation (train.py:399-441; fusion_eval/metrics.py:41-94)
+# --------------------------------------------------------------------------------------------------
+def _self_retrieval_full(embeds: torch.Tensor, metric: str = "cosine", normalize: bool = True):
+    n = embeds.shape[0]
+    return search(embeds, embeds, n - 1, metric, normalize=normalize, exclude_self=True)
+
+
+def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10)):
+    """train.py:399-441: cosine self-retrieval, standard AP over the full ranking / (#same-label - 1), R@K."""
+    if len(labels) <= 1:
+        return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
+    _require_cuda(embeds)
+    labels = _dev_i64(labels, embeds.device).view(-1)
+    _, idx = _self_retrieval_full(embeds)
+    rel, _ = relevance_single(idx, labels, labels)
+    hits, first, _, prec_sum = ranked_stats(rel)
+    hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
+    aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)   # relevant_counts == hits over the full ranking
+    metrics = {"mAP": float(np.mean(aps) * 100.0)}
+    first_np = first.cpu().numpy()
+    for k in topk:
+        actual_k = min(k, rel.shape[1])
+        metrics[f"R@{k}"] = float(np.mean(((first_np > 0) & (first_np <= actual_k)).astype(np.float32))) * 100.0
+    return metrics
+
+
+def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Optional[Sequence] = None,
+                               k_values: Iterable[int] = (1, 5, 10)) -> Dict[str, float]:
+    """fusion_eval/metrics.py:26-94 (labels may be strings; image paths are assumed unique, as the reference's
+    aligned embedding sets are)."""
+    emb = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not isinstance(embeddings, torch.Tensor) \
+        else embeddings
+    emb = emb.cuda() if not emb.is_cuda else emb
+    _, inv = np.unique(np.asarray(labels), return_inverse=True)
+    lab = torch.as_tensor(inv, dtype=torch.int64, device=emb.device)
+    k_values = sorted(set(int(k) for k in k_values))
+    _, idx = _self_retrieval_full(emb)
+    rel, _ = relevance_single(idx, lab, lab)
+    hits, _, _, prec_sum = ranked_stats(rel)
+    hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
+    aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)
+    metrics: Dict[str, float] = {"num_samples": float(len(inv)), "mAP": float(np.mean(aps) * 100.0)}
+    for k in k_values:
+        hk = ranked_stats(rel, k)[0].cpu().numpy()
+        hk = np.where(hits_np > 0, hk, 0)
+        metrics[f"mP@{k}"] = float(np.mean(hk / k) * 100.0)
+        metrics[f"R@{k}"] = float(np.mean((hk > 0).astype(np.float64)) * 100.0)
+    return metrics
+
+
+def is_retrieval_correct(query_label, retrieved_labels: Sequence, top_k: int = 1) -> bool:
+    """retrieval_analysis/evaluator.py:18-26: any label equality among the first ``top_k`` hits."""
+    return any(lbl == query_label for lbl in list(retrieved_labels)[:top_k])
+
+
+# --------------------------------------------------------------------------------------------------
+# D4 / D7 / D8: multilabel AP over the full ranking
+# --------------------------------------------------------------------------------------------------
+def compute_map_multilabel_from_embeddings(embeds: torch.Tensor, labels_multihot: torch.Tensor,
+                                           threshold: float = 0.5) -> float:
+    """test.py:941-985 on cosine self-retrieval: rank-by-rank AP, relevance = Jaccard > threshold, self removed,
+    queries without relevant items skipped."""
+    _require_cuda(embeds)
+    m = pack_multihot(labels_multihot.to(embeds.device))
+    _, idx = _self_retrieval_full(embeds)
+    rel, _ = relevance_multilabel(idx, m, m, threshold, arith="fp32")
+    hits, _, ap, _ = ranked_stats(rel)
+    hits_np = hits.cpu().numpy()
+    aps = ap.cpu().numpy()[hits_np > 0]
+    return float(np.mean(aps)) if len(aps) else 0
+
+
+def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10),
+                                          relevance_threshold: float = 0.4):
+    """train.py:444-487: sklearn AP (tied scores grouped) with self masked out, R@K = any relevant in top-k."""
+    if len(labels) <= 1:
+        return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
+    _require_cuda(embeds)
+    m = pack_multihot(labels.to(embeds.device))
+    vals, idx = _self_retrieval_full(embeds)
+    rel, _ = relevance_multilabel(idx, m, m, relevance_threshold, arith="fp32")
+    hits, first, _, _ = ranked_stats(rel)
+    hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
+    aps = ap_sklearn(vals, rel).cpu().numpy()[hits_np > 0]
+    metrics = {"mAP": float(np.mean(aps) * 100.0) if len(aps) > 0 else 0.0}
+    for k in topk:
+        actual_k = min(k, rel.shape[1])
+        metrics[f"R@{k}"] = float(np.mean(((first_np > 0) & (first_np <= actual_k)).astype(np.float64)) * 100.0)
+    return metrics
+
+
+def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jaccard_threshold: float = 0.4) -> float:
+    """nih_multilabel_training.py:66-99 on given embeddings: self is KEPT with similarity -1 and counts as a
+    relevant item (J(self, self) = 1 > threshold) ranked wherever -1 falls."""
+    _require_cuda(embeddings)
+    n = embeddings.shape[0]
+    m = pack_multihot(labels.to(embeddings.device))
+    vals, idx = search(embeddings, embeddings, n, "cosine", normalize=True, self_mode="minus1")
+    rel, _ = relevance_multilabel(idx, m, m, jaccard_threshold, arith="fp32")
+    hits = ranked_stats(rel)[0].cpu().numpy()
+    aps = ap_sklearn(vals, rel).cpu().numpy()[hits > 0]
+    if len(aps) == 0:
+        return 0.0
+    return float(np.mean(aps) * 100.0)

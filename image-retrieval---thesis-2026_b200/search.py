@@ -1,0 +1,324 @@
+"""Exact k-NN search on B200: the host-side mirror of the reference's retrieval calls.
+
+Call shapes follow what the reference's scripts consume:
+
+* ``values, indices = S.topk(k, dim=1, largest=True, sorted=True)`` on ``S = q @ g.T`` / ``-cdist(q, g)``
+  (test.py:44,1080; train.py:405-409; xai_conceptclip.py:468) -> :func:`search`
+* ``scores, neighbors = index.search(xq, k)`` after ``index.add(xb)`` (ATH.py:403-410) -> :class:`FlatIndex`
+* ``F.normalize(x, p=2, dim=1)`` (test.py:1005) / ``x / x.norm(dim=-1, keepdim=True)`` (test.py:251) /
+  ``l2_normalize`` (fusion_eval/fuse.py:11-15) -> :func:`normalize`
+* ``torch.argsort(dists, dim=1, descending=True)`` (test.py:1018) -> :func:`rank_rows`
+
+Everything runs in the CUDA library behind include/b200knn.h; torch only owns the device buffers.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+_METRICS = {"cosine": L.KNN_COSINE, "ip": L.KNN_IP, "l2": L.KNN_L2}
+_EPS_MODES = {"clamp": L.KNN_EPS_CLAMP, "none": L.KNN_EPS_NONE, "add": L.KNN_EPS_ADD, "cast": L.KNN_CAST_ONLY}
+_SELF = {"keep": L.KNN_SELF_KEEP, "exclude": L.KNN_SELF_EXCLUDE, "minus1": L.KNN_SELF_MINUS1}
+_DT = {torch.float32: L.KNN_F32, torch.bfloat16: L.KNN_BF16}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise L.KnnError("b200knn operates on CUDA tensors only (there is no CPU fallback)")
+
+
+def _as2d(x: torch.Tensor, name: str) -> torch.Tensor:
+    if x.dim() != 2:
+        raise ValueError(f"{name} must be [rows, dim], got {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def normalize(
+    x: torch.Tensor,
+    *,
+    eps: float = 1e-12,
+    eps_mode: str = "clamp",
+    out_dtype: Optional[torch.dtype] = None,
+    return_sqnorm: bool = False,
+):
+    """Row-wise L2 normalisation fused with the cast to the search dtype.
+
+    eps_mode: "clamp" = F.normalize (x / max(||x||, eps)); "none" = x / ||x|| (test.py:251);
+    "add" = x / (||x|| + eps) (test.py:444); "cast" = no normalisation, cast only.
+    """
+    _require_cuda(x)
+    x = _as2d(x, "x")
+    if x.dtype not in _DT:
+        x = x.float()
+    out_dtype = out_dtype or x.dtype
+    if out_dtype not in _DT:
+        raise ValueError(f"unsupported out_dtype {out_dtype}")
+    n, d = x.shape
+    y = torch.empty((n, d), dtype=out_dtype, device=x.device)
+    sq = torch.empty((n,), dtype=torch.float32, device=x.device) if return_sqnorm else None
+    with torch.cuda.device(x.device):
+        rc = L.load().knn_normalize(_ptr(x), _ptr(y), _ptr(sq), n, d, _DT[x.dtype], _DT[out_dtype], float(eps),
+                                    _EPS_MODES[eps_mode], _stream(x))
+    L.check(rc, "knn_normalize")
+    return (y, sq) if return_sqnorm else y
+
+
+def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
+    """fp32 squared L2 norm of every stored row (the |g|^2 term of cdist's GEMM form)."""
+    _require_cuda(x)
+    x = _as2d(x, "x")
+    sq = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.load().knn_row_sqnorm(_ptr(x), _ptr(sq), x.shape[0], x.shape[1], _DT[x.dtype], _stream(x))
+    L.check(rc, "knn_row_sqnorm")
+    return sq
+
+
+def _pad_dim(x: torch.Tensor, mult: int) -> torch.Tensor:
+    d = x.shape[1]
+    if d % mult == 0:
+        return x
+    pad = mult - d % mult
+    out = x.new_zeros((x.shape[0], d + pad))  # zero columns change no dot product and no norm
+    out[:, :d] = x
+    return out
+
+
+def _prepare(x: torch.Tensor, do_norm: bool, precision: str, eps: float, eps_mode: str, want_sq: bool):
+    """-> (rows in the search dtype, squared norms or None)."""
+    tgt = torch.bfloat16 if precision == "bf16" else torch.float32
+    x = _as2d(x, "embeddings")
+    if x.dtype not in _DT:
+        x = x.float()
+    if precision == "bf16":
+        x = _pad_dim(x, 8)
+    if do_norm:
+        if want_sq:
+            return normalize(x, eps=eps, eps_mode=eps_mode, out_dtype=tgt, return_sqnorm=True)
+        return normalize(x, eps=eps, eps_mode=eps_mode, out_dtype=tgt), None
+    if x.dtype != tgt:
+        x = normalize(x, eps_mode="cast", out_dtype=tgt)
+    return x, (row_sqnorm(x) if want_sq else None)
+
+
+class FlatIndex:
+    """Device-resident exact (FLAT) gallery: the drop-in for ``faiss.IndexFlatL2`` + ``add`` (ATH.py:401-403)
+    and for a Milvus FLAT collection (ChestMIR/milvus_embed.py:538-539).
+
+    Rows are stored once in the search dtype (fp32 exact mode or bf16 tensor-core mode), optionally
+    L2-normalised by the fused normalise+cast kernel, with their squared norms for the L2 metric.
+    ``index_base`` is the global row of local row 0 (row-sharded galleries).
+    """
+
+    def __init__(self, dim: int, metric: str = "cosine", precision: str = "fp32", *, normalize: bool = False,
+                 eps: float = 1e-12, eps_mode: str = "clamp", index_base: int = 0,
+                 device: Optional[torch.device] = None):
+        if metric not in _METRICS:
+            raise ValueError(f"metric must be one of {sorted(_METRICS)}")
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.dim, self.metric, self.precision = int(dim), metric, precision
+        self.normalize, self.eps, self.eps_mode = bool(normalize), float(eps), eps_mode
+        self.index_base = int(index_base)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.rows: Optional[torch.Tensor] = None
+        self.sqnorm: Optional[torch.Tensor] = None
+
+    @property
+    def ntotal(self) -> int:
+        return 0 if self.rows is None else int(self.rows.shape[0])
+
+    def add(self, x: torch.Tensor) -> "FlatIndex":
+        """Append rows (``index.add(xb)``, ATH.py:403; ``collection.insert``, nih_zilliz_utils.py:244-251)."""
+        _require_cuda(x)
+        if x.shape[1] != self.dim:
+            raise ValueError(f"expected dim {self.dim}, got {x.shape[1]}")
+        rows, sq = _prepare(x.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
+                            self.metric == "l2")
+        self.rows = rows if self.rows is None else torch.cat([self.rows, rows], 0)
+        if sq is not None:
+            self.sqnorm = sq if self.sqnorm is None else torch.cat([self.sqnorm, sq], 0)
+        return self
+
+    def adopt(self, rows: torch.Tensor, sqnorm: Optional[torch.Tensor] = None) -> "FlatIndex":
+        """Take ownership of rows that are ALREADY in the search dtype/layout (no copy)."""
+        _require_cuda(rows)
+        want = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        if rows.dtype != want or not rows.is_contiguous():
+            raise ValueError("adopt() needs contiguous rows already in the search dtype")
+        self.rows = rows
+        self.sqnorm = sqnorm if sqnorm is not None else (row_sqnorm(rows) if self.metric == "l2" else None)
+        return self
+
+    def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
+               query_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``scores, neighbors = index.search(xq, k)`` (ATH.py:410) -> (distances [Q,k] fp32, indices [Q,k] int64).
+
+        query_offset: global gallery row of query 0 (self-retrieval over a chunk of the gallery).
+        """
+        if self.rows is None:
+            raise L.KnnError("FlatIndex is empty")
+        _require_cuda(queries)
+        q, qsq = _prepare(queries.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
+                          self.metric == "l2")
+        mode = self_mode or ("exclude" if exclude_self else "keep")
+        return _search_prepared(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
+                                self.index_base)
+
+
+def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base):
+    nq, d = q.shape
+    ng = g.shape[0]
+    if g.shape[1] != d or g.dtype != q.dtype:
+        raise ValueError("queries and gallery must share dim and dtype")
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    dev = q.device
+    out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return out_val, out_idx
+    lib = L.load()
+    with torch.cuda.device(dev):
+        if k <= L.MAX_FUSED_K:
+            nbytes = lib.knn_search_workspace(nq, ng, d, _DT[q.dtype], k)
+            ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+            rc = lib.knn_search(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _DT[q.dtype], k, _METRICS[metric],
+                                _SELF[self_mode], query_offset, index_base, _ptr(out_val), _ptr(out_idx),
+                                _ptr(ws), ws.numel(), _stream(q))
+            L.check(rc, "knn_search")
+            return out_val, out_idx
+    # k beyond the fused limit (train.py:409 asks for topk(N-1)): dense scores + full row ranking, in query
+    # chunks so the score block stays bounded.  Still the CUDA library -- never torch.mm / torch.sort.
+    kk = min(k, ng)
+    chunk = max(1, min(nq, (1 << 28) // max(ng, 1)))
+    largest = metric != "l2"
+    out_val.fill_(float("-inf") if largest else float("inf"))
+    out_idx.fill_(-1)
+    qf = q if q.dtype == torch.float32 else normalize(q, eps_mode="cast", out_dtype=torch.float32)
+    gf = g if g.dtype == torch.float32 else normalize(g, eps_mode="cast", out_dtype=torch.float32)
+    for s in range(0, nq, chunk):
+        e = min(nq, s + chunk)
+        sc = _scores_dense_prepared(qf[s:e], None if qsq is None else qsq[s:e], gf, gsq, metric, self_mode,
+                                    query_offset - index_base + s)
+        rk = rank_rows(sc, largest_first=largest)[:, :kk]
+        out_idx[s:e, :kk] = rk + index_base
+        out_val[s:e, :kk] = torch.gather(sc, 1, rk)
+    if self_mode == "exclude":  # the masked self entry ranks last with -inf/+inf: report it as "no candidate"
+        bad = torch.isinf(out_val) & (out_idx >= 0)
+        out_idx[bad] = -1
+    return out_val, out_idx
+
+
+def _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, self_offset_local):
+    nq, d = q.shape
+    ng = g.shape[0]
+    out = torch.empty((nq, ng), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = L.load().knn_scores_dense(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _DT[q.dtype],
+                                       _METRICS[metric], _SELF[self_mode], self_offset_local, _ptr(out), _stream(q))
+    L.check(rc, "knn_scores_dense")
+    return out
+
+
+def search(
+    queries: torch.Tensor,
+    gallery,
+    k: int,
+    metric: str = "cosine",
+    *,
+    normalize: bool = False,
+    exclude_self: bool = False,
+    self_mode: Optional[str] = None,
+    query_offset: int = 0,
+    precision: str = "fp32",
+    negated: bool = False,
+    eps: float = 1e-12,
+    eps_mode: str = "clamp",
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused distance + top-k: ``(distances [Q,k] fp32, indices [Q,k] int64)``, best first, ties by ascending
+    gallery row.  cosine/ip: similarities, descending.  l2: Euclidean distances, ascending
+    (``torch.argsort(cdist(q, g), dim=1)[:, :k]``, test_ath.py:87-114); ``negated=True`` returns ``-distance``
+    like ``(-torch.cdist(e, e)).topk(k)`` (test.py:1080-1085).
+
+    ``gallery`` is a ``[N, D]`` tensor or a :class:`FlatIndex` (then metric/precision/normalize come from it).
+    ``exclude_self`` masks gallery row ``query_offset + i`` for query ``i`` (``fill_diagonal_(-inf)``,
+    test.py:1081); ``self_mode="minus1"`` keeps it with score -1 (nih_multilabel_training.py:86).
+    """
+    if isinstance(gallery, FlatIndex):
+        vals, idx = gallery.search(queries, k, exclude_self=exclude_self, self_mode=self_mode,
+                                   query_offset=query_offset)
+        metric = gallery.metric
+    else:
+        _require_cuda(queries, gallery)
+        if metric not in _METRICS:
+            raise ValueError(f"metric must be one of {sorted(_METRICS)}")
+        want_sq = metric == "l2"
+        q, qsq = _prepare(queries, normalize, precision, eps, eps_mode, want_sq)
+        if gallery is queries:
+            g, gsq = q, qsq
+        else:
+            g, gsq = _prepare(gallery, normalize, precision, eps, eps_mode, want_sq)
+        mode = self_mode or ("exclude" if exclude_self else "keep")
+        vals, idx = _search_prepared(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
+    if negated and metric == "l2":
+        vals = -vals
+    return vals, idx
+
+
+def scores_dense(queries: torch.Tensor, gallery: torch.Tensor, metric: str = "cosine", *, normalize: bool = False,
+                 self_mode: str = "keep", query_offset: int = 0, eps: float = 1e-12,
+                 eps_mode: str = "clamp") -> torch.Tensor:
+    """The dense ``dists`` matrix of test.py:1080 / fusion_eval/metrics.py:15 for SMALL problems (callers that
+    save or post-process the full matrix).  Similarities for cosine/ip, positive distances for l2."""
+    _require_cuda(queries, gallery)
+    want_sq = metric == "l2"
+    q, qsq = _prepare(queries, normalize, "fp32", eps, eps_mode, want_sq)
+    g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, "fp32", eps, eps_mode, want_sq)
+    return _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, int(query_offset))
+
+
+def rank_rows(scores: torch.Tensor, largest_first: bool = True) -> torch.Tensor:
+    """Stable full ranking of every row: best first, ties by ascending column (the deterministic form of
+    ``torch.argsort(dists, dim=1, descending=True)``, test.py:1018).  -> int64 [Q, N]."""
+    _require_cuda(scores)
+    scores = _as2d(scores.float(), "scores")
+    nq, ng = scores.shape
+    ranks = torch.empty((nq, ng), dtype=torch.int64, device=scores.device)
+    if nq == 0 or ng == 0:
+        return ranks
+    lib = L.load()
+    with torch.cuda.device(scores.device):
+        nbytes = lib.knn_rank_rows_workspace(nq, ng)
+        ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=scores.device)
+        rc = lib.knn_rank_rows(_ptr(scores), nq, ng, 1 if largest_first else 0, _ptr(ranks), _ptr(ws), ws.numel(),
+                               _stream(scores))
+    L.check(rc, "knn_rank_rows")
+    return ranks
+
+
+def merge_topk(vals: torch.Tensor, idx: torch.Tensor, metric: str = "cosine") -> Tuple[torch.Tensor, torch.Tensor]:
+    """k-way merge of per-shard results ``[parts, Q, k]`` -> ``[Q, k]`` (after the candidate all-gather)."""
+    _require_cuda(vals, idx)
+    vals = vals.contiguous().float()
+    idx = idx.contiguous().long()
+    parts, nq, k = vals.shape
+    out_val = torch.empty((nq, k), dtype=torch.float32, device=vals.device)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=vals.device)
+    with torch.cuda.device(vals.device):
+        rc = L.load().knn_merge_topk(_ptr(vals), _ptr(idx), parts, nq, k, _METRICS[metric], _ptr(out_val),
+                                     _ptr(out_idx), _stream(vals))
+    L.check(rc, "knn_merge_topk")
+    return out_val, out_idx

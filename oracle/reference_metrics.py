@@ -1,0 +1,313 @@
+"""CPU restatement of the reference's retrieval METRICS -- TEST INFRASTRUCTURE ONLY.
+
+Each function restates one reference function (file:line in its docstring) over explicit rankings, so the only
+thing that differs from running the reference itself is where the ranking comes from: here it is always the
+deterministic order (score best-first, ties by ascending gallery index) instead of torch's / numpy's unstable
+sort.  Pinned against the live reference by tests/golden/*.npz (oracle/make_golden.py).
+"""
+from __future__ import annotations
+
+from collections import Counter
+from typing import Dict, Iterable, List, Sequence
+
+import numpy as np
+
+
+# ---- D1 ---------------------------------------------------------------------------------------
+def retrieval_accuracy(topk_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray, topk=(1,)) -> List[np.float32]:
+    """test.py:38-54: 100 * (#queries with a label match in the first k) / #queries, in float32."""
+    match = glabels[topk_idx] == qlabels[:, None]
+    n = np.float32(100.0 / len(qlabels))
+    return [np.float32(np.float32(match[:, :k].any(axis=1).sum()) * n) for k in topk]
+
+
+# ---- D2 ---------------------------------------------------------------------------------------
+def compute_ap(pos_ranks: Sequence[int], nres: int) -> float:
+    """test.py:58-92: trapezoidal area under the PR curve; ranks are 0-based positions of the positives."""
+    ap = 0
+    recall_step = 1.0 / nres
+    for j, rank in enumerate(pos_ranks):
+        p0 = 1.0 if rank == 0 else float(j) / rank
+        p1 = float(j + 1) / (rank + 1)
+        ap += (p0 + p1) * recall_step / 2.0
+    return ap
+
+
+def compute_map(ranks_rowmajor: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray, kappas=()):
+    """test.py:95-146 with ranks given row-major [nq, ng] (the reference takes the transpose).  Positives of query
+    i = every gallery row with its label (for self-retrieval this includes the query itself, which sits last)."""
+    nq = len(qlabels)
+    aps = np.zeros(nq)
+    prs = np.zeros((nq, len(kappas)))
+    pr = np.zeros(len(kappas))
+    mAP, nempty = 0.0, 0
+    for i in range(nq):
+        positives = np.where(glabels == qlabels[i])[0]
+        if positives.shape[0] == 0:
+            aps[i] = np.nan
+            prs[i, :] = np.nan
+            nempty += 1
+            continue
+        pos = np.arange(ranks_rowmajor.shape[1])[np.isin(ranks_rowmajor[i], positives)]
+        ap = compute_ap(pos, len(positives))
+        mAP = mAP + ap
+        aps[i] = ap
+        pos = pos + 1
+        for j, kappa in enumerate(kappas):
+            kq = min(max(pos), kappa)
+            prs[i, j] = (pos <= kq).sum() / kq
+        pr = pr + prs[i, :]
+    return mAP / (nq - nempty), aps, pr / (nq - nempty), prs
+
+
+# ---- D3 ---------------------------------------------------------------------------------------
+def majority_vote(labels_in_rank_order: Sequence, tie: str = "first"):
+    """test.py:149-161 (Counter.most_common -> first label reaching the max count); tie='smallest' is the
+    torch.mode / np.unique+argmax convention (train_ath.py:208, evaluate_medsiglip.py:156-157)."""
+    cnt = Counter(list(labels_in_rank_order))
+    if tie == "first":
+        return cnt.most_common(1)[0][0]
+    best = max(cnt.values())
+    return min(l for l, c in cnt.items() if c == best)
+
+
+def compute_classification_metrics(topk_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray,
+                                   k_values=(1, 5, 10, 15, 20)) -> Dict[int, Dict[str, float]]:
+    """test.py:164-223 from a ranking [nq, >=max(k)]."""
+    from sklearn.metrics import accuracy_score, f1_score, precision_score, recall_score
+
+    out = {}
+    for k in k_values:
+        pred = [majority_vote(glabels[topk_idx[i, :k]]) for i in range(len(qlabels))]
+        true = list(qlabels)
+        out[k] = {
+            "precision_macro": precision_score(true, pred, average="macro", zero_division=0) * 100.0,
+            "recall_macro": recall_score(true, pred, average="macro", zero_division=0) * 100.0,
+            "f1_macro": f1_score(true, pred, average="macro", zero_division=0) * 100.0,
+            "precision_weighted": precision_score(true, pred, average="weighted", zero_division=0) * 100.0,
+            "recall_weighted": recall_score(true, pred, average="weighted", zero_division=0) * 100.0,
+            "f1_weighted": f1_score(true, pred, average="weighted", zero_division=0) * 100.0,
+            "accuracy": accuracy_score(true, pred) * 100.0,
+        }
+    return out
+
+
+# ---- Jaccard relevance ---------------------------------------------------------------------------
+def jaccard_fp32(a: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """train.py:462-464 / nih_multilabel_training.py:90-92 / test.py:956-959: float32 tensors."""
+    a, B = a.astype(np.float32), B.astype(np.float32)
+    inter = (a[None, :] * B).sum(axis=1, dtype=np.float32)
+    union = np.minimum(a[None, :] + B, np.float32(1.0)).sum(axis=1, dtype=np.float32)
+    return inter / (union + np.float32(1e-8))
+
+
+def jaccard_fp64(a: Sequence[float], b: Sequence[float]) -> float:
+    """evaluate_nih_zilliz.py:12-17: float32 sums converted to Python floats, double division."""
+    a32, b32 = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    inter = float((a32 * b32).sum())
+    union = float(np.clip(a32 + b32, 0.0, 1.0).sum())
+    return inter / (union + 1e-8)
+
+
+# ---- D4 ---------------------------------------------------------------------------------------
+def compute_map_multilabel(ranks_rowmajor: np.ndarray, labels: np.ndarray, threshold: float = 0.5):
+    """test.py:941-985: rank-by-rank AP over the full ranking, relevance = Jaccard > threshold (fp32), self
+    removed, queries without relevant items skipped.  ranks_rowmajor [n, n] may contain the query itself."""
+    n = labels.shape[0]
+    aps = []
+    for i in range(n):
+        rel = (jaccard_fp32(labels[i], labels) > np.float32(threshold)).astype(float)
+        rel[i] = 0
+        if rel.sum() > 0:
+            count_pos, ap = 0, 0
+            for rank, j in enumerate(ranks_rowmajor[i]):
+                if j >= 0 and rel[j] > 0:
+                    count_pos += 1
+                    ap += count_pos / (rank + 1)
+            aps.append(ap / rel.sum())
+    return np.mean(aps) if aps else 0
+
+
+# ---- D5 ---------------------------------------------------------------------------------------
+def multilabel_precision_recall_at_k(topk_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray,
+                                     k_values=(1, 5, 10, 15, 20)):
+    """test.py:1031-1056: match = shares >= 1 label; Precision@K = mean(#match/K); Recall@K = hit-rate."""
+    out = {}
+    nq = qlabels.shape[0]
+    for k in k_values:
+        total_p, total_r = 0, 0
+        for i in range(nq):
+            matches = (glabels[topk_idx[i, :k]] * qlabels[i]).sum(axis=1) > 0
+            nm = np.sum(matches)
+            total_p += nm / k
+            if nm > 0:
+                total_r += 1
+        out[k] = ((total_p / nq) * 100, (total_r / nq) * 100)
+    return out
+
+
+# ---- sklearn AP (D7, D8, D9 use it) ----------------------------------------------------------------
+def average_precision_ranked(scores_desc: np.ndarray, rel: np.ndarray) -> float:
+    """sklearn.metrics.average_precision_score restated for a list already sorted by descending score:
+    thresholds at the last index of each run of equal scores; AP = -sum(diff(recall) * precision[:-1]) on the
+    reversed curves (sklearn/metrics/_ranking.py)."""
+    rel = np.asarray(rel, dtype=np.float64)
+    s = np.asarray(scores_desc)
+    distinct = np.where(np.diff(s))[0]
+    thr = np.r_[distinct, len(s) - 1]
+    tps = np.cumsum(rel)[thr]
+    fps = 1 + thr - tps
+    ps = tps + fps
+    precision = np.zeros_like(tps)
+    np.divide(tps, ps, out=precision, where=ps != 0)
+    recall = tps / tps[-1]
+    precision = np.hstack((precision[::-1], [1.0]))
+    recall = np.hstack((recall[::-1], [0.0]))
+    return float(-np.sum(np.diff(recall) * precision[:-1]))
+
+
+# ---- D6 ---------------------------------------------------------------------------------------
+def single_label_retrieval_metrics(full_idx: np.ndarray, labels: np.ndarray, topk=(1, 5, 10)) -> Dict[str, float]:
+    """train.py:399-441 from the full self-excluded ranking [n, n-1].  The reference does the AP arithmetic in
+    torch float32 (cumsum / positions, .sum()); here it is float64 -> compared with a 1e-5 tolerance."""
+    n = len(labels)
+    if n <= 1:
+        return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
+    rel = labels[full_idx] == labels[:, None]
+    counts = (labels[:, None] == labels[None, :]).sum(axis=1) - 1
+    aps = []
+    for i in range(n):
+        hits = np.flatnonzero(rel[i])
+        if counts[i] <= 0 or hits.size == 0:
+            aps.append(0.0)
+            continue
+        prec = np.cumsum(rel[i].astype(np.float64))[hits] / (hits + 1.0)
+        aps.append(float(prec.sum() / counts[i]))
+    m = {"mAP": float(np.mean(aps) * 100.0)}
+    for k in topk:
+        kk = min(k, rel.shape[1])
+        m[f"R@{k}"] = float(rel[:, :kk].any(axis=1).astype(np.float32).mean()) * 100.0 if kk > 0 else 0.0
+    return m
+
+
+# ---- D7 / D8 ------------------------------------------------------------------------------------
+def multilabel_retrieval_metrics(full_val: np.ndarray, full_idx: np.ndarray, labels: np.ndarray, topk=(1, 5, 10),
+                                 relevance_threshold: float = 0.4) -> Dict[str, float]:
+    """train.py:444-487 from the full self-excluded ranking (values + indices, [n, n-1])."""
+    n = labels.shape[0]
+    aps, recalls = [], {k: [] for k in topk}
+    for i in range(n):
+        rel = (jaccard_fp32(labels[i], labels) > np.float32(relevance_threshold)).astype(np.float64)
+        rel[i] = 0.0
+        ranked_rel = rel[full_idx[i]]
+        if rel.sum() > 0:
+            aps.append(average_precision_ranked(full_val[i], ranked_rel))
+        for k in topk:
+            kk = min(k, ranked_rel.size)
+            recalls[k].append(float(ranked_rel[:kk].any()) if kk > 0 else 0.0)
+    m = {"mAP": float(np.mean(aps) * 100.0) if aps else 0.0}
+    for k in topk:
+        m[f"R@{k}"] = float(np.mean(recalls[k]) * 100.0) if recalls[k] else 0.0
+    return m
+
+
+def evaluate_map(full_val: np.ndarray, full_idx: np.ndarray, labels: np.ndarray, jaccard_threshold: float = 0.4):
+    """nih_multilabel_training.py:83-99 from the full ranking INCLUDING self at similarity -1 ([n, n])."""
+    aps = []
+    for i in range(labels.shape[0]):
+        rel = (jaccard_fp32(labels[i], labels) > np.float32(jaccard_threshold)).astype(np.float64)
+        if rel.sum() > 0:
+            aps.append(average_precision_ranked(full_val[i], rel[full_idx[i]]))
+    return float(np.mean(aps) * 100.0) if aps else 0.0
+
+
+# ---- D9 ---------------------------------------------------------------------------------------
+def evaluate_results(topk_val: np.ndarray, topk_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray,
+                     jaccard_threshold: float = 0.4, ks: Iterable[int] = (1, 5, 10, 20, 50)) -> Dict[str, float]:
+    """evaluate_nih_zilliz.py:34-64 over hit lists given as arrays (scores + gallery rows, best first)."""
+    aps = []
+    ks = list(ks)
+    P = {k: [] for k in ks}
+    R = {k: [] for k in ks}
+    for i in range(topk_idx.shape[0]):
+        rels = [1.0 if jaccard_fp64(qlabels[i], glabels[j]) > jaccard_threshold else 0.0 for j in topk_idx[i]]
+        total = int(sum(rels))
+        if total > 0:
+            aps.append(average_precision_ranked(topk_val[i], np.asarray(rels)))
+        for k in ks:
+            kk = min(k, len(rels))
+            P[k].append(float(np.mean(rels[:kk])) if rels else 0.0)
+            R[k].append(float(np.sum(rels[:kk]) / total) if total > 0 else 0.0)
+    m = {"mAP": float(np.mean(aps) * 100.0) if aps else 0.0, "num_queries": float(topk_idx.shape[0]),
+         "num_valid_ap_queries": float(len(aps))}
+    for k in ks:
+        m[f"P@{k}"] = float(np.mean(P[k]) * 100.0) if P[k] else 0.0
+        m[f"R@{k}"] = float(np.mean(R[k]) * 100.0) if R[k] else 0.0
+    return m
+
+
+# ---- D10 --------------------------------------------------------------------------------------
+def ath_compute_metrics(sorted_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray, topk_values=(1, 5, 10)):
+    """test_ath.py:90-172 from the ascending-distance ranking [nq, >= max(topk)]."""
+    retrieval = {}
+    total_rel = [(glabels == int(l)).sum() for l in qlabels]
+    for topk in topk_values:
+        hit, ap, rr, vote, pk, rk = [], [], [], [], [], []
+        for row, label in enumerate(qlabels):
+            label = int(label)
+            ranked = glabels[sorted_idx[row, :topk]]
+            matches = (ranked == label).astype(np.int32)
+            hit.append(float(matches.any()))
+            nrel = matches.sum()
+            pk.append(nrel / topk)
+            rk.append(nrel / total_rel[row] if total_rel[row] > 0 else 0.0)
+            if nrel == 0:
+                ap.append(0.0)
+                rr.append(0.0)
+            else:
+                first, psum, positives = None, 0.0, 0
+                for rank, m in enumerate(matches, start=1):
+                    if m:
+                        positives += 1
+                        psum += positives / rank
+                        if first is None:
+                            first = rank
+                ap.append(psum / positives)
+                rr.append(1.0 / first)
+            vote.append(float(majority_vote(ranked.tolist()) == label))
+        retrieval[topk] = {"mhr": float(np.mean(hit)), "map": float(np.mean(ap)), "mrr": float(np.mean(rr)),
+                           "mp@k": float(np.mean(pk)), "r@k": float(np.mean(rk)),
+                           "majority_acc": float(np.mean(vote))}
+    return retrieval
+
+
+# ---- D11 --------------------------------------------------------------------------------------
+def fusion_evaluate_retrieval_metrics(full_idx: np.ndarray, labels: Sequence, k_values=(1, 5, 10)):
+    """fusion_eval/metrics.py:41-94 from the full self-excluded ranking [n, n-1] (unique image paths)."""
+    labels = np.asarray(labels)
+    k_values = sorted(set(int(k) for k in k_values))
+    aps, P, R = [], {k: [] for k in k_values}, {k: [] for k in k_values}
+    for q in range(len(labels)):
+        relevant = labels[full_idx[q]] == labels[q]
+        count = int(np.sum(labels == labels[q]) - 1)
+        if count <= 0:
+            aps.append(0.0)
+            for k in k_values:
+                P[k].append(0.0)
+                R[k].append(0.0)
+            continue
+        hits = np.flatnonzero(relevant)
+        if len(hits) == 0:
+            aps.append(0.0)
+        else:
+            prec = np.cumsum(relevant.astype(np.int32))[hits] / (hits + 1)
+            aps.append(float(np.sum(prec) / count))
+        for k in k_values:
+            h = int(np.sum(relevant[:k]))
+            P[k].append(h / k)
+            R[k].append(1.0 if h > 0 else 0.0)
+    m = {"num_samples": float(len(labels)), "mAP": float(np.mean(aps) * 100.0)}
+    for k in k_values:
+        m[f"mP@{k}"] = float(np.mean(P[k]) * 100.0)
+        m[f"R@{k}"] = float(np.mean(R[k]) * 100.0)
+    return m
