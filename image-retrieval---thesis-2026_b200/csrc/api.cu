@@ -15,6 +15,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Optional per-thread profiling: CUDA events recorded on the caller's stream right around the distance kernel
+// and the unit-merge kernel of knn_search (bench.py derives the roofline fraction of the dominant kernel from
+// these; nothing is recorded and nothing synchronises unless the caller opted in).
+struct Profile {
+  bool on = false;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  bool valid = false;
+};
+static thread_local Profile g_prof;
+
 static int sm_count() {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -120,12 +130,48 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + tau_bytes);
   p.dense_out = nullptr;
 
+  const bool prof = g_prof.on;
+  if (prof) {
+    for (auto& e : g_prof.ev)
+      if (!e) KNN_CHECK_CUDA(cudaEventCreate(&e));
+    g_prof.valid = false;
+  }
   if (geo.splits > 0) {
     KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
+    if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
     rc = (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
     if (rc != KNN_OK) return rc;
+  } else if (prof) {
+    KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
   }
-  return launch_merge_units(p, index_base, out_val, out_idx, s);
+  if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[1], s));
+  rc = launch_merge_units(p, index_base, out_val, out_idx, s);
+  if (rc != KNN_OK) return rc;
+  if (prof) {
+    KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[2], s));
+    g_prof.valid = true;
+  }
+  return KNN_OK;
+}
+
+extern "C" int knn_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.valid = false;
+  return KNN_OK;
+}
+
+extern "C" int knn_profile_last(float* distance_ms, float* merge_ms) {
+  if (!g_prof.valid) {
+    set_error("knn_profile_last: no profiled knn_search call on this thread");
+    return KNN_E_INVALID;
+  }
+  KNN_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[2]));
+  float a = 0.f, b = 0.f;
+  KNN_CHECK_CUDA(cudaEventElapsedTime(&a, g_prof.ev[0], g_prof.ev[1]));
+  KNN_CHECK_CUDA(cudaEventElapsedTime(&b, g_prof.ev[1], g_prof.ev[2]));
+  if (distance_ms) *distance_ms = a;
+  if (merge_ms) *merge_ms = b;
+  return KNN_OK;
 }
 
 extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,

@@ -92,6 +92,12 @@ KNN_API int knn_search(const void* q, const void* g, const float* q_sqnorm, cons
                void* workspace, size_t workspace_bytes, void* stream);
 KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k);
 
+/* Opt-in, per calling thread: knn_search records CUDA events on its stream around (a) the distance+select
+ * kernel and (b) the unit-merge kernel; knn_profile_last synchronises on them and returns the two durations of
+ * the most recent knn_search call (measurement harness only; host pointers). */
+KNN_API int knn_profile_enable(int on);
+KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
+
 /* Dense score matrix (small problems only; compatibility with callers that want the full `dists`
  * matrix of test.py:1080 / fusion_eval/metrics.py:15).  out [nq,ng] fp32, same score definition and
  * self handling as knn_search (KNN_SELF_EXCLUDE writes -inf for similarity, +inf for L2). */

@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads and exports exactly what include/b200knn.h declares; argument validation
+that needs no device returns the documented error codes."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "b200knn.h")).read()
+    return sorted(set(re.findall(r"KNN_API\s+[\w\s\*]+?\b(knn_\w+)\s*\(", hdr)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _declared_symbols()
+    for must in ("knn_normalize", "knn_search", "knn_search_workspace", "knn_merge_topk", "knn_rank_rows",
+                 "knn_relevance_single", "knn_relevance_multilabel", "knn_ranked_stats", "knn_map_full"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from b200knn import _lib
+
+    lib = _lib.load()
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/b200knn.h but not exported"
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+    assert lib.knn_version() == 1
+
+
+def test_argument_validation_without_a_device():
+    from b200knn import _lib
+
+    lib = _lib.load()
+    # bad dtype / metric / k are rejected before any CUDA call
+    rc = lib.knn_search(None, None, None, None, 4, 4, 8, 7, 1, 0, 0, 0, 0, None, None, None, 0, None)
+    assert rc == -1 and b"dtype" in lib.knn_last_error()
+    rc = lib.knn_search(None, None, None, None, 4, 4, 8, 0, 1, 9, 0, 0, 0, None, None, None, 0, None)
+    assert rc == -1 and b"metric" in lib.knn_last_error()
+    rc = lib.knn_search(None, None, None, None, 4, 4, 8, 0, 0, 0, 0, 0, 0, None, None, None, 0, None)
+    assert rc == -1  # null q/g
+    rc = lib.knn_normalize(None, None, None, 4, 0, 0, 0, 1e-12, 0, None)
+    assert rc == -1
+    rc = lib.knn_merge_topk(None, None, 2, 4, 8, 0, None, None, None)
+    assert rc == -1
+    assert lib.knn_search_workspace(0, 100, 8, 0, 10) == 0
+    assert lib.knn_search_workspace(300, 100000, 64, 0, 100) > 0
+    assert lib.knn_rank_rows_workspace(4, 100) == 0 and lib.knn_rank_rows_workspace(4, 5000) == 4 * 8192 * 8
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "image-retrieval---thesis-2026_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in src.replace("# oracle", ""), name
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    import torch
+
+    import b200knn
+
+    with pytest.raises(b200knn.KnnError):
+        b200knn.search(torch.zeros(2, 8), torch.zeros(4, 8), 1)
+    with pytest.raises(b200knn.KnnError):
+        b200knn.normalize(torch.zeros(2, 8))

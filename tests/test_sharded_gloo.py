@@ -1,0 +1,85 @@
+"""CPU, world_size 2 over gloo: the row-sharding plan, the single candidate all-gather and the merge logic of
+ShardedFlatIndex.  The two device steps (local search, k-way merge) are replaced by the CPU oracle here -- the
+product path itself has no CPU implementation."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from b200knn.sharded import pack_candidates, shard_rows, unpack_candidates
+
+
+def test_shard_rows_cover_everything():
+    for n in (0, 1, 7, 100, 50_000_000):
+        for w in (1, 2, 4, 8):
+            parts = shard_rows(n, w)
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+            for (s0, c0), (s1, _) in zip(parts, parts[1:]):
+                assert s0 + c0 == s1
+
+
+def test_pack_unpack_roundtrip():
+    vals = torch.randn(5, 7)
+    idx = torch.randint(0, 1 << 40, (5, 7))
+    buf = torch.cat([pack_candidates(vals, idx), pack_candidates(vals + 1, idx + 1)])
+    v, i = unpack_candidates(buf, 2, 5, 7)
+    assert torch.equal(v[0], vals) and torch.equal(i[1], idx + 1)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import oracle
+    from b200knn.search import FlatIndex
+    from b200knn.sharded import ShardedFlatIndex
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = np.random.RandomState(0)
+    g = oracle.normalize(rs.standard_normal((301, 32)).astype(np.float32))
+    g[17] = g[250]  # a tie across the shard boundary: must resolve to the lower global row
+    q = g[:40].copy()
+    start, count = shard_rows(g.shape[0], world)[rank]
+
+    class OracleShard(ShardedFlatIndex):
+        def __init__(self):
+            self.local = FlatIndex.__new__(FlatIndex)
+            self.local.metric = "cosine"
+            self.group, self.world_size, self.rank = None, world, rank
+
+        def _search_local(self, queries, k, self_mode, query_offset):
+            v, i = oracle.search(queries.numpy(), g[start:start + count], k, "cosine", self_mode, query_offset, start)
+            return torch.from_numpy(v), torch.from_numpy(i)
+
+        def _merge(self, vals, idx):
+            v, i = oracle.merge_topk(vals.numpy(), idx.numpy(), "cosine")
+            return torch.from_numpy(v), torch.from_numpy(i)
+
+    v, i = OracleShard().search(torch.from_numpy(q), 10, exclude_self=True)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), v=v.numpy(), i=i.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_search_equals_single_shard(tmp_path):
+    import oracle
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    rs = np.random.RandomState(0)
+    g = oracle.normalize(rs.standard_normal((301, 32)).astype(np.float32))
+    g[17] = g[250]
+    v1, i1 = oracle.search(g[:40].copy(), g, 10, "cosine", "exclude", 0)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(z["i"], i1) and np.array_equal(z["v"], v1)
