@@ -45,6 +45,7 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int dtype, int k) {
   g.L = 2 * g.kp;
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
+  if (dtype == KNN_BF16 && (g.qblocks & 1)) g.qblocks += 1;  // CTA pairs own 256 query rows
   const int tile = dtype == KNN_BF16 ? bf16_tile_cols() : 128;
   const int64_t ntiles = (ng + tile - 1) / tile;
   const int sms = sm_count();

@@ -26,7 +26,8 @@ struct SearchParams {
 };
 
 int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream);
-int launch_search_bf16(const SearchParams& p, cudaStream_t stream);
+int launch_search_bf16(const SearchParams& p, cudaStream_t stream);       // dispatch (pair kernel by default)
+int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream);  // cta_group::2, csrc/search_tc2.cu
 int bf16_tile_cols();  // gallery rows per tile of the tcgen05 kernel
 
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,

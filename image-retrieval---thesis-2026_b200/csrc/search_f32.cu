@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p)
             if (kL2) return fmaf(2.0f, dot, -(qn + gs[cb + j]));
             return dot;
           };
-          select_chunk<32, kL2>(st, fv, (uint32_t)cg, nvalid, self_row, p.self_mode, row_valid);
+          select_chunk_mem<kL2>(st, fv, srow + cb, 4, qn, gs + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
+                                row_valid);
           warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
         }
       }

@@ -11,6 +11,7 @@
 //                               runs the threshold filter / candidate lists of select.cuh
 // The selection of tile t overlaps the MMAs of tile t+1 through the two TMEM stages, so the Q x N score
 // matrix never exists outside TMEM.
+#include <stdlib.h>
 #include "select.cuh"
 #include "ptx.cuh"
 #include "kernels.h"
@@ -41,7 +42,7 @@ struct alignas(8) TcBarriers {
   uint32_t pad;
 };
 
-constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * STAGE_BYTES +
+constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * STAGE_BYTES + kDumpBytes +
                               sizeof(float) * kAccStages * TN + sizeof(TcBarriers);
 
 template <int E, bool kL2>
@@ -52,7 +53,8 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                       // [kStages][128][64] bf16, swizzled
   uint8_t* smem_b = smem + (size_t)kStages * A_STAGE_BYTES;     // [kStages][256][64] bf16, swizzled
-  float* gs = reinterpret_cast<float*>(smem + (size_t)kStages * STAGE_BYTES);  // [kAccStages][TN]
+  float* dump = reinterpret_cast<float*>(smem + (size_t)kStages * STAGE_BYTES);  // slow-path staging, 16 KB
+  float* gs = dump + kDumpBytes / 4;                                             // [kAccStages][TN]
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(gs + kAccStages * TN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,16 +176,12 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       for (int cb = 0; cb < TN; cb += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_fence(v);
         const int64_t cg = col0 + cb;
         const int64_t rem = c_end - cg;
         const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
-        auto fv = [&](int j) -> float {
-          const float dot = __uint_as_float(v[j]);
-          if (kL2) return fmaf(2.0f, dot, -(qn + gst[cb + j]));
-          return dot;
-        };
-        select_chunk<32, kL2>(st, fv, (uint32_t)cg, nvalid, self_row, p.self_mode, row_valid);
+        select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
+                               row_valid);
         warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
       }
       ptx::tc_fence_before();
@@ -266,6 +264,10 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
 int bf16_tile_cols() { return TN; }
 
 int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
+  static const bool single = [] {
+    const char* e = getenv("KNN_BF16_SINGLE_CTA");  // A/B switch: 1 = the cta_group::1 kernel of this file
+    return e != nullptr && e[0] == '1';
+  }();
   if (p.d % 8 != 0) {
     set_error("bf16 search needs d %% 8 == 0 (TMA row pitch must be a multiple of 16 bytes), got d=%d", p.d);
     return KNN_E_UNSUPPORTED;
@@ -274,6 +276,7 @@ int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
     set_error("bf16 search needs 16-byte aligned q and g");
     return KNN_E_INVALID;
   }
+  if (!single) return launch_search_bf16_pair(p, stream);
   switch (p.kp) {
     case 32: return launch_e<2>(p, stream);
     case 64: return launch_e<4>(p, stream);

@@ -1,0 +1,339 @@
+// bf16 distance + fused top-k on CTA PAIRS (tcgen05 cta_group::2) -- the tensor-bound kernel.
+//
+// A cluster of two CTAs (one TPC) owns 256 query rows and streams its gallery split in tiles of 256 rows:
+//   * each CTA keeps ITS 128 query rows (UMMA A operand half) in shared memory -- resident for the whole unit when
+//     D <= 512 (128 KB), otherwise streamed k-block by k-block next to B;
+//   * each CTA TMA-loads HALF of every gallery tile (128 rows x 64 k, 16 KB per stage) into its own smem, so the
+//     L2 -> SM traffic per SM is half of the single-CTA kernel's (32 B/cycle/SM at full tensor rate);
+//   * one thread of the leader CTA issues tcgen05.mma.cta_group::2 (M=256, N=256, K=16): the tensor cores of both
+//     SMs read A/B halves from both shared memories; each CTA's TMEM receives its own 128 rows x 256 columns;
+//   * smem slots and TMEM stages are recycled through mbarriers: TMA of both CTAs completes on the leader's `full`
+//     barrier, tcgen05.commit multicasts to the `empty` / `tmem_full` barriers of both CTAs, the epilogue warps of
+//     both CTAs arrive (remotely for the peer) on the leader's `tmem_empty`.
+// Epilogue/selection is identical to search_tc.cu: thread i of warps 2..5 owns TMEM lane i = one query row.
+#include <stdlib.h>
+#include "select.cuh"
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace knn {
+
+namespace {
+
+constexpr int TM = 128;        // query rows per CTA (256 per pair)
+constexpr int TN = 256;        // gallery rows per pair tile
+constexpr int TNH = 128;       // gallery rows loaded by each CTA
+constexpr int BKE = 64;        // bf16 elements per k-block (128 B = one swizzle row)
+constexpr int UMMA_K = 16;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxStages = 12;
+constexpr uint32_t KB_BYTES = TM * BKE * 2;  // 16 KB: one k-block of 128 rows (A half or B half)
+constexpr size_t kSmemBudget = 232448;       // 227 KB opt-in limit per CTA
+
+struct alignas(8) PairBarriers {
+  uint64_t full[kMaxStages];        // leader only: 2 arrivals (both producers) + tx bytes of both CTAs
+  uint64_t empty[kMaxStages];       // every CTA: 1 arrival (multicast tcgen05.commit)
+  uint64_t a_full;                  // leader only: resident query tile of both CTAs landed
+  uint64_t tmem_full[kAccStages];   // every CTA: 1 arrival (multicast tcgen05.commit)
+  uint64_t tmem_empty[kAccStages];  // leader only: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct PairCfg {
+  int stages;      // ring depth
+  int resident;    // 1: query k-blocks stay in smem for the whole unit
+  int nkb;         // k-blocks
+  uint32_t a_bytes;      // resident A region
+  uint32_t stage_bytes;  // bytes per ring stage in ONE CTA (B half [+ A k-block when streaming])
+  int debug;             // measurement knob (KNN_PAIR_DEBUG=1): the epilogue skips the selection (results are
+                         // garbage; isolates the TMA + MMA pipeline in timing experiments)
+};
+
+template <int E, bool kL2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                        SearchParams p, PairCfg cfg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_a = smem;                                    // resident A: [nkb][128][64] bf16 (swizzled)
+  uint8_t* ring = smem + cfg.a_bytes;                        // [stages][stage_bytes]
+  float* dump = reinterpret_cast<float*>(ring + (size_t)cfg.stages * cfg.stage_bytes);  // slow-path staging, 16 KB
+  float* gs = dump + kDumpBytes / 4;                                                     // [2][TN] (L2 metric)
+  PairBarriers* bars = reinterpret_cast<PairBarriers*>(gs + kAccStages * TN);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int qb = blockIdx.x;  // 128-row query block of THIS CTA (pair = blockIdx.x >> 1)
+  const int sp = blockIdx.y;
+  const int64_t row0 = (int64_t)qb * TM;
+  const int64_t c_begin = (int64_t)sp * p.split_len;
+  const int64_t c_end = (c_begin + p.split_len < p.ng) ? c_begin + p.split_len : p.ng;
+  const int ntiles = c_end > c_begin ? (int)((c_end - c_begin + TN - 1) / TN) : 0;
+  const int nkb = cfg.nkb;
+  const int stages = cfg.stages;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("b200knn: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_g);
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&bars->full[s], 2);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    ptx::mbar_init(&bars->a_full, 2);
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(&bars->tmem_full[s], 1);
+      ptx::mbar_init(&bars->tmem_empty[s], 2 * kEpiThreads / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(&bars->tmem_base, kTmemCols);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barrier inits + TMEM allocation of BOTH CTAs visible before any remote traffic
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      if (cfg.resident) {
+        const uint32_t a_full_leader = ptx::mapa(ptx::smem_u32(&bars->a_full), 0);
+        for (int kb = 0; kb < nkb; ++kb)
+          ptx::tma_load_2d_2sm(smem_a + (size_t)kb * KB_BYTES, &tmap_q, a_full_leader, kb * BKE, (int32_t)row0,
+                               ptx::kEvictLast);
+        if (leader) ptx::mbar_arrive_expect_tx(&bars->a_full, 2u * (uint32_t)nkb * KB_BYTES);
+        else ptx::mbar_arrive_cluster(a_full_leader);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int32_t col0 = (int32_t)(c_begin + (int64_t)t * TN + (int64_t)rank * TNH);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* st = ring + (size_t)stage * cfg.stage_bytes;
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+          ptx::tma_load_2d_2sm(st, &tmap_g, full_leader, kb * BKE, col0, ptx::kEvictNormal);
+          if (!cfg.resident)
+            ptx::tma_load_2d_2sm(st + KB_BYTES, &tmap_q, full_leader, kb * BKE, (int32_t)row0, ptx::kEvictLast);
+          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2u * cfg.stage_bytes);
+          else ptx::mbar_arrive_cluster(full_leader);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * TM, TN);
+      if (cfg.resident) {
+        ptx::mbar_wait(&bars->a_full, 0);
+        ptx::tc_fence_after();
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int as = t & 1;
+        const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+        ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * TN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(ring + (size_t)stage * cfg.stage_bytes);
+          const uint32_t a_addr = cfg.resident ? ptx::smem_u32(smem_a + (size_t)kb * KB_BYTES) : b_addr + KB_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKE / UMMA_K; ++k) {
+            const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr + k * UMMA_K * 2);
+            const uint64_t db = ptx::make_sw128_kmajor_desc(b_addr + k * UMMA_K * 2);
+            ptx::mma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit_2sm(&bars->empty[stage], 3);  // frees this slot in BOTH CTAs when the MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit_2sm(&bars->tmem_full[as], 3);   // accumulator tile complete (both CTAs' epilogues)
+      }
+    }
+  } else {
+    // ===================================================================== epilogue / selection (both CTAs)
+    constexpr int L = 32 * E;
+    const int quarter = warp & 3;
+    const int rloc = quarter * 32 + lane;
+    const bool row_valid = row0 + rloc < p.nq;
+    const int64_t unit = (int64_t)sp * p.qblocks + qb;
+    RowState st;
+    rowstate_init(st, p.lists + ((unit * TM + rloc) * (int64_t)L));
+    uint32_t self_row = 0xFFFFFFFFu;
+    float qn = 0.f;
+    uint32_t* tau_row = nullptr;
+    if (row_valid) {
+      const int64_t sr = p.self_offset + row0 + rloc;
+      if (p.self_mode != KNN_SELF_KEEP && sr >= 0 && sr < p.ng) self_row = (uint32_t)sr;
+      if (kL2) qn = __ldg(p.qsq + row0 + rloc);
+      tau_row = p.tau_global + row0 + rloc;
+    }
+    const int et = threadIdx.x - 64;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int as = t & 1;
+      const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+      const int64_t col0 = c_begin + (int64_t)t * TN;
+      float* gst = gs + as * TN;
+      if (kL2) {
+#pragma unroll
+        for (int h = 0; h < TN / kEpiThreads; ++h) {
+          int64_t c = col0 + et + h * kEpiThreads;
+          if (c >= p.ng) c = p.ng - 1;
+          gst[et + h * kEpiThreads] = __ldg(p.gsq + c);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+      const uint32_t tau_peek = peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
+      ptx::mbar_wait(&bars->tmem_full[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
+      if (cfg.debug != 1) {
+        // software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is examined
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(taddr, v0);
+        apply_tau<kL2>(st, tau_peek);
+        ptx::tmem_ld_fence(v0);
+        auto process = [&](const uint32_t (&v)[32], int cb) {
+          const int64_t cg = col0 + cb;
+          const int64_t rem = c_end - cg;
+          const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
+          select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
+                                 row_valid);
+          warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+        };
+#pragma unroll 1
+        for (int cb = 0; cb < TN; cb += 64) {
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(cb + 32), v1);
+          process(v0, cb);
+          ptx::tmem_ld_fence(v1);
+          if (cb + 64 < TN) ptx::tmem_ld_32x32(taddr + (uint32_t)(cb + 64), v0);
+          process(v1, cb + 32);
+          if (cb + 64 < TN) ptx::tmem_ld_fence(v0);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) ptx::mbar_arrive(&bars->tmem_empty[as]);
+        else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
+      }
+    }
+    warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // nobody exits (or frees TMEM) while the peer may still touch its smem / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn2(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    KNN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return KNN_E_CUDA;
+    }
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return KNN_OK;
+}
+
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn2(&enc);
+  if (rc != KNN_OK) return rc;
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);
+    return KNN_E_CUDA;
+  }
+  return KNN_OK;
+}
+
+template <int E>
+int launch_e(const SearchParams& p, cudaStream_t stream) {
+  CUtensorMap tq, tg;
+  int rc = make_tmap(&tq, p.q, p.nq, p.d, TM);
+  if (rc != KNN_OK) return rc;
+  rc = make_tmap(&tg, p.g, p.ng, p.d, TNH);
+  if (rc != KNN_OK) return rc;
+
+  PairCfg cfg;
+  cfg.nkb = (p.d + BKE - 1) / BKE;
+  const size_t fixed = kDumpBytes + sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
+  cfg.resident = ((size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
+  cfg.a_bytes = cfg.resident ? (uint32_t)cfg.nkb * KB_BYTES : 0u;
+  cfg.stage_bytes = cfg.resident ? KB_BYTES : 2 * KB_BYTES;
+  int stages = (int)((kSmemBudget - fixed - cfg.a_bytes) / cfg.stage_bytes);
+  cfg.stages = stages > kMaxStages ? kMaxStages : stages;
+  cfg.debug = 0;
+  if (const char* e = getenv("KNN_PAIR_DEBUG")) cfg.debug = atoi(e);
+  if (const char* e = getenv("KNN_PAIR_STAGES")) {
+    const int want = atoi(e);
+    if (want >= 2 && want < cfg.stages) cfg.stages = want;
+  }
+  const size_t smem = (size_t)cfg.a_bytes + (size_t)cfg.stages * cfg.stage_bytes + fixed;
+
+  dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);  // qblocks is even: consecutive CTAs form the pair
+  if (p.metric == KNN_L2) {
+    auto kern = search_bf16_pair_kernel<E, true>;
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+  } else {
+    auto kern = search_bf16_pair_kernel<E, false>;
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+  }
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+}  // namespace
+
+int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream) {
+  if (p.qblocks % 2 != 0) {
+    set_error("internal: pair kernel needs an even number of 128-row query blocks");
+    return KNN_E_INVALID;
+  }
+  switch (p.kp) {
+    case 32: return launch_e<2>(p, stream);
+    case 64: return launch_e<4>(p, stream);
+    case 128: return launch_e<8>(p, stream);
+    case 256: return launch_e<16>(p, stream);
+    default: set_error("unsupported padded k %d", p.kp); return KNN_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace knn

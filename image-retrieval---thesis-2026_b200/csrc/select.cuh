@@ -59,10 +59,15 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&v)[E], int lane) {
 }
 
 // Warp-cooperative compaction of one row's list: sort, keep the best `keep` (k, or KP at unit end),
-// return the new count and (if >= k candidates exist) the new threshold.  All 32 lanes must call.
+// return the new count and (if >= k candidates exist) the new threshold key.  All 32 lanes must call.
+// Deliberately NOT inlined: the sorting network is ~2.5k instructions and runs rarely; one copy per kernel keeps
+// the hot epilogue loop inside the instruction cache.
+struct CompactOut {
+  int cnt;
+  uint64_t taukey;
+};
 template <int E>
-__device__ __forceinline__ void compact_row(uint64_t* __restrict__ list, int cnt, int k, int keep, int lane,
-                                            int& new_cnt, uint64_t& new_taukey) {
+__device__ __noinline__ CompactOut compact_row(uint64_t* __restrict__ list, int cnt, int k, int keep, int lane) {
   uint64_t v[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -82,8 +87,10 @@ __device__ __forceinline__ void compact_row(uint64_t* __restrict__ list, int cnt
     uint64_t t = __shfl_sync(kFullMask, v[e], kl);
     if (e == ke) kth = t;
   }
-  new_cnt = cnt < k ? cnt : k;
-  new_taukey = (cnt >= k) ? kth : 0ull;  // 0 = "no threshold yet"
+  CompactOut o;
+  o.cnt = cnt < k ? cnt : k;
+  o.taukey = (cnt >= k) ? kth : 0ull;  // 0 = "no threshold yet"
+  return o;
 }
 
 struct RowState {
@@ -119,34 +126,90 @@ __device__ __forceinline__ float exact_score(float f) {
   return -__fsqrt_rn(fmaxf(-f, 0.0f));
 }
 
-// One chunk of CH filter values owned by this thread (fv(j): value of column col0+j, larger = better).
-// Fast path: one max-reduce + one compare.  Slow path: exact score, self handling, tie-aware key test,
-// append to the row's list.  The caller guarantees cnt <= L - CH on entry.
-template <int CH, bool kL2, class FV>
-__device__ __forceinline__ void select_chunk(RowState& st, FV fv, uint32_t col0, uint32_t ncols_valid,
-                                             uint32_t self_row, int self_mode, bool row_valid) {
-  float m = fv(0);
+// Slow path of the selection, shared by all kernels and NOT inlined (one compact loop instead of 32 unrolled,
+// predicated copies per call site).  The chunk's raw dot products were staged in shared memory by the caller:
+// value j of this row lives at sv[(j >> 2) * quad_stride + (j & 3)].  `mask` has bit j set when the filter value
+// of column col0 + j passed the cheap threshold test.  Returns the new list length.
+template <bool kL2>
+__device__ __noinline__ int append_hits(uint64_t* __restrict__ list, int cnt, uint64_t taukey, const float* sv,
+                                        int quad_stride, float qn, const float* __restrict__ gn, uint32_t mask,
+                                        uint32_t col0, uint32_t self_row, int self_mode) {
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    float f = sv[(j >> 2) * quad_stride + (j & 3)];
+    if (kL2) f = fmaf(2.0f, f, -(qn + gn[j]));
+    const uint32_t row = col0 + (uint32_t)j;
+    float s = exact_score<kL2>(f);
+    bool take = true;
+    if (row == self_row) {
+      if (self_mode == KNN_SELF_EXCLUDE) take = false;
+      else if (self_mode == KNN_SELF_MINUS1) s = -1.0f;
+    }
+    const uint64_t key = make_key(s, row);
+    if (take && key > taukey) {
+      __stcg(list + cnt, key);
+      ++cnt;
+    }
+  }
+  return cnt;
+}
+
+// Max of 32 values as a shallow tree of 3-input maxima (FMNMX3): 16 instructions, depth 4.
+template <class FV>
+__device__ __forceinline__ float chunk_max32(FV fv) {
+  float t[11];
 #pragma unroll
-  for (int j = 1; j < CH; ++j) m = fmaxf(m, fv(j));
+  for (int i = 0; i < 10; ++i) t[i] = fmaxf(fmaxf(fv(3 * i), fv(3 * i + 1)), fv(3 * i + 2));
+  t[10] = fmaxf(fv(30), fv(31));
+  const float a = fmaxf(fmaxf(t[0], t[1]), t[2]), b = fmaxf(fmaxf(t[3], t[4]), t[5]);
+  const float c = fmaxf(fmaxf(t[6], t[7]), t[8]), d = fmaxf(t[9], t[10]);
+  return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+// Bit j set iff fv(j) >= ftau and column j is valid.
+template <class FV>
+__device__ __forceinline__ uint32_t chunk_mask32(FV fv, float ftau, uint32_t ncols_valid) {
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mask |= (fv(j) >= ftau) ? (1u << j) : 0u;
+  return ncols_valid >= 32 ? mask : (mask & ((1u << ncols_valid) - 1u));
+}
+
+// One chunk of 32 filter values owned by this thread (fv(j): value of column col0+j, larger = better) whose raw
+// dot products are ALSO available in memory (sv/quad_stride, see append_hits).  Fast path: max tree + compare.
+template <bool kL2, class FV>
+__device__ __forceinline__ void select_chunk_mem(RowState& st, FV fv, const float* sv, int quad_stride, float qn,
+                                                 const float* gn, uint32_t col0, uint32_t ncols_valid,
+                                                 uint32_t self_row, int self_mode, bool row_valid) {
+  const float m = chunk_max32(fv);
+  if (row_valid && m >= st.ftau) {
+    const uint32_t mask = chunk_mask32(fv, st.ftau, ncols_valid);
+    if (mask) st.cnt = append_hits<kL2>(st.list, st.cnt, st.taukey, sv, quad_stride, qn, gn, mask, col0, self_row, self_mode);
+  }
+}
+
+// Same for a chunk held in REGISTERS (tcgen05.ld output): on the slow path the 32 raw dot products are first
+// staged in this thread's private slice of a shared-memory scratch area laid out [8 quads][128 threads] float4
+// (conflict-free STS.128), so append_hits can index them dynamically.  `dump` points at this thread's float4 slot 0.
+constexpr int kDumpQuadStride = 128 * 4;                 // floats between consecutive quads of one thread
+constexpr int kDumpBytes = 8 * 128 * 16;                 // 16 KB per 128 row-owner threads
+template <bool kL2>
+__device__ __forceinline__ void select_chunk_regs(RowState& st, const uint32_t (&v)[32], float* dump, float qn,
+                                                  const float* gn, uint32_t col0, uint32_t ncols_valid,
+                                                  uint32_t self_row, int self_mode, bool row_valid) {
+  auto fv = [&](int j) -> float {
+    const float dot = __uint_as_float(v[j]);
+    if (kL2) return fmaf(2.0f, dot, -(qn + gn[j]));
+    return dot;
+  };
+  const float m = chunk_max32(fv);
   if (row_valid && m >= st.ftau) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const float f = fv(j);
-      if (f >= st.ftau && (uint32_t)j < ncols_valid) {
-        const uint32_t row = col0 + (uint32_t)j;
-        float s = exact_score<kL2>(f);
-        bool take = true;
-        if (row == self_row) {
-          if (self_mode == KNN_SELF_EXCLUDE) take = false;
-          else if (self_mode == KNN_SELF_MINUS1) s = -1.0f;
-        }
-        const uint64_t key = make_key(s, row);
-        if (take && key > st.taukey) {
-          __stcg(st.list + st.cnt, key);
-          st.cnt++;
-        }
-      }
-    }
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(dump + q * kDumpQuadStride) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    const uint32_t mask = chunk_mask32(fv, st.ftau, ncols_valid);
+    if (mask) st.cnt = append_hits<kL2>(st.list, st.cnt, st.taukey, dump, kDumpQuadStride, qn, gn, mask, col0, self_row, self_mode);
   }
 }
 
@@ -162,9 +225,10 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
     need &= need - 1;
     uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
     const int rc = __shfl_sync(kFullMask, st.cnt, r);
-    int nc; uint64_t nk;
     __syncwarp();
-    compact_row<E>(rl, rc, k, k, lane, nc, nk);
+    const CompactOut co = compact_row<E>(rl, rc, k, k, lane);
+    const int nc = co.cnt;
+    const uint64_t nk = co.taukey;
     if (lane == r) {
       st.cnt = nc;
       if (nk > st.taukey) {
@@ -189,8 +253,9 @@ __device__ __forceinline__ void warp_finalize(RowState& st, int k, int kp, int l
     const int rc = __shfl_sync(kFullMask, st.cnt, r);
     const int rv = __shfl_sync(kFullMask, (int)row_valid, r);
     if (!rv) continue;
-    int nc; uint64_t nk;
-    compact_row<E>(rl, rc, k, kp, lane, nc, nk);
+    const CompactOut co = compact_row<E>(rl, rc, k, kp, lane);
+    const int nc = co.cnt;
+    const uint64_t nk = co.taukey;
     if (lane == r) {
       st.cnt = nc;
       if (nk > st.taukey) {
@@ -204,6 +269,18 @@ __device__ __forceinline__ void warp_finalize(RowState& st, int k, int kp, int l
 }
 
 // Pull the shared threshold (other CTAs working on the same query row may have tightened it).
+// Split in two so the L2 round trip of the load can be hidden behind a barrier wait: o = peek_tau(); ...; apply_tau(o).
+__device__ __forceinline__ uint32_t peek_tau(const uint32_t* __restrict__ tau_global_row) {
+  return tau_global_row ? __ldcg(tau_global_row) : 0u;
+}
+template <bool kL2>
+__device__ __forceinline__ void apply_tau(RowState& st, uint32_t o) {
+  if (o != 0u && ord2f(o) > st.tau) {
+    st.tau = ord2f(o);
+    st.ftau = filter_tau<kL2>(st.tau);
+    st.taukey = (uint64_t)o << 32;
+  }
+}
 template <bool kL2>
 __device__ __forceinline__ void refresh_tau(RowState& st, const uint32_t* __restrict__ tau_global_row) {
   if (!tau_global_row) return;
