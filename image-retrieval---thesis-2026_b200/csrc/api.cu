@@ -45,12 +45,17 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int dtype, int k) {
   g.L = 2 * g.kp;
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
-  if (dtype == KNN_BF16 && (g.qblocks & 1)) g.qblocks += 1;  // CTA pairs own 256 query rows
+  // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernel); a single block
+  // (small-batch, HBM-bound regime) runs on the one-CTA kernel where every SM streams its own gallery tiles
+  if (dtype == KNN_BF16 && g.qblocks > 1 && (g.qblocks & 1)) g.qblocks += 1;
   const int tile = dtype == KNN_BF16 ? bf16_tile_cols() : 128;
   const int64_t ntiles = (ng + tile - 1) / tile;
   const int sms = sm_count();
   const int per_sm = dtype == KNN_BF16 ? 1 : 2;
-  int64_t want = ((int64_t)4 * sms * per_sm + g.qblocks - 1) / g.qblocks;   // ~4 waves
+  // ~4 waves balance the tail when many query blocks share the machine; a single query block (HBM-bound
+  // streaming) gets 2 waves: every extra split adds KP candidate slots per query to the final merge
+  const int waves = g.qblocks <= 2 ? 2 : 4;
+  int64_t want = ((int64_t)waves * sms * per_sm + g.qblocks - 1) / g.qblocks;
   const int64_t fill = ((int64_t)sms * per_sm + g.qblocks - 1) / g.qblocks;  // one full wave
   int64_t by_len = ntiles / 8;                                               // >= 8 tiles per unit
   if (by_len < fill) by_len = fill;
@@ -66,6 +71,8 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int dtype, int k) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+constexpr int64_t kSeedRows = 4096;  // gallery prefix scanned by the threshold-seeding pre-pass
+
 }  // namespace knn
 
 using namespace knn;
@@ -78,7 +85,8 @@ extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype,
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, dtype, k);
   const size_t tau = align_up((size_t)g.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
-  const size_t lists = (size_t)(g.splits > 0 ? g.splits : 1) * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
+  // +1 unit row: scratch lists of the threshold-seeding pre-pass
+  const size_t lists = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
   return tau + lists;
 }
 
@@ -140,6 +148,19 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   if (geo.splits > 0) {
     KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
     if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
+    // Threshold seeding: a pre-pass over the first kSeedRows gallery rows leaves its k-th best score in
+    // tau_global (a valid lower bound of the final k-th best); the main pass then starts with a ~k/kSeedRows
+    // pass rate instead of accepting everything until each list has filled up.  Its candidate lists go to a
+    // scratch unit and are discarded (the main pass visits those rows again).
+    if (ng >= 8 * kSeedRows) {
+      SearchParams ps = p;
+      ps.ng = kSeedRows;
+      ps.splits = 1;
+      ps.split_len = kSeedRows;
+      ps.lists = p.lists + (size_t)geo.splits * geo.qblocks * kRowsPerUnit * (size_t)geo.L;
+      rc = (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
+      if (rc != KNN_OK) return rc;
+    }
     rc = (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
     if (rc != KNN_OK) return rc;
   } else if (prof) {

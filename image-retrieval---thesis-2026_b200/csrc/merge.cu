@@ -46,25 +46,63 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   const int64_t M = (int64_t)p.splits * kp;
   const bool l2 = p.metric == KNN_L2;
 
-  for (int i = threadIdx.x; i < kp; i += blockDim.x) s[i] = 0ull;
-  int64_t consumed = 0;
-  do {
-    const int64_t left = M - consumed;
-    const int take = (int)(left < (kSortCap - kp) ? left : (kSortCap - kp));
-    const int n = pow2_ge(kp + take);
-    for (int i = threadIdx.x; i < n - kp; i += blockDim.x) {
-      uint64_t key = 0ull;
-      if (i < take) {
-        const int64_t c = consumed + i;
+  // Pre-filter with the shared threshold: tau_global[r] is the best k-th-best score any unit reached, a lower
+  // bound of the final k-th best, so only keys with score >= it can be in the answer (typically k + a few
+  // out of splits * KP slots).  Survivors are compacted into shared memory and sorted once.
+  __shared__ int n_surv;
+  const uint64_t thr_key = (uint64_t)__ldcg(p.tau_global + r) << 32;
+  if (threadIdx.x == 0) n_surv = 0;
+  __syncthreads();
+  constexpr int kBatch = 8;  // independent loads in flight per thread (the lists are L2/HBM resident)
+  for (int64_t c0 = threadIdx.x; c0 < M; c0 += (int64_t)blockDim.x * kBatch) {
+    uint64_t keys[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const int64_t c = c0 + (int64_t)b * blockDim.x;
+      keys[b] = 0ull;
+      if (c < M) {
         const int sp = (int)(c / kp), j = (int)(c % kp);
-        key = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
+        keys[b] = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
       }
-      s[kp + i] = key;
     }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      if (keys[b] != 0ull && keys[b] >= thr_key) {
+        const int slot = atomicAdd(&n_surv, 1);
+        if (slot < kSortCap) s[slot] = keys[b];
+      }
+    }
+  }
+  __syncthreads();
+  const int ns = n_surv;
+  if (ns <= kSortCap) {
+    const int n = pow2_ge(ns > p.k ? ns : p.k);
+    for (int i = ns + threadIdx.x; i < n; i += blockDim.x) s[i] = 0ull;
     __syncthreads();
     smem_bitonic(s, n, 2, n, n, 0);
-    consumed += take;
-  } while (consumed < M);
+  } else {
+    // fallback (no usable threshold, e.g. every split saw fewer than k rows): rounds of sort-and-keep-best
+    __syncthreads();
+    for (int i = threadIdx.x; i < kp; i += blockDim.x) s[i] = 0ull;
+    int64_t consumed = 0;
+    do {
+      const int64_t left = M - consumed;
+      const int take = (int)(left < (kSortCap - kp) ? left : (kSortCap - kp));
+      const int n = pow2_ge(kp + take);
+      for (int i = threadIdx.x; i < n - kp; i += blockDim.x) {
+        uint64_t key = 0ull;
+        if (i < take) {
+          const int64_t c = consumed + i;
+          const int sp = (int)(c / kp), j = (int)(c % kp);
+          key = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
+        }
+        s[kp + i] = key;
+      }
+      __syncthreads();
+      smem_bitonic(s, n, 2, n, n, 0);
+      consumed += take;
+    } while (consumed < M);
+  }
 
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
     const uint64_t key = s[j];

@@ -276,7 +276,7 @@ int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
     set_error("bf16 search needs 16-byte aligned q and g");
     return KNN_E_INVALID;
   }
-  if (!single) return launch_search_bf16_pair(p, stream);
+  if (!single && (p.qblocks % 2) == 0) return launch_search_bf16_pair(p, stream);
   switch (p.kp) {
     case 32: return launch_e<2>(p, stream);
     case 64: return launch_e<4>(p, stream);
