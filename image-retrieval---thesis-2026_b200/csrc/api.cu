@@ -1,5 +1,6 @@
 // C-ABI entry points: argument validation, work decomposition, workspace carving, launches.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -35,41 +36,82 @@ static int sm_count() {
   return sms;
 }
 
+// Which bf16 kernel serves a problem.  The shared-memory-A kernels (search_tc.cu, search_tc2.cu) are the default;
+// the TMEM-resident-query kernel (search_ts.cu) is kept as a measured alternative, KNN_BF16_TS=1 selects it
+// (d <= 768 only).  Measured on B200 (20M x 512 gallery, 8192 queries): N = 128 tiles cost it ~9 %, see DESIGN.md.
+static bool use_ts(int dtype, int d) {
+  static const bool on = [] {
+    const char* e = getenv("KNN_BF16_TS");
+    return e != nullptr && e[0] == '1';
+  }();
+  return dtype == KNN_BF16 && on && ts_tile_cols(d) > 0;
+}
+
 // Work decomposition: a unit = (128-query block, gallery split).  Splits are contiguous gallery ranges,
-// multiples of the column tile; their number fills the 148 SMs for a few waves while keeping every unit
-// at least a handful of tiles long.  Query block is the fast grid index so concurrently resident CTAs
-// walk the SAME gallery range (L2 reuse of the gallery stream).
-static SearchGeom make_geom(int64_t nq, int64_t ng, int dtype, int k) {
+// multiples of the column tile.  Query block is the fast grid index so concurrently resident CTAs walk the SAME
+// gallery range (L2 reuse of the gallery stream).  Units all take the same time and CTAs are scheduled in order,
+// so the number of splits is chosen to make qblocks * splits fill WHOLE waves of the machine: between one wave
+// and ~4 waves' worth of splits, the count with the best (work / waves) efficiency wins (8192 queries on 148 SMs:
+// 37 splits = 16 full waves instead of 10 splits = 4.32 waves).
+static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   SearchGeom g;
   g.kp = kpad_for(k);
   g.L = 2 * g.kp;
+  g.groups = use_ts(dtype, d) ? 2 : 1;
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
-  // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernel); a single block
-  // (small-batch, HBM-bound regime) runs on the one-CTA kernel where every SM streams its own gallery tiles
+  // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernels); a single block
+  // (small-batch, HBM-bound regime) runs one CTA per unit: every SM streams its own gallery tiles
   if (dtype == KNN_BF16 && g.qblocks > 1 && (g.qblocks & 1)) g.qblocks += 1;
-  const int tile = dtype == KNN_BF16 ? bf16_tile_cols() : 128;
+  const int tile = dtype == KNN_BF16 ? (g.groups == 2 ? ts_tile_cols(d) : bf16_tile_cols()) : 128;
   const int64_t ntiles = (ng + tile - 1) / tile;
-  const int sms = sm_count();
-  const int per_sm = dtype == KNN_BF16 ? 1 : 2;
-  // ~4 waves balance the tail when many query blocks share the machine; a single query block (HBM-bound
-  // streaming) gets 2 waves: every extra split adds KP candidate slots per query to the final merge
-  const int waves = g.qblocks <= 2 ? 2 : 4;
-  int64_t want = ((int64_t)waves * sms * per_sm + g.qblocks - 1) / g.qblocks;
-  const int64_t fill = ((int64_t)sms * per_sm + g.qblocks - 1) / g.qblocks;  // one full wave
-  int64_t by_len = ntiles / 8;                                               // >= 8 tiles per unit
-  if (by_len < fill) by_len = fill;
-  if (want > by_len) want = by_len;
-  if (want > ntiles) want = ntiles;
-  if (want > 2048) want = 2048;
-  if (want < 1) want = 1;
-  const int64_t tiles_per_split = ntiles > 0 ? (ntiles + want - 1) / want : 1;
+  const int64_t slots = (int64_t)sm_count() * (dtype == KNN_BF16 ? 1 : 2);  // co-resident CTAs
+  static const int env_waves = [] {
+    const char* e = getenv("KNN_WAVES");
+    return e ? atoi(e) : 0;
+  }();
+  // a single query block (HBM-bound streaming) gets ~2 waves: every extra split adds KP candidate slots per
+  // query to the final merge; many query blocks get up to ~4 waves' worth of splits
+  const int waves = env_waves > 0 ? env_waves : (g.qblocks <= 2 ? 2 : 4);
+  int64_t hi = ((int64_t)waves * slots + g.qblocks - 1) / g.qblocks;
+  int64_t lo = (slots + g.qblocks - 1) / g.qblocks;                    // one full wave
+  const int64_t min_tiles = (32 * 256) / tile;                          // >= 8192 gallery rows per unit
+  int64_t by_len = ntiles / min_tiles;
+  if (by_len < lo) by_len = lo;
+  if (hi > by_len) hi = by_len;
+  if (hi > ntiles) hi = ntiles;
+  if (hi > 2048) hi = 2048;
+  if (hi < 1) hi = 1;
+  if (lo > hi) lo = hi;
+  int64_t best = hi;
+  double best_eff = -1.0;
+  for (int64_t s = hi; s >= lo && ntiles > 0; --s) {  // ties -> more splits (smaller tail in absolute time)
+    const int64_t tps = (ntiles + s - 1) / s;
+    const int64_t real = (ntiles + tps - 1) / tps;   // splits actually used
+    const int64_t ctas = real * g.qblocks;
+    const int64_t nw = (ctas + slots - 1) / slots;
+    // time ~ waves * tiles-per-split; work ~ ntiles * qblocks / slots
+    const double eff = (double)ntiles * g.qblocks / ((double)nw * slots * tps);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  const int64_t tiles_per_split = ntiles > 0 ? (ntiles + best - 1) / best : 1;
   g.split_len = tiles_per_split * tile;
   g.splits = ntiles > 0 ? (int)((ntiles + tiles_per_split - 1) / tiles_per_split) : 0;
   return g;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+unsigned long long* debug_stats_buffer() {
+  static unsigned long long* buf = [] {
+    const char* e = getenv("KNN_PAIR_STATS");
+    unsigned long long* b = nullptr;
+    if (e && e[0] == '1' && cudaMalloc(&b, 32 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(b, 0, 32 * sizeof(unsigned long long));
+    return b;
+  }();
+  return buf;
+}
 
 constexpr int64_t kSeedRows = 4096;  // gallery prefix scanned by the threshold-seeding pre-pass
 
@@ -81,12 +123,11 @@ extern "C" int knn_version(void) { return KNN_ABI_VERSION; }
 extern "C" const char* knn_last_error(void) { return g_err; }
 
 extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
-  (void)d;
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
-  const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, dtype, k);
+  const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
   const size_t tau = align_up((size_t)g.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
-  // +1 unit row: scratch lists of the threshold-seeding pre-pass
-  const size_t lists = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
+  // +1 split: scratch lists of the threshold-seeding pre-pass
+  const size_t lists = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.groups * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
   return tau + lists;
 }
 
@@ -125,7 +166,8 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   }
   KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const SearchGeom geo = make_geom(nq, ng, dtype, k);
+  const SearchGeom geo = make_geom(nq, ng, d, dtype, k);
+  const bool ts = geo.groups == 2;
 
   SearchParams p;
   memset(&p, 0, sizeof(p));
@@ -133,7 +175,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.nq = nq; p.ng = ng; p.d = d; p.k = k; p.kp = geo.kp;
   p.metric = metric; p.self_mode = self_mode;
   p.self_offset = self_offset - index_base;
-  p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks;
+  p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
   const size_t tau_bytes = align_up((size_t)geo.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
   p.tau_global = reinterpret_cast<uint32_t*>(workspace);
   p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + tau_bytes);
@@ -157,11 +199,13 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
       ps.ng = kSeedRows;
       ps.splits = 1;
       ps.split_len = kSeedRows;
-      ps.lists = p.lists + (size_t)geo.splits * geo.qblocks * kRowsPerUnit * (size_t)geo.L;
-      rc = (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
+      ps.lists = p.lists + (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit * (size_t)geo.L;
+      rc = ts ? launch_search_bf16_ts(ps, s)
+              : (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
       if (rc != KNN_OK) return rc;
     }
-    rc = (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
+    rc = ts ? launch_search_bf16_ts(p, s)
+            : (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
     if (rc != KNN_OK) return rc;
   } else if (prof) {
     KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
@@ -196,6 +240,18 @@ extern "C" int knn_profile_last(float* distance_ms, float* merge_ms) {
   return KNN_OK;
 }
 
+extern "C" int knn_debug_stats(unsigned long long* out32, int reset) {
+  unsigned long long* b = debug_stats_buffer();
+  if (!b) {
+    set_error("knn_debug_stats: diagnostics are off (set KNN_PAIR_STATS=1 before the first search)");
+    return KNN_E_INVALID;
+  }
+  KNN_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out32) KNN_CHECK_CUDA(cudaMemcpy(out32, b, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) KNN_CHECK_CUDA(cudaMemset(b, 0, 32 * sizeof(unsigned long long)));
+  return KNN_OK;
+}
+
 extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
                                 int64_t nq, int64_t ng, int d, int dtype, int metric, int self_mode,
                                 int64_t self_offset, float* out, void* stream) {
@@ -212,6 +268,7 @@ extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqn
   p.q = q; p.g = g; p.qsq = q_sqnorm; p.gsq = g_sqnorm;
   p.nq = nq; p.ng = ng; p.d = d; p.k = 1; p.kp = 32;
   p.metric = metric; p.self_mode = self_mode; p.self_offset = self_offset;
+  p.groups = 1;
   p.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   const int64_t ntiles = (ng + 127) / 128;
   int64_t want = ((int64_t)2 * sm_count() + p.qblocks - 1) / p.qblocks;

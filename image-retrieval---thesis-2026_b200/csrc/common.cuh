@@ -74,6 +74,7 @@ constexpr int kMaxFusedK = 256;  // larger k goes through the dense + rank path
 struct SearchGeom {
   int qblocks;        // ceil(nq / 128)
   int splits;         // gallery splits S
+  int groups;         // candidate lists per (split, row)
   int64_t split_len;  // gallery rows per split (multiple of the column tile)
   int kp;             // padded k
   int L;              // list capacity per row

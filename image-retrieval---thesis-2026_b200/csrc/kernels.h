@@ -19,8 +19,9 @@ struct SearchParams {
   int64_t self_offset;  // LOCAL gallery row of query 0 (query i is local row self_offset + i)
   int64_t split_len;    // gallery rows per split
   int splits;
+  int groups;            // candidate lists per (split, row): 2 for the TMEM-resident kernel, else 1
   int qblocks;
-  uint64_t* lists;       // [splits][qblocks][128][2*kp] candidate keys
+  uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
   float* dense_out;      // dense mode only
 };
@@ -28,7 +29,12 @@ struct SearchParams {
 int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream);
 int launch_search_bf16(const SearchParams& p, cudaStream_t stream);       // dispatch (pair kernel by default)
 int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream);  // cta_group::2, csrc/search_tc2.cu
-int bf16_tile_cols();  // gallery rows per tile of the tcgen05 kernel
+int bf16_tile_cols();  // gallery rows per tile of the shared-memory-A tcgen05 kernels
+int launch_search_bf16_ts(const SearchParams& p, cudaStream_t stream);    // query tile in TMEM, csrc/search_ts.cu
+int ts_tile_cols(int d);  // gallery rows per tile of the TMEM-resident kernel, 0 = d does not fit
+
+// Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
+unsigned long long* debug_stats_buffer();
 
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
                        cudaStream_t stream);

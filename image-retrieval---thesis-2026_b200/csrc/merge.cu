@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   const int64_t r = blockIdx.x;
   const int qb = (int)(r / kRowsPerUnit), lr = (int)(r % kRowsPerUnit);
   const int kp = p.kp, L = 2 * p.kp;
-  const int64_t M = (int64_t)p.splits * kp;
+  const int64_t M = (int64_t)p.splits * p.groups * kp;  // (split, group) pairs are laid out as virtual splits
   const bool l2 = p.metric == KNN_L2;
 
   // Pre-filter with the shared threshold: tau_global[r] is the best k-th-best score any unit reached, a lower

@@ -48,7 +48,7 @@ constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * STAGE
 template <int E, bool kL2>
 __global__ void __launch_bounds__(kThreads, 1)
 search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
-                   SearchParams p) {
+                   SearchParams p, unsigned long long* stats, int debug, int prefetch) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;                                       // [kStages][128][64] bf16, swizzled
@@ -92,10 +92,22 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
+      int pf_t = prefetch / nkb, pf_kb = prefetch % nkb;
+      if (prefetch > 0) {
+        for (int i = 0; i < prefetch && i < ntiles * nkb; ++i)
+          ptx::tma_prefetch_2d(&tmap_g, (i % nkb) * BKE, (int32_t)(c_begin + (int64_t)(i / nkb) * TN));
+      }
       for (int t = 0; t < ntiles; ++t) {
         const int32_t col0 = (int32_t)(c_begin + (int64_t)t * TN);
         for (int kb = 0; kb < nkb; ++kb) {
+          if (prefetch > 0) {
+            if (pf_t < ntiles) ptx::tma_prefetch_2d(&tmap_g, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN));
+            if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
+          }
+          const long long c0 = stats ? clock64() : 0;
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          if (stats) w_empty += clock64() - c0;
           ptx::mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
           ptx::tma_load_2d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_q, &bars->full[stage], kb * BKE,
                            (int32_t)row0, ptx::kEvictLast);
@@ -104,6 +116,7 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (stats) atomicAdd(stats + 7, (unsigned long long)w_empty);
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
@@ -111,27 +124,41 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       constexpr uint32_t idesc = ptx::make_idesc_bf16(TM, TN);
       int stage = 0;
       uint32_t phase = 0;
+      long long w_tmem = 0, w_full = 0;
+      const long long m_begin = stats ? clock64() : 0;
       for (int t = 0; t < ntiles; ++t) {
         const int as = t & 1;
         const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+        long long c0 = stats ? clock64() : 0;
         ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        if (stats) w_tmem += clock64() - c0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TN);
         for (int kb = 0; kb < nkb; ++kb) {
+          c0 = stats ? clock64() : 0;
           ptx::mbar_wait(&bars->full[stage], phase);
+          if (stats) w_full += clock64() - c0;
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES);
+          if (!(debug & 1)) {
 #pragma unroll
-          for (int k = 0; k < BKE / UMMA_K; ++k) {
-            const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr + k * UMMA_K * 2);
-            const uint64_t db = ptx::make_sw128_kmajor_desc(b_addr + k * UMMA_K * 2);
-            ptx::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BKE / UMMA_K; ++k) {
+              const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr + k * UMMA_K * 2);
+              const uint64_t db = ptx::make_sw128_kmajor_desc(b_addr + k * UMMA_K * 2);
+              ptx::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::tc_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         ptx::tc_commit(&bars->tmem_full[as]);   // accumulator tile complete
+      }
+      if (stats) {
+        atomicAdd(stats + 0, (unsigned long long)(clock64() - m_begin));
+        atomicAdd(stats + 1, (unsigned long long)w_tmem);
+        atomicAdd(stats + 2, (unsigned long long)w_full);
+        atomicAdd(stats + 8, 1ull);
       }
     }
   } else {
@@ -153,6 +180,9 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tau_row = p.tau_global + row0 + rloc;
     }
     const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    long long e_wait = 0, e_slow = 0;
+    unsigned long long n_slow = 0;
+    const long long e_begin = stats ? clock64() : 0;
 
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
@@ -169,7 +199,9 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       refresh_tau<kL2>(st, tau_row);
+      const long long cw = stats ? clock64() : 0;
       ptx::mbar_wait(&bars->tmem_full[as], aphase);
+      if (stats) e_wait += clock64() - cw;
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
 #pragma unroll 1
@@ -180,15 +212,31 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int64_t cg = col0 + cb;
         const int64_t rem = c_end - cg;
         const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
+        const int cnt0 = st.cnt;
+        const long long c0 = stats ? clock64() : 0;
         select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
-                               row_valid);
+                               row_valid && !(debug & 2));
         warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+        if (stats && __any_sync(kFullMask, st.cnt != cnt0)) {
+          e_slow += clock64() - c0;
+          ++n_slow;
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[as]);
     }
+    if (stats && lane == 0) {
+      atomicAdd(stats + 3, (unsigned long long)(clock64() - e_begin));
+      atomicAdd(stats + 4, (unsigned long long)e_wait);
+      atomicAdd(stats + 5, (unsigned long long)e_slow);
+      atomicAdd(stats + 6, n_slow);
+      atomicAdd(stats + 9, 1ull);
+      atomicAdd(stats + 10, (unsigned long long)ntiles * (TN / 32));
+    }
+    const long long cf = stats ? clock64() : 0;
     warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
+    if (stats && lane == 0) atomicAdd(stats + 11, (unsigned long long)(clock64() - cf));
   }
 
   ptx::tc_fence_before();
@@ -238,6 +286,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int d, int 
   return KNN_OK;
 }
 
+int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
 template <int E>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
   CUtensorMap tq, tg;
@@ -249,11 +302,11 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   if (p.metric == KNN_L2) {
     auto kern = search_bf16_kernel<E, true>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, debug_stats_buffer(), env_int("KNN_TC_DEBUG"), env_int("KNN_TC_PREFETCH"));
   } else {
     auto kern = search_bf16_kernel<E, false>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, debug_stats_buffer(), env_int("KNN_TC_DEBUG"), env_int("KNN_TC_PREFETCH"));
   }
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;

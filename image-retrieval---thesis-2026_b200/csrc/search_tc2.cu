@@ -50,13 +50,18 @@ struct PairCfg {
   uint32_t a_bytes;      // resident A region
   uint32_t stage_bytes;  // bytes per ring stage in ONE CTA (B half [+ A k-block when streaming])
   int debug;             // measurement knob (KNN_PAIR_DEBUG=1): the epilogue skips the selection (results are
-                         // garbage; isolates the TMA + MMA pipeline in timing experiments)
+                         // garbage; isolates the TMA + MMA pipeline in timing experiments); 2 = fast path only
+  int prefetch;          // L2 prefetch distance of the gallery stream in k-blocks (0 = off)
+  unsigned long long* stats;  // diagnostics (KNN_PAIR_STATS=1): stall-cycle counters, see knn_debug_stats()
 };
 
-template <int E, bool kL2>
+// kDiag = false is the production build: the stall counters and timing-experiment switches compile away.
+template <int E, bool kL2, bool kDiag>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                         SearchParams p, PairCfg cfg) {
+  const bool stats_on = kDiag && cfg.stats != nullptr;
+  const int debug = kDiag ? cfg.debug : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;                                    // resident A: [nkb][128][64] bf16 (swizzled)
   uint8_t* ring = smem + cfg.a_bytes;                        // [stages][stage_bytes]
@@ -105,6 +110,8 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
+    // One thread; a single thread's dependent instruction stream costs ~5 cycles per instruction, so the loop
+    // body is kept to a handful of instructions per slot (addresses advance by adds, nothing is recomputed).
     if (lane == 0) {
       if (cfg.resident) {
         const uint32_t a_full_leader = ptx::mapa(ptx::smem_u32(&bars->a_full), 0);
@@ -116,24 +123,45 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const int32_t col0 = (int32_t)(c_begin + (int64_t)t * TN + (int64_t)rank * TNH);
+      long long w_empty = 0;
+      const uint32_t ring_u32 = ptx::smem_u32(ring);
+      const uint32_t full0 = ptx::mapa(ptx::smem_u32(&bars->full[0]), 0);
+      const uint32_t tx_bytes = 2u * cfg.stage_bytes;
+      // L2 prefetch cursor: runs cfg.prefetch k-blocks ahead of the ring's loads (experiment knob, default off)
+      int pf_t = cfg.prefetch / nkb, pf_kb = cfg.prefetch % nkb;
+      if (cfg.prefetch > 0) {
+        for (int i = 0; i < cfg.prefetch && i < ntiles * nkb; ++i)
+          ptx::tma_prefetch_2d(&tmap_g, (i % nkb) * BKE,
+                               (int32_t)(c_begin + (int64_t)(i / nkb) * TN + (int64_t)rank * TNH));
+      }
+      int32_t col0 = (int32_t)(c_begin + (int64_t)rank * TNH);
+      for (int t = 0; t < ntiles; ++t, col0 += TN) {
         for (int kb = 0; kb < nkb; ++kb) {
+          if (cfg.prefetch > 0) {
+            if (pf_t < ntiles)
+              ptx::tma_prefetch_2d(&tmap_g, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
+            if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
+          }
+          const long long c0 = stats_on ? clock64() : 0;
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
-          uint8_t* st = ring + (size_t)stage * cfg.stage_bytes;
-          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
-          ptx::tma_load_2d_2sm(st, &tmap_g, full_leader, kb * BKE, col0, ptx::kEvictNormal);
+          if (stats_on) w_empty += clock64() - c0;
+          const uint32_t dst = ring_u32 + (uint32_t)stage * cfg.stage_bytes;
+          const uint32_t full_bar = full0 + (uint32_t)stage * 8u;
+          ptx::tma_load_2d_2sm_u32(dst, &tmap_g, full_bar, kb * BKE, col0, ptx::kEvictNormal);
           if (!cfg.resident)
-            ptx::tma_load_2d_2sm(st + KB_BYTES, &tmap_q, full_leader, kb * BKE, (int32_t)row0, ptx::kEvictLast);
-          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2u * cfg.stage_bytes);
-          else ptx::mbar_arrive_cluster(full_leader);
+            ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
+          if (leader) ptx::mbar_arrive_expect_tx_u32(full_bar, tx_bytes);
+          else ptx::mbar_arrive_cluster(full_bar);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (stats_on) atomicAdd(cfg.stats + 7, (unsigned long long)w_empty);
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (leader CTA, one thread)
-    if (leader && lane == 0) {
+    // ===================================================================== MMA issuer (leader CTA)
+    // The whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions.
+    // Per k-block: one try_wait, four MMAs whose descriptors differ by an immediate, one commit.
+    if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * TM, TN);
       if (cfg.resident) {
         ptx::mbar_wait(&bars->a_full, 0);
@@ -141,27 +169,47 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       int stage = 0;
       uint32_t phase = 0;
+      long long w_tmem = 0, w_full = 0;
+      const long long m_begin = stats_on ? clock64() : 0;
+      const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(ring));
+      const uint32_t b_step = cfg.stage_bytes >> 4;
+      const uint32_t a_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(smem_a));
+      uint32_t b_lo = b_lo0;
+      const bool issuer = ptx::elect_one();
       for (int t = 0; t < ntiles; ++t) {
         const int as = t & 1;
         const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+        long long c0 = stats_on ? clock64() : 0;
         ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        if (stats_on) w_tmem += clock64() - c0;
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        uint32_t a_res = a_lo0;
+        for (int kb = 0; kb < nkb; ++kb, a_res += KB_BYTES >> 4) {
+          c0 = stats_on ? clock64() : 0;
           ptx::mbar_wait(&bars->full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t b_addr = ptx::smem_u32(ring + (size_t)stage * cfg.stage_bytes);
-          const uint32_t a_addr = cfg.resident ? ptx::smem_u32(smem_a + (size_t)kb * KB_BYTES) : b_addr + KB_BYTES;
+          if (stats_on) w_full += clock64() - c0;
+          if (issuer) {
+            const uint32_t a_lo = cfg.resident ? a_res : b_lo + (KB_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BKE / UMMA_K; ++k) {
-            const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr + k * UMMA_K * 2);
-            const uint64_t db = ptx::make_sw128_kmajor_desc(b_addr + k * UMMA_K * 2);
-            ptx::mma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BKE / UMMA_K; ++k) {
+              const uint64_t da = ptx::sw128_desc(a_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+              const uint64_t db = ptx::sw128_desc(b_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+              ptx::mma_bf16_ss_2sm(tmem_d, da, db, idesc, (k != 0 || kb != 0) ? 1u : 0u);
+            }
+            ptx::tc_commit_2sm(&bars->empty[stage], 3);  // frees this slot in BOTH CTAs when the MMAs retire
           }
-          ptx::tc_commit_2sm(&bars->empty[stage], 3);  // frees this slot in BOTH CTAs when the MMAs retire
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          b_lo += b_step;
+          if (++stage == stages) { stage = 0; phase ^= 1; b_lo = b_lo0; }
         }
-        ptx::tc_commit_2sm(&bars->tmem_full[as], 3);   // accumulator tile complete (both CTAs' epilogues)
+        if (issuer) ptx::tc_commit_2sm(&bars->tmem_full[as], 3);  // accumulator tile complete (both epilogues)
+        __syncwarp();
+      }
+      if (stats_on && issuer) {
+        atomicAdd(cfg.stats + 0, (unsigned long long)(clock64() - m_begin));
+        atomicAdd(cfg.stats + 1, (unsigned long long)w_tmem);
+        atomicAdd(cfg.stats + 2, (unsigned long long)w_full);
+        atomicAdd(cfg.stats + 8, 1ull);
       }
     }
   } else {
@@ -183,6 +231,9 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tau_row = p.tau_global + row0 + rloc;
     }
     const int et = threadIdx.x - 64;
+    long long e_wait = 0, e_slow = 0;
+    unsigned long long n_slow = 0;
+    const long long e_begin = stats_on ? clock64() : 0;
 
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
@@ -199,10 +250,12 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       const uint32_t tau_peek = peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
+      const long long cw = stats_on ? clock64() : 0;
       ptx::mbar_wait(&bars->tmem_full[as], aphase);
+      if (stats_on) e_wait += clock64() - cw;
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
-      if (cfg.debug != 1) {
+      if (debug != 1) {
         // software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is examined
         uint32_t v0[32], v1[32];
         ptx::tmem_ld_32x32(taddr, v0);
@@ -212,9 +265,22 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const int64_t cg = col0 + cb;
           const int64_t rem = c_end - cg;
           const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
-          select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
-                                 row_valid);
-          warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+          if (stats_on) {
+            // diagnostics build of the same step: time the chunks in which any lane left the fast path
+            const int cnt0 = st.cnt;
+            const long long c0 = clock64();
+            select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
+                                   row_valid && debug != 2);
+            warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+            if (__any_sync(kFullMask, st.cnt != cnt0)) {
+              e_slow += clock64() - c0;
+              ++n_slow;
+            }
+          } else {
+            select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
+                                   row_valid && debug != 2);
+            warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
+          }
         };
 #pragma unroll 1
         for (int cb = 0; cb < TN; cb += 64) {
@@ -233,7 +299,17 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
       }
     }
+    if (stats_on && lane == 0) {
+      atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));
+      atomicAdd(cfg.stats + 4, (unsigned long long)e_wait);
+      atomicAdd(cfg.stats + 5, (unsigned long long)e_slow);
+      atomicAdd(cfg.stats + 6, n_slow);
+      atomicAdd(cfg.stats + 9, 1ull);
+      atomicAdd(cfg.stats + 10, (unsigned long long)ntiles * (TN / 32));
+    }
+    const long long cf = stats_on ? clock64() : 0;
     warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
+    if (stats_on && lane == 0) atomicAdd(cfg.stats + 11, (unsigned long long)(clock64() - cf));
   }
 
   ptx::tc_fence_before();
@@ -300,6 +376,9 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   cfg.stages = stages > kMaxStages ? kMaxStages : stages;
   cfg.debug = 0;
   if (const char* e = getenv("KNN_PAIR_DEBUG")) cfg.debug = atoi(e);
+  cfg.stats = debug_stats_buffer();
+  cfg.prefetch = 0;
+  if (const char* e = getenv("KNN_PAIR_PREFETCH")) cfg.prefetch = atoi(e);
   if (const char* e = getenv("KNN_PAIR_STAGES")) {
     const int want = atoi(e);
     if (want >= 2 && want < cfg.stages) cfg.stages = want;
@@ -307,12 +386,17 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)cfg.a_bytes + (size_t)cfg.stages * cfg.stage_bytes + fixed;
 
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);  // qblocks is even: consecutive CTAs form the pair
+  const bool diag = cfg.stats != nullptr || cfg.debug != 0;
   if (p.metric == KNN_L2) {
-    auto kern = search_bf16_pair_kernel<E, true>;
+    auto kern = search_bf16_pair_kernel<E, true, false>;
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+  } else if (diag && E == 8) {  // diagnostics build exists for the k <= 128, similarity instantiation only
+    auto kern = search_bf16_pair_kernel<8, false, true>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
   } else {
-    auto kern = search_bf16_pair_kernel<E, false>;
+    auto kern = search_bf16_pair_kernel<E, false, false>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
   }

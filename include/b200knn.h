@@ -97,6 +97,10 @@ KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, in
  * the most recent knn_search call (measurement harness only; host pointers). */
 KNN_API int knn_profile_enable(int on);
 KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
+/* Diagnostics, off unless the process was started with KNN_PAIR_STATS=1: the tcgen05 kernels then add the cycles
+ * their TMA / MMA / selection roles spend waiting on each other to 32 device counters (layout: DESIGN.md
+ * "stall counters").  Synchronises the device, copies the counters to out32 (host), optionally clears them. */
+KNN_API int knn_debug_stats(unsigned long long* out32_host, int reset);
 
 /* Dense score matrix (small problems only; compatibility with callers that want the full `dists`
  * matrix of test.py:1080 / fusion_eval/metrics.py:15).  out [nq,ng] fp32, same score definition and

@@ -184,7 +184,13 @@ def test_nih_sized_gallery_subsample_vs_oracle(knn):
 
 # ------------------------------------------------------------------------------------------ bf16 tensor-core path
 @pytest.mark.parametrize("nq,ng,d,k", [(1, 256, 64, 10), (64, 5000, 768, 100), (200, 9000, 512, 100), (130, 777, 128, 50),
-                                       (8, 20000, 72, 32)])
+                                       (8, 20000, 72, 32),
+                                       # several splits + threshold-seeding pre-pass (ng >= 32768), CTA pairs
+                                       (300, 34000, 256, 100), (140, 33000, 768, 10),
+                                       # d > 768: query tile does not fit TMEM -> shared-memory-A kernels (1 and 2 CTAs)
+                                       (70, 3000, 1024, 20), (300, 3000, 1024, 20),
+                                       # d not a multiple of the 64-element k-block, k at the fused limit; tiny d
+                                       (33, 2000, 200, 256), (129, 1500, 8, 5)])
 @pytest.mark.parametrize("metric", ["cosine", "l2"])
 def test_bf16_recall_and_scores(knn, nq, ng, d, k, metric):
     rs = np.random.RandomState(nq + ng)
