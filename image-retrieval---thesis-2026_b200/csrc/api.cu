@@ -57,13 +57,15 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   SearchGeom g;
   g.kp = kpad_for(k);
   g.L = 2 * g.kp;
-  g.groups = use_ts(dtype, d) ? 2 : 1;
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
+  const bool ts = use_ts(dtype, d);
+  // the CTA-pair kernel and the TMEM-resident kernel run two selection threads (two lists) per row
+  g.groups = (dtype == KNN_BF16 && (ts || g.qblocks > 1)) ? 2 : 1;
   // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernels); a single block
   // (small-batch, HBM-bound regime) runs one CTA per unit: every SM streams its own gallery tiles
   if (dtype == KNN_BF16 && g.qblocks > 1 && (g.qblocks & 1)) g.qblocks += 1;
-  const int tile = dtype == KNN_BF16 ? (g.groups == 2 ? ts_tile_cols(d) : bf16_tile_cols()) : 128;
+  const int tile = dtype == KNN_BF16 ? (ts ? ts_tile_cols(d) : bf16_tile_cols()) : 128;
   const int64_t ntiles = (ng + tile - 1) / tile;
   const int64_t slots = (int64_t)sm_count() * (dtype == KNN_BF16 ? 1 : 2);  // co-resident CTAs
   static const int env_waves = [] {
@@ -113,7 +115,13 @@ unsigned long long* debug_stats_buffer() {
   return buf;
 }
 
-constexpr int64_t kSeedRows = 4096;  // gallery prefix scanned by the threshold-seeding pre-pass
+static int64_t seed_rows() {  // gallery prefix scanned by the threshold-seeding pre-pass (KNN_SEED_ROWS overrides)
+  static const int64_t v = [] {
+    const char* e = getenv("KNN_SEED_ROWS");
+    return e ? (int64_t)atoll(e) : (int64_t)4096;
+  }();
+  return v;
+}
 
 }  // namespace knn
 
@@ -167,7 +175,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const SearchGeom geo = make_geom(nq, ng, d, dtype, k);
-  const bool ts = geo.groups == 2;
+  const bool ts = use_ts(dtype, d);
 
   SearchParams p;
   memset(&p, 0, sizeof(p));
@@ -194,7 +202,8 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
     // tau_global (a valid lower bound of the final k-th best); the main pass then starts with a ~k/kSeedRows
     // pass rate instead of accepting everything until each list has filled up.  Its candidate lists go to a
     // scratch unit and are discarded (the main pass visits those rows again).
-    if (ng >= 8 * kSeedRows) {
+    const int64_t kSeedRows = seed_rows();
+    if (kSeedRows > 0 && ng >= 8 * kSeedRows) {
       SearchParams ps = p;
       ps.ng = kSeedRows;
       ps.splits = 1;

@@ -317,10 +317,6 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
 int bf16_tile_cols() { return TN; }
 
 int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
-  static const bool single = [] {
-    const char* e = getenv("KNN_BF16_SINGLE_CTA");  // A/B switch: 1 = the cta_group::1 kernel of this file
-    return e != nullptr && e[0] == '1';
-  }();
   if (p.d % 8 != 0) {
     set_error("bf16 search needs d %% 8 == 0 (TMA row pitch must be a multiple of 16 bytes), got d=%d", p.d);
     return KNN_E_UNSUPPORTED;
@@ -329,7 +325,7 @@ int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
     set_error("bf16 search needs 16-byte aligned q and g");
     return KNN_E_INVALID;
   }
-  if (!single && (p.qblocks % 2) == 0) return launch_search_bf16_pair(p, stream);
+  if (p.qblocks > 1) return launch_search_bf16_pair(p, stream);  // one query block: the one-CTA kernel below
   switch (p.kp) {
     case 32: return launch_e<2>(p, stream);
     case 64: return launch_e<4>(p, stream);

@@ -27,8 +27,9 @@ constexpr int BKE = 64;        // bf16 elements per k-block (128 B = one swizzle
 constexpr int UMMA_K = 16;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter: each row is owned by two threads (alternate chunks)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kMaxStages = 12;
 constexpr uint32_t KB_BYTES = TM * BKE * 2;  // 16 KB: one k-block of 128 rows (A half or B half)
 constexpr size_t kSmemBudget = 232448;       // 227 KB opt-in limit per CTA
@@ -38,7 +39,7 @@ struct alignas(8) PairBarriers {
   uint64_t empty[kMaxStages];       // every CTA: 1 arrival (multicast tcgen05.commit)
   uint64_t a_full;                  // leader only: resident query tile of both CTAs landed
   uint64_t tmem_full[kAccStages];   // every CTA: 1 arrival (multicast tcgen05.commit)
-  uint64_t tmem_empty[kAccStages];  // leader only: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint64_t tmem_empty[kAccStages];  // leader only: 16 arrivals (8 selection warps x 2 CTAs)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -65,8 +66,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;                                    // resident A: [nkb][128][64] bf16 (swizzled)
   uint8_t* ring = smem + cfg.a_bytes;                        // [stages][stage_bytes]
-  float* dump = reinterpret_cast<float*>(ring + (size_t)cfg.stages * cfg.stage_bytes);  // slow-path staging, 16 KB
-  float* gs = dump + kDumpBytes / 4;                                                     // [2][TN] (L2 metric)
+  float* gs = reinterpret_cast<float*>(ring + (size_t)cfg.stages * cfg.stage_bytes);    // [2][TN] (L2 metric)
   PairBarriers* bars = reinterpret_cast<PairBarriers*>(gs + kAccStages * TN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +95,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     ptx::mbar_init(&bars->a_full, 2);
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&bars->tmem_full[s], 1);
-      ptx::mbar_init(&bars->tmem_empty[s], 2 * kEpiThreads / 32);
+      ptx::mbar_init(&bars->tmem_empty[s], 2 * kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -213,14 +213,17 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else {
-    // ===================================================================== epilogue / selection (both CTAs)
+    // ===================================================================== selection (both CTAs, 8 warps)
+    // TMEM lane i = query row i is owned by TWO threads (warp groups 0 and 1) that take alternate 32-column
+    // chunks of every tile and keep separate candidate lists; the unit merge sees splits * 2 lists per row.
     constexpr int L = 32 * E;
+    const int grp = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int rloc = quarter * 32 + lane;
     const bool row_valid = row0 + rloc < p.nq;
-    const int64_t unit = (int64_t)sp * p.qblocks + qb;
+    const int64_t vunit = ((int64_t)sp * 2 + grp) * p.qblocks + qb;
     RowState st;
-    rowstate_init(st, p.lists + ((unit * TM + rloc) * (int64_t)L));
+    rowstate_init(st, p.lists + ((vunit * TM + rloc) * (int64_t)L));
     uint32_t self_row = 0xFFFFFFFFu;
     float qn = 0.f;
     uint32_t* tau_row = nullptr;
@@ -241,12 +244,9 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const int64_t col0 = c_begin + (int64_t)t * TN;
       float* gst = gs + as * TN;
       if (kL2) {
-#pragma unroll
-        for (int h = 0; h < TN / kEpiThreads; ++h) {
-          int64_t c = col0 + et + h * kEpiThreads;
-          if (c >= p.ng) c = p.ng - 1;
-          gst[et + h * kEpiThreads] = __ldg(p.gsq + c);
-        }
+        int64_t c = col0 + et;
+        if (c >= p.ng) c = p.ng - 1;
+        gst[et] = __ldg(p.gsq + c);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
       const uint32_t tau_peek = peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
@@ -254,50 +254,20 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       ptx::mbar_wait(&bars->tmem_full[as], aphase);
       if (stats_on) e_wait += clock64() - cw;
       ptx::tc_fence_after();
+      apply_tau<kL2>(st, tau_peek);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
-      if (debug != 1) {
-        // software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is examined
-        uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32(taddr, v0);
-        apply_tau<kL2>(st, tau_peek);
-        ptx::tmem_ld_fence(v0);
-        auto process = [&](const uint32_t (&v)[32], int cb) {
-          const int64_t cg = col0 + cb;
-          const int64_t rem = c_end - cg;
-          const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
-          if (stats_on) {
-            // diagnostics build of the same step: time the chunks in which any lane left the fast path
-            const int cnt0 = st.cnt;
-            const long long c0 = clock64();
-            select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
-                                   row_valid && debug != 2);
-            warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
-            if (__any_sync(kFullMask, st.cnt != cnt0)) {
-              e_slow += clock64() - c0;
-              ++n_slow;
-            }
-          } else {
-            select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
-                                   row_valid && debug != 2);
-            warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
-          }
-        };
-#pragma unroll 1
-        for (int cb = 0; cb < TN; cb += 64) {
-          ptx::tmem_ld_32x32(taddr + (uint32_t)(cb + 32), v1);
-          process(v0, cb);
-          ptx::tmem_ld_fence(v1);
-          if (cb + 64 < TN) ptx::tmem_ld_32x32(taddr + (uint32_t)(cb + 64), v0);
-          process(v1, cb + 32);
-          if (cb + 64 < TN) ptx::tmem_ld_fence(v0);
-        }
-      }
+      PendingHits pend;
+      pend.n = 0;
+      if (debug != 1)
+        select_tile_tmem<E, kL2>(st, pend, taddr, grp, 2, TN / 32, col0, c_end, gst, qn, self_row, p.self_mode, p.k,
+                                 lane, tau_row, row_valid && debug != 2, stats_on, e_slow, n_slow);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0) {  // the accumulator stage is free again; the list work for this tile's hits comes after
         if (leader) ptx::mbar_arrive(&bars->tmem_empty[as]);
         else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
       }
+      flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
     if (stats_on && lane == 0) {
       atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));
@@ -305,7 +275,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       atomicAdd(cfg.stats + 5, (unsigned long long)e_slow);
       atomicAdd(cfg.stats + 6, n_slow);
       atomicAdd(cfg.stats + 9, 1ull);
-      atomicAdd(cfg.stats + 10, (unsigned long long)ntiles * (TN / 32));
+      atomicAdd(cfg.stats + 10, (unsigned long long)ntiles * (TN / 64));
     }
     const long long cf = stats_on ? clock64() : 0;
     warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
@@ -368,7 +338,7 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
 
   PairCfg cfg;
   cfg.nkb = (p.d + BKE - 1) / BKE;
-  const size_t fixed = kDumpBytes + sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
+  const size_t fixed = sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
   cfg.resident = ((size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
   cfg.a_bytes = cfg.resident ? (uint32_t)cfg.nkb * KB_BYTES : 0u;
   cfg.stage_bytes = cfg.resident ? KB_BYTES : 2 * KB_BYTES;
@@ -407,8 +377,8 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
 }  // namespace
 
 int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream) {
-  if (p.qblocks % 2 != 0) {
-    set_error("internal: pair kernel needs an even number of 128-row query blocks");
+  if (p.qblocks % 2 != 0 || p.groups != 2) {
+    set_error("internal: pair kernel needs an even number of 128-row query blocks and 2 lists per row and split");
     return KNN_E_INVALID;
   }
   switch (p.kp) {

@@ -285,63 +285,18 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
       apply_tau<kL2>(st, tau_peek);
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(as * TN);
 
-#pragma unroll 1
-      for (int ch = grp; ch < ((debug & 8) ? 0 : nchunks); ch += 2) {
-        const int cb = ch * 32;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
-        ptx::tmem_ld_fence(v);
-        const int64_t cg = col0 + cb;
-        const int64_t rem = c_end - cg;
-        const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
-        const float* gn = gst + cb;
-        auto fv = [&](int j) -> float {
-          const float dot = __uint_as_float(v[j]);
-          if (kL2) return fmaf(2.0f, dot, -(qn + gn[j]));
-          return dot;
-        };
-        const float m = chunk_max32(fv);
-        const bool hit = row_valid && m >= st.ftau && !(debug & 2);
-        if (__any_sync(kFullMask, hit)) {
-          // slow path (warp-uniform): the lanes with a hit build their column masks; every column in the UNION is
-          // re-read from TMEM with one warp-wide single-column load, and the lanes that flagged it append.
-          const long long c0 = stats_on ? clock64() : 0;
-          const uint32_t mask = hit ? chunk_mask32(fv, st.ftau, nvalid) : 0u;
-          uint32_t uni = __reduce_or_sync(kFullMask, mask);
-          while (uni) {
-            const int j = __ffs(uni) - 1;
-            uni &= uni - 1;
-            const uint32_t x = ptx::tmem_ld_32x32_x1(taddr + (uint32_t)(cb + j));
-            if ((mask >> j) & 1u) {
-              float f = __uint_as_float(x);
-              if (kL2) f = fmaf(2.0f, f, -(qn + gn[j]));
-              const uint32_t row = (uint32_t)cg + (uint32_t)j;
-              float s = exact_score<kL2>(f);
-              bool take = true;
-              if (row == self_row) {
-                if (p.self_mode == KNN_SELF_EXCLUDE) take = false;
-                else if (p.self_mode == KNN_SELF_MINUS1) s = -1.0f;
-              }
-              const uint64_t key = make_key(s, row);
-              if (take && key > st.taukey) {
-                __stcg(st.list + st.cnt, key);
-                ++st.cnt;
-              }
-            }
-          }
-          warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
-          if (stats_on) {
-            e_slow += clock64() - c0;
-            ++n_slow;
-          }
-        }
-      }
+      PendingHits pend;
+      pend.n = 0;
+      if (!(debug & 8))
+        select_tile_tmem<E, kL2>(st, pend, taddr, grp, 2, nchunks, col0, c_end, gst, qn, self_row, p.self_mode, p.k,
+                                 lane, tau_row, row_valid && !(debug & 2), stats_on, e_slow, n_slow);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (leader) ptx::mbar_arrive(&bars->tmem_empty[as]);
         else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
       }
+      flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
     if (stats_on && lane == 0) {
       atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));

@@ -16,6 +16,7 @@
 // by ascending gallery row through the key encoding) therefore survives to the final merge.
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace knn {
 
@@ -90,6 +91,68 @@ __device__ __noinline__ CompactOut compact_row(uint64_t* __restrict__ list, int 
   CompactOut o;
   o.cnt = cnt < k ? cnt : k;
   o.taukey = (cnt >= k) ? kth : 0ull;  // 0 = "no threshold yet"
+  return o;
+}
+
+// Cheap compaction by SELECTION instead of sorting (the list does not need to be ordered, only trimmed): a pivot
+// key p with at least k list entries >= p is a valid threshold, and every entry below it can be dropped.  The warp
+// sorts a 32-key sample of the list (one key per lane), binary-searches the sample for the LARGEST sample with
+// count(list >= sample) >= k (5 counting rounds: E compares per lane + one warp reduction each), and writes the
+// survivors back contiguously (unordered).  ~350 instructions instead of the ~2.5k of the full sorting network, so
+// a compaction no longer holds an accumulator stage long enough to stall the tensor pipe.  Expected survivors:
+// k .. k + ~L/32.  Falls back to the sorting network when the sample cannot shrink the list (returns cnt unchanged).
+template <int E>
+__device__ __noinline__ CompactOut compact_row_select(uint64_t* __restrict__ list, int cnt, int k, int lane) {
+  uint64_t v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int i = e * 32 + lane;
+    v[e] = (i < cnt) ? __ldcg(list + i) : 0ull;
+  }
+  // sample: lane l offers its key in slot (l mod E) -> positions spread over the whole list
+  uint64_t smp = 0ull;
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if ((lane % E) == e) smp = v[e];
+  // 32-key bitonic sort across lanes, descending in lane index
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const uint64_t o = __shfl_xor_sync(kFullMask, smp, stride);
+      const bool desc = (lane & size) == 0;
+      const bool lower = (lane & stride) == 0;
+      const bool keep_max = lower == desc;
+      smp = keep_max ? (smp > o ? smp : o) : (smp > o ? o : smp);
+    }
+  }
+  // smallest sample index j whose count(list >= sample[j]) >= k  (counts grow with j)
+  int lo = 0, hi = 32;  // answer in [lo, hi]; hi == 32 means "no sample qualifies"
+#pragma unroll 1
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint64_t pv = __shfl_sync(kFullMask, smp, mid);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (v[e] >= pv) ? 1 : 0;
+    c = __reduce_add_sync(kFullMask, c);
+    if (pv != 0ull && c >= k) hi = mid; else lo = mid + 1;
+  }
+  CompactOut o;
+  o.cnt = cnt;
+  o.taukey = 0ull;
+  if (lo >= 32) return o;  // (near-)degenerate sample: caller falls back to the sorting network
+  const uint64_t pv = __shfl_sync(kFullMask, smp, lo);
+  int base = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool keep = v[e] >= pv;
+    const unsigned b = __ballot_sync(kFullMask, keep);
+    if (keep) __stcg(list + base + __popc(b & ((1u << lane) - 1u)), v[e]);
+    base += __popc(b);
+  }
+  o.cnt = base;
+  o.taukey = pv;
   return o;
 }
 
@@ -226,7 +289,8 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
     uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
     const int rc = __shfl_sync(kFullMask, st.cnt, r);
     __syncwarp();
-    const CompactOut co = compact_row<E>(rl, rc, k, k, lane);
+    CompactOut co = compact_row_select<E>(rl, rc, k, lane);
+    if (co.cnt > (L + k) / 2) co = compact_row<E>(rl, rc, k, k, lane);  // too little progress: sort, keep exactly k
     const int nc = co.cnt;
     const uint64_t nk = co.taukey;
     if (lane == r) {
@@ -291,6 +355,110 @@ __device__ __forceinline__ void refresh_tau(RowState& st, const uint32_t* __rest
     st.tau = ord2f(o);
     st.ftau = filter_tau<kL2>(st.tau);
     st.taukey = (uint64_t)o << 32;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Selection over one accumulator tile that lives in TENSOR MEMORY (tcgen05 kernels).  The calling thread owns TMEM
+// lane `taddr.lane + lane` = one query row and examines the 32-column chunks first, first + step, ... < nchunks.
+// Two phases, so that the accumulator stage is held only as long as the scores must be READ:
+//   select_tile_tmem   (stage held)     per chunk one tcgen05.ld.x32, a max tree, one compare.  A lane whose chunk
+//                      has exactly ONE passing score -- the chunk maximum, already in a register -- just records
+//                      (column, value) in a two-entry register queue.  Several passing scores in one lane's chunk,
+//                      or a full queue, are rare: those lanes append at once, re-reading the flagged columns from
+//                      TMEM with warp-wide single-column loads.
+//   flush_pending_hits (stage released) key construction, self handling, the list append and, when a list is
+//                      about to overflow, its compaction.
+// ------------------------------------------------------------------------------------------------------------
+struct PendingHits {
+  uint32_t col[2];  // local gallery row
+  float val[2];     // filter value (dot, or -(d^2) for L2)
+  int n;
+};
+
+template <bool kL2>
+__device__ __forceinline__ void append_candidate(RowState& st, float f, uint32_t row, uint32_t self_row,
+                                                 int self_mode) {
+  float sc = exact_score<kL2>(f);
+  bool take = true;
+  if (row == self_row) {
+    if (self_mode == KNN_SELF_EXCLUDE) take = false;
+    else if (self_mode == KNN_SELF_MINUS1) sc = -1.0f;
+  }
+  const uint64_t key = make_key(sc, row);
+  if (take && key > st.taukey) {
+    __stcg(st.list + st.cnt, key);
+    ++st.cnt;
+  }
+}
+
+template <int E, bool kL2>
+__device__ __forceinline__ void select_tile_tmem(RowState& st, PendingHits& pend, uint32_t taddr, int first, int step,
+                                                 int nchunks, int64_t col0, int64_t c_end, const float* gst, float qn,
+                                                 uint32_t self_row, int self_mode, int k, int lane,
+                                                 uint32_t* tau_row, bool row_valid, bool stats_on,
+                                                 long long& e_slow, unsigned long long& n_slow) {
+#pragma unroll 1
+  for (int ch = first; ch < nchunks; ch += step) {
+    const int cb = ch * 32;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
+    ptx::tmem_ld_fence(v);
+    const int64_t cg = col0 + cb;
+    const int64_t rem = c_end - cg;
+    const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
+    const float* gn = gst + cb;
+    auto fv = [&](int j) -> float {
+      const float dot = __uint_as_float(v[j]);
+      if (kL2) return fmaf(2.0f, dot, -(qn + gn[j]));
+      return dot;
+    };
+    const float m = chunk_max32(fv);
+    const bool hit = row_valid && m >= st.ftau;
+    if (__any_sync(kFullMask, hit)) {
+      const long long c0 = stats_on ? clock64() : 0;
+      uint32_t mask = hit ? chunk_mask32(fv, st.ftau, nvalid) : 0u;
+      if (mask != 0u && (mask & (mask - 1u)) == 0u && pend.n < 2 && nvalid == 32u) {  // (tail chunk: the maximum may sit in a padding column)
+        // the single passing score is the chunk maximum: queue it, the list work waits until the stage is released
+        const uint32_t row = (uint32_t)cg + (uint32_t)(__ffs(mask) - 1);
+        if (pend.n == 0) { pend.col[0] = row; pend.val[0] = m; }
+        else { pend.col[1] = row; pend.val[1] = m; }
+        ++pend.n;
+        mask = 0u;
+      }
+      uint32_t uni = __reduce_or_sync(kFullMask, mask);
+      if (uni) {  // rare: some lane has several hits in this chunk (or a full queue) -> append them now
+        while (uni) {
+          const int j = __ffs(uni) - 1;
+          uni &= uni - 1;
+          const uint32_t x = ptx::tmem_ld_32x32_x1(taddr + (uint32_t)(cb + j));
+          if ((mask >> j) & 1u) {
+            float f = __uint_as_float(x);
+            if (kL2) f = fmaf(2.0f, f, -(qn + gn[j]));
+            append_candidate<kL2>(st, f, (uint32_t)cg + (uint32_t)j, self_row, self_mode);
+          }
+        }
+        warp_compact_if_needed<E, 32, kL2>(st, k, lane, tau_row);
+      }
+      if (stats_on) {
+        e_slow += clock64() - c0;
+        ++n_slow;
+      }
+    }
+  }
+}
+
+template <int E, bool kL2>
+__device__ __forceinline__ void flush_pending_hits(RowState& st, PendingHits& pend, uint32_t self_row, int self_mode,
+                                                   int k, int lane, uint32_t* tau_row, bool stats_on,
+                                                   long long& e_slow) {
+  if (__any_sync(kFullMask, pend.n > 0)) {
+    const long long c0 = stats_on ? clock64() : 0;
+    if (pend.n > 0) append_candidate<kL2>(st, pend.val[0], pend.col[0], self_row, self_mode);
+    if (pend.n > 1) append_candidate<kL2>(st, pend.val[1], pend.col[1], self_row, self_mode);
+    pend.n = 0;
+    warp_compact_if_needed<E, 32, kL2>(st, k, lane, tau_row);
+    if (stats_on) e_slow += clock64() - c0;
   }
 }
 
