@@ -60,6 +60,18 @@ def load_peaks():
     return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
 
 
+def traffic_bytes(workload, nq, rows, d):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this very configuration (profiles/traffic.json); None when it was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        table = json.load(fh)
+    ent = table.get(f"{workload}:{nq}x{rows}x{d}")
+    return None if ent is None else ent["dram_bytes_per_launch"]
+
+
 class ClockSampler:
     """Samples SM clock + throttle reasons through NVML every 100 ms while the timed region runs."""
 
@@ -295,17 +307,20 @@ def main():
         "roofline": ({
             "bound": "hbm", "achieved": algo_bytes / (dist_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": algo_bytes / (dist_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-            "kernel": "search_bf16_pair_kernel", "kernel_ms": dist_ms, "merge_kernel_ms": merge_ms,
-            "tensor_TFLOPs": achieved, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+            "kernel": "search_bf16_kernel (+ its threshold-seeding pre-pass launch)", "kernel_ms": dist_ms,
+            "merge_kernel_ms": merge_ms, "tensor_TFLOPs": achieved, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
         } if hbm_bound else {
             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "search_bf16_pair_kernel",
+            "frac": achieved / peaks["tflops"], "traffic": traffic_bytes(args.workload, nq, count, d),
+            "kernel": "search_bf16_pair_kernel (+ its threshold-seeding pre-pass launch)",
             "kernel_ms": dist_ms, "merge_kernel_ms": merge_ms, "gallery_stream_GBps": gallery_gbs,
+            "algorithmic_bytes": algo_bytes,
             "peak_source": peaks["source"],
         }),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": args.steps * (2 + (1 if world > 1 else 0)),
+        # per step: seeding pre-pass + distance/selection kernel + unit merge (+ k-way shard merge after the all-gather)
+        "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
         "clocks": clocks.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

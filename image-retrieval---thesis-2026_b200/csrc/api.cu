@@ -72,14 +72,21 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
     const char* e = getenv("KNN_WAVES");
     return e ? atoi(e) : 0;
   }();
-  // a single query block (HBM-bound streaming) gets ~2 waves: every extra split adds KP candidate slots per
-  // query to the final merge; many query blocks get up to ~4 waves' worth of splits
+  // Lower end: one full wave, and units short enough (<= kMaxUnitTiles tiles) that the CTAs streaming the same
+  // gallery range stay within an L2-sized window of each other -- they start together but nothing re-synchronises
+  // them, and over longer units their random drift turned 2/3 of the L2 hits into HBM re-reads (measured).
+  // Upper end: ~4 waves' worth for many query blocks, ~2 waves for a single block (every extra split adds a
+  // candidate list per query to the final merge), at least twice the lower end.
+  constexpr int64_t kMaxUnitTiles = 6144;
   const int waves = env_waves > 0 ? env_waves : (g.qblocks <= 2 ? 2 : 4);
+  int64_t lo = (slots + g.qblocks - 1) / g.qblocks;
+  const int64_t lo_len = (ntiles + kMaxUnitTiles - 1) / kMaxUnitTiles;
+  if (lo < lo_len) lo = lo_len;
   int64_t hi = ((int64_t)waves * slots + g.qblocks - 1) / g.qblocks;
-  int64_t lo = (slots + g.qblocks - 1) / g.qblocks;                    // one full wave
+  if (hi < 2 * lo_len) hi = 2 * lo_len;
   const int64_t min_tiles = (32 * 256) / tile;                          // >= 8192 gallery rows per unit
   int64_t by_len = ntiles / min_tiles;
-  if (by_len < lo) by_len = lo;
+  if (by_len < (slots + g.qblocks - 1) / g.qblocks) by_len = (slots + g.qblocks - 1) / g.qblocks;
   if (hi > by_len) hi = by_len;
   if (hi > ntiles) hi = ntiles;
   if (hi > 2048) hi = 2048;
@@ -115,12 +122,19 @@ unsigned long long* debug_stats_buffer() {
   return buf;
 }
 
-static int64_t seed_rows() {  // gallery prefix scanned by the threshold-seeding pre-pass (KNN_SEED_ROWS overrides)
-  static const int64_t v = [] {
+// Gallery prefix scanned by the threshold-seeding pre-pass (KNN_SEED_ROWS overrides; 0 = no pre-pass).  The pre-pass
+// runs one CTA per query block, i.e. on qblocks of the `slots` SMs only, so its share of the step is
+// (rows / ng) * (slots / qblocks): sized for <= ~0.5 % of the main pass, between 4096 and 65536 rows (power of two).
+static int64_t seed_rows(int64_t ng, int qblocks, int64_t slots) {
+  static const int64_t forced = [] {
     const char* e = getenv("KNN_SEED_ROWS");
-    return e ? (int64_t)atoll(e) : (int64_t)4096;
+    return e ? (int64_t)atoll(e) : (int64_t)-1;
   }();
-  return v;
+  if (forced >= 0) return forced;
+  const double budget = 0.005 * (double)ng * (double)qblocks / (double)slots;
+  int64_t rows = 4096;
+  while (rows * 2 <= 65536 && (double)(rows * 2) <= budget) rows *= 2;
+  return rows;
 }
 
 }  // namespace knn
@@ -130,13 +144,27 @@ using namespace knn;
 extern "C" int knn_version(void) { return KNN_ABI_VERSION; }
 extern "C" const char* knn_last_error(void) { return g_err; }
 
+// Workspace layout: tau_global [qblocks*128] u32 | counts [(splits+1)*groups][qblocks*128] i32 |
+//                   lists [(splits+1)*groups][qblocks*128][L] u64.  The "+1" split is the scratch of the
+//                   threshold-seeding pre-pass.
+struct WsLayout {
+  size_t tau_bytes, counts_bytes, lists_bytes;
+};
+static WsLayout ws_layout(const SearchGeom& g) {
+  WsLayout w;
+  const size_t rows = (size_t)g.qblocks * kRowsPerUnit;
+  const size_t vsplits = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.groups;
+  w.tau_bytes = align_up(rows * sizeof(uint32_t), 256);
+  w.counts_bytes = align_up(vsplits * rows * sizeof(int32_t), 256);
+  w.lists_bytes = vsplits * rows * (size_t)g.L * sizeof(uint64_t);
+  return w;
+}
+
 extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
-  const size_t tau = align_up((size_t)g.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
-  // +1 split: scratch lists of the threshold-seeding pre-pass
-  const size_t lists = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.groups * g.qblocks * kRowsPerUnit * (size_t)g.L * sizeof(uint64_t);
-  return tau + lists;
+  const WsLayout w = ws_layout(g);
+  return w.tau_bytes + w.counts_bytes + w.lists_bytes;
 }
 
 static int check_common(const void* q, const void* g, const float* qs, const float* gs, int64_t nq, int64_t ng,
@@ -184,9 +212,11 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.metric = metric; p.self_mode = self_mode;
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
-  const size_t tau_bytes = align_up((size_t)geo.qblocks * kRowsPerUnit * sizeof(uint32_t), 256);
+  const WsLayout wl = ws_layout(geo);
+  const size_t tau_bytes = wl.tau_bytes;
   p.tau_global = reinterpret_cast<uint32_t*>(workspace);
-  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + tau_bytes);
+  p.counts = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes);
+  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes + wl.counts_bytes);
   p.dense_out = nullptr;
 
   const bool prof = g_prof.on;
@@ -198,19 +228,24 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   if (geo.splits > 0) {
     KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
     if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
-    // Threshold seeding: a pre-pass over the first kSeedRows gallery rows leaves its k-th best score in
-    // tau_global (a valid lower bound of the final k-th best); the main pass then starts with a ~k/kSeedRows
-    // pass rate instead of accepting everything until each list has filled up.  Its candidate lists go to a
-    // scratch unit and are discarded (the main pass visits those rows again).
-    const int64_t kSeedRows = seed_rows();
+    // Threshold seeding: a pre-pass searches the first kSeedRows gallery rows (lists in the scratch split) and a
+    // unit merge in seeding mode publishes each row's exact k-th best score of that sample in tau_global -- a valid
+    // lower bound of the final k-th best.  The main pass then starts with a pass rate of ~k / kSeedRows instead of
+    // accepting everything until each list has filled up.  The sample's candidates are discarded (the main pass
+    // visits those rows again).
+    const int64_t kSeedRows = seed_rows(ng, geo.qblocks, (int64_t)sm_count() * (dtype == KNN_BF16 ? 1 : 2));
     if (kSeedRows > 0 && ng >= 8 * kSeedRows) {
       SearchParams ps = p;
       ps.ng = kSeedRows;
       ps.splits = 1;
       ps.split_len = kSeedRows;
-      ps.lists = p.lists + (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit * (size_t)geo.L;
+      const size_t scratch_rows = (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit;
+      ps.lists = p.lists + scratch_rows * (size_t)geo.L;
+      ps.counts = p.counts + scratch_rows;
       rc = ts ? launch_search_bf16_ts(ps, s)
               : (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
+      if (rc != KNN_OK) return rc;
+      rc = launch_merge_units(ps, 0, nullptr, nullptr, p.tau_global, s);
       if (rc != KNN_OK) return rc;
     }
     rc = ts ? launch_search_bf16_ts(p, s)
@@ -220,7 +255,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
     KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
   }
   if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[1], s));
-  rc = launch_merge_units(p, index_base, out_val, out_idx, s);
+  rc = launch_merge_units(p, index_base, out_val, out_idx, nullptr, s);
   if (rc != KNN_OK) return rc;
   if (prof) {
     KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[2], s));

@@ -21,7 +21,8 @@ struct SearchParams {
   int splits;
   int groups;            // candidate lists per (split, row): 2 for the TMEM-resident kernel, else 1
   int qblocks;
-  uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys
+  uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys (unordered)
+  int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
   float* dense_out;      // dense mode only
 };
@@ -36,7 +37,8 @@ int ts_tile_cols(int d);  // gallery rows per tile of the TMEM-resident kernel, 
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();
 
+// tau_out != nullptr: seeding mode (publish each row's k-th best score instead of writing results)
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
-                       cudaStream_t stream);
+                       uint32_t* tau_out, cudaStream_t stream);
 
 }  // namespace knn

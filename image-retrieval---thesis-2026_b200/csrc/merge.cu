@@ -35,75 +35,109 @@ __device__ __forceinline__ int pow2_ge(int x) {
   return p;
 }
 
-// One CTA per query row: gather the best-KP prefix of every gallery split's list, sort, emit top-k.
+// One CTA per query row: exact top-k of the union of the row's candidate lists (one UNORDERED list of counts[..]
+// keys per gallery split and selection group), written best-first.
+//   1. keys below the shared threshold tau_global[row] (a lower bound of the final k-th best) cannot be in the answer;
+//   2. if more than kSortCap keys remain (many splits), an MSB radix select over the 64-bit keys (8 bits per pass,
+//      256-bin shared-memory histogram) raises the bound until at most kSortCap keys are >= it -- the k-th best
+//      key always stays above the bound, whatever the score distribution or number of ties;
+//   3. the survivors are gathered into shared memory, sorted by a bitonic network and the first k are emitted.
+// Seeding mode (tau_out != nullptr): nothing is emitted; the k-th best SCORE of the sample is published as the
+// row's starting threshold for the main pass.
 __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams p, int64_t index_base,
                                                                  float* __restrict__ out_val,
-                                                                 int64_t* __restrict__ out_idx) {
+                                                                 int64_t* __restrict__ out_idx,
+                                                                 uint32_t* __restrict__ tau_out) {
   __shared__ uint64_t s[kSortCap];
+  __shared__ int hist[256];
+  __shared__ int n_surv;
+  __shared__ unsigned long long sh_lo;
+  __shared__ int sh_done, sh_kk;
   const int64_t r = blockIdx.x;
   const int qb = (int)(r / kRowsPerUnit), lr = (int)(r % kRowsPerUnit);
-  const int kp = p.kp, L = 2 * p.kp;
-  const int64_t M = (int64_t)p.splits * p.groups * kp;  // (split, group) pairs are laid out as virtual splits
+  const int L = 2 * p.kp;
+  const int V = p.splits * p.groups;  // (split, group) pairs are laid out as virtual splits
   const bool l2 = p.metric == KNN_L2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-  // Pre-filter with the shared threshold: tau_global[r] is the best k-th-best score any unit reached, a lower
-  // bound of the final k-th best, so only keys with score >= it can be in the answer (typically k + a few
-  // out of splits * KP slots).  Survivors are compacted into shared memory and sorted once.
-  __shared__ int n_surv;
-  const uint64_t thr_key = (uint64_t)__ldcg(p.tau_global + r) << 32;
+  // visit every key of this row: warp w walks lists w, w + nwarps, ...; lanes stride through a list (coalesced)
+  auto for_each_key = [&](auto&& fn) {
+    for (int v = warp; v < V; v += nwarps) {
+      const int64_t unit_row = ((int64_t)v * p.qblocks + qb) * kRowsPerUnit + lr;
+      int cnt = __ldcg(p.counts + unit_row);
+      cnt = cnt < 0 ? 0 : (cnt > L ? L : cnt);
+      const uint64_t* base = p.lists + unit_row * (int64_t)L;
+      for (int j = lane; j < cnt; j += 32) fn(__ldcg(base + j));
+    }
+  };
+
+  unsigned long long lo = (unsigned long long)__ldcg(p.tau_global + r) << 32;
   if (threadIdx.x == 0) n_surv = 0;
   __syncthreads();
-  constexpr int kBatch = 8;  // independent loads in flight per thread (the lists are L2/HBM resident)
-  for (int64_t c0 = threadIdx.x; c0 < M; c0 += (int64_t)blockDim.x * kBatch) {
-    uint64_t keys[kBatch];
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const int64_t c = c0 + (int64_t)b * blockDim.x;
-      keys[b] = 0ull;
-      if (c < M) {
-        const int sp = (int)(c / kp), j = (int)(c % kp);
-        keys[b] = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      if (keys[b] != 0ull && keys[b] >= thr_key) {
-        const int slot = atomicAdd(&n_surv, 1);
-        if (slot < kSortCap) s[slot] = keys[b];
-      }
-    }
+  {
+    int c = 0;
+    for_each_key([&](uint64_t key) { c += key >= lo ? 1 : 0; });
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if (lane == 0 && c) atomicAdd(&n_surv, c);
   }
   __syncthreads();
-  const int ns = n_surv;
-  if (ns <= kSortCap) {
-    const int n = pow2_ge(ns > p.k ? ns : p.k);
-    for (int i = ns + threadIdx.x; i < n; i += blockDim.x) s[i] = 0ull;
+  const int total = n_surv;
+  __syncthreads();
+  if (total > kSortCap) {
+    // MSB radix select of the k-th largest key among the keys >= lo.  sh_kk = rank still to find inside the
+    // current bin; k - sh_kk = keys known to lie strictly above it (all of them are in the answer).
+    if (threadIdx.x == 0) {
+      sh_lo = 0ull;
+      sh_kk = p.k;
+      sh_done = 0;
+    }
     __syncthreads();
-    smem_bitonic(s, n, 2, n, n, 0);
-  } else {
-    // fallback (no usable threshold, e.g. every split saw fewer than k rows): rounds of sort-and-keep-best
-    __syncthreads();
-    for (int i = threadIdx.x; i < kp; i += blockDim.x) s[i] = 0ull;
-    int64_t consumed = 0;
-    do {
-      const int64_t left = M - consumed;
-      const int take = (int)(left < (kSortCap - kp) ? left : (kSortCap - kp));
-      const int n = pow2_ge(kp + take);
-      for (int i = threadIdx.x; i < n - kp; i += blockDim.x) {
-        uint64_t key = 0ull;
-        if (i < take) {
-          const int64_t c = consumed + i;
-          const int sp = (int)(c / kp), j = (int)(c % kp);
-          key = __ldcg(p.lists + ((((int64_t)sp * p.qblocks + qb) * kRowsPerUnit + lr) * (int64_t)L + j));
+    for (int d = 56; d >= 0; d -= 8) {
+      const unsigned long long prefix = sh_lo;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for_each_key([&](uint64_t key) {
+        if (key >= lo && (d == 56 || (key >> (d + 8)) == (prefix >> (d + 8))))
+          atomicAdd(&hist[(int)((key >> d) & 255ull)], 1);
+      });
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int kk = sh_kk;
+        int acc = 0, b = 255;
+        for (; b > 0; --b) {
+          if (acc + hist[b] >= kk) break;
+          acc += hist[b];
         }
-        s[kp + i] = key;
+        sh_kk = kk - acc;
+        sh_lo = prefix | ((unsigned long long)b << d);
+        const int cnt_ge = (p.k - sh_kk) + hist[b];  // keys >= the new bound
+        sh_done = (cnt_ge <= kSortCap || d == 0) ? 1 : 0;
       }
       __syncthreads();
-      smem_bitonic(s, n, 2, n, n, 0);
-      consumed += take;
-    } while (consumed < M);
+      if (sh_done) break;
+    }
+    if (sh_lo > lo) lo = sh_lo;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) n_surv = 0;
+  __syncthreads();
+  for_each_key([&](uint64_t key) {
+    if (key >= lo) {
+      const int slot = atomicAdd(&n_surv, 1);
+      if (slot < kSortCap) s[slot] = key;
+    }
+  });
+  __syncthreads();
+  const int ns = n_surv < kSortCap ? n_surv : kSortCap;
+  const int n = pow2_ge(ns > p.k ? ns : p.k);
+  for (int i = ns + threadIdx.x; i < n; i += blockDim.x) s[i] = 0ull;
+  __syncthreads();
+  smem_bitonic(s, n, 2, n, n, 0);
 
+  if (tau_out != nullptr) {
+    if (threadIdx.x == 0 && ns >= p.k) atomicMax(tau_out + r, (uint32_t)(s[p.k - 1] >> 32));
+    return;
+  }
   for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
     const uint64_t key = s[j];
     float v; int64_t id;
@@ -248,9 +282,9 @@ __global__ void __launch_bounds__(kSortThreads) rank_rows_kernel(const float* __
 }  // namespace
 
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
-                       cudaStream_t stream) {
+                       uint32_t* tau_out, cudaStream_t stream) {
   if (p.nq == 0) return KNN_OK;
-  merge_units_kernel<<<(unsigned)p.nq, kSortThreads, 0, stream>>>(p, index_base, out_val, out_idx);
+  merge_units_kernel<<<(unsigned)p.nq, kSortThreads, 0, stream>>>(p, index_base, out_val, out_idx, tau_out);
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
 }

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p)
     }
   }
 
-  if (!kDense && owner) warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
+  // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
+  if (!kDense && owner) p.counts[((int64_t)sp * p.qblocks + qb) * BM + tid] = row_valid ? st.cnt : 0;
 }
 
 size_t f32_smem_bytes() { return sizeof(float) * (size_t)(4 * BK * LDA + BM * LDS + BN); }

@@ -234,9 +234,8 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       atomicAdd(stats + 9, 1ull);
       atomicAdd(stats + 10, (unsigned long long)ntiles * (TN / 32));
     }
-    const long long cf = stats ? clock64() : 0;
-    warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
-    if (stats && lane == 0) atomicAdd(stats + 11, (unsigned long long)(clock64() - cf));
+    // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
+    p.counts[unit * TM + rloc] = row_valid ? st.cnt : 0;
   }
 
   ptx::tc_fence_before();

@@ -306,9 +306,8 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
       atomicAdd(cfg.stats + 9, 1ull);
       atomicAdd(cfg.stats + 10, (unsigned long long)ntiles * ((nchunks + 1 - grp) / 2));
     }
-    const long long cf = stats_on ? clock64() : 0;
-    warp_finalize<E, kL2>(st, p.k, p.kp, lane, tau_row, row_valid);
-    if (stats_on && lane == 0) atomicAdd(cfg.stats + 11, (unsigned long long)(clock64() - cf));
+    // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
+    p.counts[vunit * TM + rloc] = row_valid ? st.cnt : 0;
   }
 
   ptx::tc_fence_before();

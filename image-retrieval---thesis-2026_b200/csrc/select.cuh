@@ -306,32 +306,6 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
   }
 }
 
-// End of unit: leave the best KP keys (sorted, zero padded) in list[0..KP) of every row of the warp.
-template <int E, bool kL2>
-__device__ __forceinline__ void warp_finalize(RowState& st, int k, int kp, int lane,
-                                              uint32_t* __restrict__ tau_global_row, bool row_valid) {
-  __syncwarp();
-#pragma unroll 1
-  for (int r = 0; r < 32; ++r) {
-    uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
-    const int rc = __shfl_sync(kFullMask, st.cnt, r);
-    const int rv = __shfl_sync(kFullMask, (int)row_valid, r);
-    if (!rv) continue;
-    const CompactOut co = compact_row<E>(rl, rc, k, kp, lane);
-    const int nc = co.cnt;
-    const uint64_t nk = co.taukey;
-    if (lane == r) {
-      st.cnt = nc;
-      if (nk > st.taukey) {
-        st.taukey = nk;
-        st.tau = key_score(nk);
-        if (tau_global_row) atomicMax(tau_global_row, (uint32_t)(nk >> 32));
-      }
-    }
-  }
-  __syncwarp();
-}
-
 // Pull the shared threshold (other CTAs working on the same query row may have tightened it).
 // Split in two so the L2 round trip of the load can be hidden behind a barrier wait: o = peek_tau(); ...; apply_tau(o).
 __device__ __forceinline__ uint32_t peek_tau(const uint32_t* __restrict__ tau_global_row) {
