@@ -36,15 +36,21 @@ static int sm_count() {
   return sms;
 }
 
-// Which bf16 kernel serves a problem.  The shared-memory-A kernels (search_tc.cu, search_tc2.cu) are the default;
-// the TMEM-resident-query kernel (search_ts.cu) is kept as a measured alternative, KNN_BF16_TS=1 selects it
-// (d <= 768 only).  Measured on B200 (20M x 512 gallery, 8192 queries): N = 128 tiles cost it ~9 %, see DESIGN.md.
-static bool use_ts(int dtype, int d) {
-  static const bool on = [] {
+// Which bf16 kernel serves a problem.
+//   one 128-row query block (HBM-bound streaming), d <= 768 : the TMEM-resident-query kernel (search_ts.cu) -- every
+//       byte that crosses L2 -> SM is a gallery byte;
+//   one query block, d > 768                                 : the one-CTA shared-memory-A kernel (search_tc.cu);
+//   several query blocks (tensor-bound)                      : the CTA-pair kernel (search_tc2.cu).  Its N = 256 tiles
+//       beat the N = 128 tiles the TMEM-resident layout leaves room for (measured).
+// KNN_BF16_TS=0 / 1 forces the TMEM-resident kernel off / on wherever it fits.
+static bool use_ts(int dtype, int d, int qblocks) {
+  static const int forced = [] {
     const char* e = getenv("KNN_BF16_TS");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }();
-  return dtype == KNN_BF16 && on && ts_tile_cols(d) > 0;
+  if (dtype != KNN_BF16 || ts_tile_cols(d) == 0) return false;
+  if (forced >= 0) return forced == 1;
+  return qblocks == 1;
 }
 
 // Work decomposition: a unit = (128-query block, gallery split).  Splits are contiguous gallery ranges,
@@ -53,13 +59,15 @@ static bool use_ts(int dtype, int d) {
 // so the number of splits is chosen to make qblocks * splits fill WHOLE waves of the machine: between one wave
 // and ~4 waves' worth of splits, the count with the best (work / waves) efficiency wins (8192 queries on 148 SMs:
 // 37 splits = 16 full waves instead of 10 splits = 4.32 waves).
+static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots);
+
 static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   SearchGeom g;
   g.kp = kpad_for(k);
   g.L = 2 * g.kp;
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
-  const bool ts = use_ts(dtype, d);
+  const bool ts = use_ts(dtype, d, g.qblocks);
   // the CTA-pair kernel and the TMEM-resident kernel run two selection threads (two lists) per row
   g.groups = (dtype == KNN_BF16 && (ts || g.qblocks > 1)) ? 2 : 1;
   // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernels); a single block
@@ -106,6 +114,7 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   const int64_t tiles_per_split = ntiles > 0 ? (ntiles + best - 1) / best : 1;
   g.split_len = tiles_per_split * tile;
   g.splits = ntiles > 0 ? (int)((ntiles + tiles_per_split - 1) / tiles_per_split) : 0;
+  seed_geometry(g, ng, tile, slots);
   return g;
 }
 
@@ -122,19 +131,38 @@ unsigned long long* debug_stats_buffer() {
   return buf;
 }
 
-// Gallery prefix scanned by the threshold-seeding pre-pass (KNN_SEED_ROWS overrides; 0 = no pre-pass).  The pre-pass
-// runs one CTA per query block, i.e. on qblocks of the `slots` SMs only, so its share of the step is
-// (rows / ng) * (slots / qblocks): sized for <= ~0.5 % of the main pass, between 4096 and 65536 rows (power of two).
-static int64_t seed_rows(int64_t ng, int qblocks, int64_t slots) {
+// Threshold-seeding pre-pass: a sample of the gallery's first rows is searched by seed_splits units per query block
+// and merged; the sample's exact k-th best score becomes every row's starting threshold (a valid lower bound of the
+// final k-th best), so the main pass starts with a pass rate of ~k / sample instead of accepting everything.
+//   * sample size: <= ~0.5 % of the main pass's work, 4096 .. 65536 rows (KNN_SEED_ROWS overrides; 0 = no pre-pass);
+//   * spread over ~2 waves of CTAs (a single query block gets 2 * #SM units), but never fewer than kSeedUnitMin rows
+//     per unit: a unit that short fills its candidate lists without a single compaction.  With one query block the
+//     sample therefore grows to 2 * #SM * 224 = 66 k rows -- searched in parallel it costs about one tile time.
+constexpr int64_t kSeedUnitMin = 224;  // = list capacity (256 for k <= 128) - one 32-column chunk
+static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
   static const int64_t forced = [] {
     const char* e = getenv("KNN_SEED_ROWS");
     return e ? (int64_t)atoll(e) : (int64_t)-1;
   }();
-  if (forced >= 0) return forced;
-  const double budget = 0.005 * (double)ng * (double)qblocks / (double)slots;
-  int64_t rows = 4096;
-  while (rows * 2 <= 65536 && (double)(rows * 2) <= budget) rows *= 2;
-  return rows;
+  g.seed_splits = 0;
+  g.seed_len = 0;
+  int64_t rows = forced;
+  if (rows < 0) {
+    const double budget = 0.005 * (double)ng * (double)g.qblocks / (double)slots;
+    rows = 4096;
+    while (rows * 2 <= 65536 && (double)(rows * 2) <= budget) rows *= 2;
+  }
+  if (rows <= 0) return;
+  int64_t units = (2 * slots + g.qblocks - 1) / g.qblocks;
+  if (units < 1) units = 1;
+  int64_t len = (rows + units - 1) / units;
+  if (len < kSeedUnitMin) len = kSeedUnitMin;
+  if (g.L - 32 < kSeedUnitMin && len < 4096) len = 4096;  // small k: short lists compact anyway, keep units long
+  (void)tile;
+  while (units > 1 && units * len > ng / 8) --units;       // the sample stays a small prefix of the gallery
+  if (units * len > ng / 8) return;
+  g.seed_splits = (int)units;
+  g.seed_len = len;
 }
 
 }  // namespace knn
@@ -144,16 +172,16 @@ using namespace knn;
 extern "C" int knn_version(void) { return KNN_ABI_VERSION; }
 extern "C" const char* knn_last_error(void) { return g_err; }
 
-// Workspace layout: tau_global [qblocks*128] u32 | counts [(splits+1)*groups][qblocks*128] i32 |
-//                   lists [(splits+1)*groups][qblocks*128][L] u64.  The "+1" split is the scratch of the
-//                   threshold-seeding pre-pass.
+// Workspace layout: tau_global [qblocks*128] u32 | counts [(splits+seed_splits)*groups][qblocks*128] i32 |
+//                   lists [(splits+seed_splits)*groups][qblocks*128][L] u64.  The extra splits are the scratch of
+//                   the threshold-seeding pre-pass.
 struct WsLayout {
   size_t tau_bytes, counts_bytes, lists_bytes;
 };
 static WsLayout ws_layout(const SearchGeom& g) {
   WsLayout w;
   const size_t rows = (size_t)g.qblocks * kRowsPerUnit;
-  const size_t vsplits = (size_t)((g.splits > 0 ? g.splits : 1) + 1) * g.groups;
+  const size_t vsplits = (size_t)((g.splits > 0 ? g.splits : 1) + g.seed_splits) * g.groups;
   w.tau_bytes = align_up(rows * sizeof(uint32_t), 256);
   w.counts_bytes = align_up(vsplits * rows * sizeof(int32_t), 256);
   w.lists_bytes = vsplits * rows * (size_t)g.L * sizeof(uint64_t);
@@ -203,7 +231,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   const SearchGeom geo = make_geom(nq, ng, d, dtype, k);
-  const bool ts = use_ts(dtype, d);
+  const bool ts = use_ts(dtype, d, geo.qblocks);
 
   SearchParams p;
   memset(&p, 0, sizeof(p));
@@ -228,17 +256,13 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   if (geo.splits > 0) {
     KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
     if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
-    // Threshold seeding: a pre-pass searches the first kSeedRows gallery rows (lists in the scratch split) and a
-    // unit merge in seeding mode publishes each row's exact k-th best score of that sample in tau_global -- a valid
-    // lower bound of the final k-th best.  The main pass then starts with a pass rate of ~k / kSeedRows instead of
-    // accepting everything until each list has filled up.  The sample's candidates are discarded (the main pass
-    // visits those rows again).
-    const int64_t kSeedRows = seed_rows(ng, geo.qblocks, (int64_t)sm_count() * (dtype == KNN_BF16 ? 1 : 2));
-    if (kSeedRows > 0 && ng >= 8 * kSeedRows) {
+    // Threshold seeding (see seed_geometry): search the sample into the scratch lists, merge in seeding mode.
+    // The sample's candidates are discarded -- the main pass visits those rows again.
+    if (geo.seed_splits > 0) {
       SearchParams ps = p;
-      ps.ng = kSeedRows;
-      ps.splits = 1;
-      ps.split_len = kSeedRows;
+      ps.ng = (int64_t)geo.seed_splits * geo.seed_len;
+      ps.splits = geo.seed_splits;
+      ps.split_len = geo.seed_len;
       const size_t scratch_rows = (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit;
       ps.lists = p.lists + scratch_rows * (size_t)geo.L;
       ps.counts = p.counts + scratch_rows;

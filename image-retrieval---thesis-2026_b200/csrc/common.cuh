@@ -78,6 +78,8 @@ struct SearchGeom {
   int64_t split_len;  // gallery rows per split (multiple of the column tile)
   int kp;             // padded k
   int L;              // list capacity per row
+  int seed_splits;    // units per query block of the threshold-seeding pre-pass (0 = none)
+  int64_t seed_len;   // gallery rows per seeding unit
 };
 
 }  // namespace knn

@@ -53,6 +53,7 @@ struct TsCfg {
   int stages;        // ring depth
   int nkb;           // k-blocks
   int tn;            // gallery rows per tile (whole CTA group)
+  int acc_stages;    // accumulator stages in TMEM: 2 when the query tile leaves room, else 1
   uint32_t stage_bytes;  // per CTA: (tn / CG) rows x 128 B
   int debug;         // KNN_TS_DEBUG (timing experiments, results are garbage): bit 0 = no MMA, bit 1 = selection
                      // fast path only, bit 2 = no TMA (MMAs run on whatever the ring holds), bit 3 = no selection
@@ -83,7 +84,8 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
   const int ntiles = c_end > c_begin ? (int)((c_end - c_begin + TN - 1) / TN) : 0;
   const int nkb = cfg.nkb;
   const int stages = cfg.stages;
-  const uint32_t a_col0 = 2u * (uint32_t)TN;  // TMEM column of the query tile (after the two accumulator stages)
+  const int ACC = cfg.acc_stages;
+  const uint32_t a_col0 = (uint32_t)(ACC * TN);  // TMEM column of the query tile (after the accumulator stages)
 
   if (threadIdx.x == 0) {
     if (ptx::smem_u32(smem) & 1023u) {
@@ -166,8 +168,8 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
       const uint32_t a_tmem0 = tmem_base + a_col0;
       const bool issuer = ptx::elect_one();
       for (int t = 0; t < ntiles; ++t) {
-        const int as = t & 1;
-        const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+        const int as = ACC == 2 ? (t & 1) : 0;
+        const uint32_t aphase = (uint32_t)(ACC == 2 ? (t >> 1) : t) & 1u;
         long long c0 = stats_on ? clock64() : 0;
         ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         if (stats_on) w_tmem += clock64() - c0;
@@ -265,10 +267,10 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
     const long long e_begin = stats_on ? clock64() : 0;
 
     for (int t = 0; t < ntiles; ++t) {
-      const int as = t & 1;
-      const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+      const int as = ACC == 2 ? (t & 1) : 0;
+      const uint32_t aphase = (uint32_t)(ACC == 2 ? (t >> 1) : t) & 1u;
       const int64_t col0 = c_begin + (int64_t)t * TN;
-      float* gst = gs + as * kMaxTileN;
+      float* gst = gs + (t & 1) * kMaxTileN;
       if (kL2) {
         if (et < TN) {
           int64_t c = col0 + et;
@@ -364,11 +366,15 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
     set_error("internal: d=%d does not fit the TMEM-resident query tile", p.d);
     return KNN_E_INVALID;
   }
+  cfg.acc_stages = (kTmemCols - cfg.nkb * (BKE / 2)) >= 2 * cfg.tn ? 2 : 1;
   const int rows_cta = cfg.tn / CG;
   cfg.stage_bytes = (uint32_t)rows_cta * BKE * 2;
   const size_t fixed = sizeof(float) * 2 * kMaxTileN + sizeof(TsBarriers);
   int stages = (int)((kSmemBudget - fixed) / cfg.stage_bytes);
   cfg.stages = stages > kMaxStages ? kMaxStages : stages;
+  // one CTA per unit = HBM-bound streaming: ~128 KB in flight per SM is the sweet spot (tools/tma_probe.cu: 8 slots
+  // of 16 KB stream at 7.3 TB/s, 13 slots at 6.5 TB/s)
+  if (CG == 1 && cfg.stages > 8) cfg.stages = 8;
   if (const int want = env_int_ts("KNN_TS_STAGES")) {
     if (want >= 2 && want < cfg.stages) cfg.stages = want;
   }
@@ -426,13 +432,10 @@ int launch_cg(const SearchParams& p, cudaStream_t stream) {
 }  // namespace
 
 // Gallery rows per tile when the query tile lives in TMEM: 512 columns = D/2 (A, rounded up to whole k-blocks)
-// + two accumulator stages.  0 = does not fit (use the shared-memory-A kernels).
+// + one or two accumulator stages of 128 columns.  0 = does not fit (use the shared-memory-A kernels).
 int ts_tile_cols(int d) {
   const int a_cols = ((d + BKE - 1) / BKE) * (BKE / 2);
-  const int left = kTmemCols - a_cols;
-  if (left >= 2 * 128) return 128;
-  if (left >= 2 * 64) return 64;
-  return 0;  // a 32-row tile is legal but too small to be worth a third shape
+  return kTmemCols - a_cols >= 128 ? 128 : 0;
 }
 
 int launch_search_bf16_ts(const SearchParams& p, cudaStream_t stream) {
