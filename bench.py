@@ -261,22 +261,16 @@ def main():
     for _ in range(2):
         step_e2e()
 
-    # ---- timed region: device-resident, with clocks sampled and the dominant kernel's own events ----------
+    # ---- timed region: device-resident, clocks sampled; the library records CUDA events around its kernels on the
+    # launching stream during these very steps (no synchronisation), read back after the region has ended ----------
     lib.knn_profile_enable(1)
-    kern_ms = []
-
-    def step_profiled():
-        out = step_resident()
-        a, b = ctypes.c_float(), ctypes.c_float()
-        _lib.check(lib.knn_profile_last(ctypes.byref(a), ctypes.byref(b)), "knn_profile_last")
-        kern_ms.append((a.value, b.value))
-        return out
-
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step_resident, args.steps)
-    lib.knn_profile_enable(1)
-    for _ in range(min(args.steps, 3)):                   # separate passes: the profile query synchronises
-        step_profiled()
+    kern_ms = []
+    for i in range(max(0, lib.knn_profile_count() - args.steps), lib.knn_profile_count()):
+        sd, a, b = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
+        _lib.check(lib.knn_profile_read(i, ctypes.byref(sd), ctypes.byref(a), ctypes.byref(b)), "knn_profile_read")
+        kern_ms.append((a.value, b.value, sd.value))
     lib.knn_profile_enable(0)
     e2e_ms = timed(step_e2e, args.steps)
 
@@ -284,8 +278,9 @@ def main():
     value = nq / (ms_per_step / 1e3)
     e2e_value = nq / (e2e_ms / args.steps / 1e3)
     peaks = load_peaks()
-    dist_ms = sum(a for a, _ in kern_ms) / len(kern_ms)
-    merge_ms = sum(b for _, b in kern_ms) / len(kern_ms)
+    dist_ms = sum(a for a, _, _ in kern_ms) / len(kern_ms)     # the dominant kernel alone
+    merge_ms = sum(b for _, b, _ in kern_ms) / len(kern_ms)
+    seed_ms = sum(c for _, _, c in kern_ms) / len(kern_ms)     # threshold-seeding pre-pass + seeding merge
     flops = 2.0 * nq * count * d
     achieved = flops / (dist_ms / 1e3) / 1e12
     gallery_gbs = count * d * 2 / (dist_ms / 1e3) / 1e9
@@ -293,6 +288,9 @@ def main():
     ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
     hbm_bound = nq < ridge
     algo_bytes = count * d * 2 + nq * d * 2 + nq * k * 12
+    # dispatch rule of knn_search (csrc/api.cu): one 128-row query block and d <= 768 -> TMEM-resident-query kernel,
+    # several query blocks -> CTA-pair kernel
+    kernel_name = ("search_bf16_ts_kernel" if d <= 768 else "search_bf16_kernel") if nq <= 128 else "search_bf16_pair_kernel"
 
     # recall sanity of the timed configuration is covered by tests; here only the top-1 self-consistency
     line = {
@@ -306,21 +304,23 @@ def main():
         },
         "roofline": ({
             "bound": "hbm", "achieved": algo_bytes / (dist_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": algo_bytes / (dist_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-            "kernel": "search_bf16_kernel (+ its threshold-seeding pre-pass launch)", "kernel_ms": dist_ms,
+            "frac": algo_bytes / (dist_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "traffic": traffic_bytes(args.workload, nq, count, d), "algorithmic_bytes": algo_bytes,
+            "kernel": kernel_name, "kernel_ms": dist_ms, "seeding_ms": seed_ms,
             "merge_kernel_ms": merge_ms, "tensor_TFLOPs": achieved, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
         } if hbm_bound else {
             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["tflops"], "traffic": traffic_bytes(args.workload, nq, count, d),
-            "kernel": "search_bf16_pair_kernel (+ its threshold-seeding pre-pass launch)",
+            "kernel": kernel_name, "seeding_ms": seed_ms,
             "kernel_ms": dist_ms, "merge_kernel_ms": merge_ms, "gallery_stream_GBps": gallery_gbs,
             "algorithmic_bytes": algo_bytes,
             "peak_source": peaks["source"],
         }),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps},
-        # per step: seeding pre-pass + distance/selection kernel + unit merge (+ k-way shard merge after the all-gather)
-        "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+        # per step: seeding pre-pass + seeding merge + distance/selection kernel + unit merge
+        # (+ k-way shard merge after the all-gather)
+        "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
         "clocks": clocks.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -30,6 +30,8 @@ SIGNATURES = {
     "knn_search": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
     "knn_search_workspace": (_sz, [_i64, _i64, _i, _i, _i]),
     "knn_profile_enable": (_i, [_i]),
+    "knn_profile_count": (_i, []),
+    "knn_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "knn_profile_last": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "knn_debug_stats": (_i, [C.POINTER(C.c_ulonglong), _i]),
     "knn_scores_dense": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p]),

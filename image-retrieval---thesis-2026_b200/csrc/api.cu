@@ -19,10 +19,11 @@ void set_error(const char* fmt, ...) {
 // Optional per-thread profiling: CUDA events recorded on the caller's stream right around the distance kernel
 // and the unit-merge kernel of knn_search (bench.py derives the roofline fraction of the dominant kernel from
 // these; nothing is recorded and nothing synchronises unless the caller opted in).
+constexpr int kProfSlots = 64;
 struct Profile {
   bool on = false;
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-  bool valid = false;
+  cudaEvent_t ev[kProfSlots][4] = {};  // per recorded call: start, after seeding, after the main kernel, after the merge
+  int calls = 0;                        // knn_search calls recorded since knn_profile_enable(1)
 };
 static thread_local Profile g_prof;
 
@@ -146,6 +147,9 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
   }();
   g.seed_splits = 0;
   g.seed_len = 0;
+  // the sample's threshold is shared by every list of a row: it pays for itself only when there are many of them
+  // (8192 x 50M: 74 lists per row; 25000 x 112k: 6 -- there the pre-pass cost half as much as the main pass)
+  if (forced < 0 && g.splits * g.groups < 8) return;
   int64_t rows = forced;
   if (rows < 0) {
     const double budget = 0.005 * (double)ng * (double)g.qblocks / (double)slots;
@@ -248,14 +252,14 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.dense_out = nullptr;
 
   const bool prof = g_prof.on;
+  cudaEvent_t* pev = g_prof.ev[g_prof.calls % kProfSlots];
   if (prof) {
-    for (auto& e : g_prof.ev)
-      if (!e) KNN_CHECK_CUDA(cudaEventCreate(&e));
-    g_prof.valid = false;
+    for (int i = 0; i < 4; ++i)
+      if (!pev[i]) KNN_CHECK_CUDA(cudaEventCreate(&pev[i]));
   }
   if (geo.splits > 0) {
     KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, tau_bytes, s));
-    if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
+    if (prof) KNN_CHECK_CUDA(cudaEventRecord(pev[0], s));
     // Threshold seeding (see seed_geometry): search the sample into the scratch lists, merge in seeding mode.
     // The sample's candidates are discarded -- the main pass visits those rows again.
     if (geo.seed_splits > 0) {
@@ -272,40 +276,56 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
       rc = launch_merge_units(ps, 0, nullptr, nullptr, p.tau_global, s);
       if (rc != KNN_OK) return rc;
     }
+    if (prof) KNN_CHECK_CUDA(cudaEventRecord(pev[1], s));
     rc = ts ? launch_search_bf16_ts(p, s)
             : (dtype == KNN_BF16) ? launch_search_bf16(p, s) : launch_search_f32(p, false, s);
     if (rc != KNN_OK) return rc;
   } else if (prof) {
-    KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[0], s));
+    KNN_CHECK_CUDA(cudaEventRecord(pev[0], s));
+    KNN_CHECK_CUDA(cudaEventRecord(pev[1], s));
   }
-  if (prof) KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[1], s));
+  if (prof) KNN_CHECK_CUDA(cudaEventRecord(pev[2], s));
   rc = launch_merge_units(p, index_base, out_val, out_idx, nullptr, s);
   if (rc != KNN_OK) return rc;
   if (prof) {
-    KNN_CHECK_CUDA(cudaEventRecord(g_prof.ev[2], s));
-    g_prof.valid = true;
+    KNN_CHECK_CUDA(cudaEventRecord(pev[3], s));
+    ++g_prof.calls;
   }
   return KNN_OK;
 }
 
 extern "C" int knn_profile_enable(int on) {
   g_prof.on = on != 0;
-  g_prof.valid = false;
+  g_prof.calls = 0;
+  return KNN_OK;
+}
+
+extern "C" int knn_profile_count(void) { return g_prof.calls; }
+
+extern "C" int knn_profile_read(int call, float* seed_ms, float* distance_ms, float* merge_ms) {
+  if (call < 0 || call >= g_prof.calls || call < g_prof.calls - kProfSlots) {
+    set_error("knn_profile_read: call %d not recorded (%d calls since enable, last %d kept)", call, g_prof.calls,
+              kProfSlots);
+    return KNN_E_INVALID;
+  }
+  cudaEvent_t* pev = g_prof.ev[call % kProfSlots];
+  KNN_CHECK_CUDA(cudaEventSynchronize(pev[3]));
+  float sd = 0.f, a = 0.f, b = 0.f;
+  KNN_CHECK_CUDA(cudaEventElapsedTime(&sd, pev[0], pev[1]));
+  KNN_CHECK_CUDA(cudaEventElapsedTime(&a, pev[1], pev[2]));
+  KNN_CHECK_CUDA(cudaEventElapsedTime(&b, pev[2], pev[3]));
+  if (seed_ms) *seed_ms = sd;
+  if (distance_ms) *distance_ms = a;
+  if (merge_ms) *merge_ms = b;
   return KNN_OK;
 }
 
 extern "C" int knn_profile_last(float* distance_ms, float* merge_ms) {
-  if (!g_prof.valid) {
+  if (g_prof.calls == 0) {
     set_error("knn_profile_last: no profiled knn_search call on this thread");
     return KNN_E_INVALID;
   }
-  KNN_CHECK_CUDA(cudaEventSynchronize(g_prof.ev[2]));
-  float a = 0.f, b = 0.f;
-  KNN_CHECK_CUDA(cudaEventElapsedTime(&a, g_prof.ev[0], g_prof.ev[1]));
-  KNN_CHECK_CUDA(cudaEventElapsedTime(&b, g_prof.ev[1], g_prof.ev[2]));
-  if (distance_ms) *distance_ms = a;
-  if (merge_ms) *merge_ms = b;
-  return KNN_OK;
+  return knn_profile_read(g_prof.calls - 1, nullptr, distance_ms, merge_ms);
 }
 
 extern "C" int knn_debug_stats(unsigned long long* out32, int reset) {

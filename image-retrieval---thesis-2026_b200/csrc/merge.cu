@@ -17,8 +17,9 @@ __device__ __forceinline__ void smem_bitonic(uint64_t* s, int n, int size_from, 
     int stride = size >> 1;
     if (stride > stride_cap) stride = stride_cap;
     for (; stride > 0; stride >>= 1) {
+      const int lowmask = stride - 1;  // strides are powers of two: no integer division in the inner loop
       for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
-        const int pos = ((i / stride) * (stride << 1)) + (i % stride);
+        const int pos = ((i & ~lowmask) << 1) | (i & lowmask);
         const bool desc = (((gbase + pos) & (int64_t)size) == 0);
         uint64_t a = s[pos], b = s[pos + stride];
         const bool swap = desc ? (a < b) : (a > b);
@@ -47,8 +48,10 @@ __device__ __forceinline__ int pow2_ge(int x) {
 __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams p, int64_t index_base,
                                                                  float* __restrict__ out_val,
                                                                  int64_t* __restrict__ out_idx,
-                                                                 uint32_t* __restrict__ tau_out) {
-  __shared__ uint64_t s[kSortCap];
+                                                                 uint32_t* __restrict__ tau_out, int cap) {
+  // `cap` (power of two <= kSortCap) = shared-memory sort capacity of this launch: min(kSortCap, keys per row)
+  extern __shared__ __align__(16) uint8_t merge_smem[];
+  uint64_t* s = reinterpret_cast<uint64_t*>(merge_smem);
   __shared__ int hist[256];
   __shared__ int n_surv;
   __shared__ unsigned long long sh_lo;
@@ -60,14 +63,18 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   const bool l2 = p.metric == KNN_L2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
-  // visit every key of this row: warp w walks lists w, w + nwarps, ...; lanes stride through a list (coalesced)
+  // visit every key of this row: warp w walks lists w, w + nwarps, ...; lanes stride through a list (coalesced).
+  // fn(key, valid) is called by ALL lanes of the warp in every iteration (warp-aggregated atomics inside).
   auto for_each_key = [&](auto&& fn) {
     for (int v = warp; v < V; v += nwarps) {
       const int64_t unit_row = ((int64_t)v * p.qblocks + qb) * kRowsPerUnit + lr;
       int cnt = __ldcg(p.counts + unit_row);
       cnt = cnt < 0 ? 0 : (cnt > L ? L : cnt);
       const uint64_t* base = p.lists + unit_row * (int64_t)L;
-      for (int j = lane; j < cnt; j += 32) fn(__ldcg(base + j));
+      for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const bool valid = j0 + lane < cnt;
+        fn(valid ? __ldcg(base + j0 + lane) : 0ull, valid);
+      }
     }
   };
 
@@ -76,14 +83,14 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   __syncthreads();
   {
     int c = 0;
-    for_each_key([&](uint64_t key) { c += key >= lo ? 1 : 0; });
+    for_each_key([&](uint64_t key, bool valid) { c += (valid && key >= lo) ? 1 : 0; });
     c = __reduce_add_sync(0xFFFFFFFFu, c);
     if (lane == 0 && c) atomicAdd(&n_surv, c);
   }
   __syncthreads();
   const int total = n_surv;
   __syncthreads();
-  if (total > kSortCap) {
+  if (total > cap) {
     // MSB radix select of the k-th largest key among the keys >= lo.  sh_kk = rank still to find inside the
     // current bin; k - sh_kk = keys known to lie strictly above it (all of them are in the answer).
     if (threadIdx.x == 0) {
@@ -96,8 +103,8 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
       const unsigned long long prefix = sh_lo;
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for_each_key([&](uint64_t key) {
-        if (key >= lo && (d == 56 || (key >> (d + 8)) == (prefix >> (d + 8))))
+      for_each_key([&](uint64_t key, bool valid) {
+        if (valid && key >= lo && (d == 56 || (key >> (d + 8)) == (prefix >> (d + 8))))
           atomicAdd(&hist[(int)((key >> d) & 255ull)], 1);
       });
       __syncthreads();
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
         sh_kk = kk - acc;
         sh_lo = prefix | ((unsigned long long)b << d);
         const int cnt_ge = (p.k - sh_kk) + hist[b];  // keys >= the new bound
-        sh_done = (cnt_ge <= kSortCap || d == 0) ? 1 : 0;
+        sh_done = (cnt_ge <= cap || d == 0) ? 1 : 0;
       }
       __syncthreads();
       if (sh_done) break;
@@ -121,14 +128,75 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   }
   if (threadIdx.x == 0) n_surv = 0;
   __syncthreads();
-  for_each_key([&](uint64_t key) {
-    if (key >= lo) {
-      const int slot = atomicAdd(&n_surv, 1);
-      if (slot < kSortCap) s[slot] = key;
-    }
+  for_each_key([&](uint64_t key, bool valid) {
+    const bool keep = valid && key >= lo;
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(&n_surv, __popc(b));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const int slot = base + __popc(b & ((1u << lane) - 1u));
+    if (keep && slot < cap) s[slot] = key;
   });
   __syncthreads();
-  const int ns = n_surv < kSortCap ? n_surv : kSortCap;
+  int ns = n_surv < cap ? n_surv : cap;
+  __syncthreads();
+  if (ns > 4 * p.kp) {
+    // Still far more survivors than k: the bitonic network below costs O(n log^2 n) shared-memory passes, so first
+    // cut the set down with the same MSB radix select, now over the keys held in shared memory (a pass is ns/threads
+    // shared-memory atomics per thread), stopping as soon as at most 2*KP keys are >= the bound.
+    if (threadIdx.x == 0) {
+      sh_lo = 0ull;
+      sh_kk = p.k;
+      sh_done = 0;
+    }
+    __syncthreads();
+    for (int d = 56; d >= 0; d -= 8) {
+      const unsigned long long prefix = sh_lo;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const uint64_t key = s[i];
+        if (d == 56 || (key >> (d + 8)) == (prefix >> (d + 8))) atomicAdd(&hist[(int)((key >> d) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int kk = sh_kk;
+        int acc = 0, b = 255;
+        for (; b > 0; --b) {
+          if (acc + hist[b] >= kk) break;
+          acc += hist[b];
+        }
+        sh_kk = kk - acc;
+        sh_lo = prefix | ((unsigned long long)b << d);
+        const int cnt_ge = (p.k - sh_kk) + hist[b];
+        sh_done = (cnt_ge <= 2 * p.kp || d == 0) ? 1 : 0;
+      }
+      __syncthreads();
+      if (sh_done) break;
+    }
+    // compact the keys >= bound to the front: every thread first pulls its keys into registers (cap / threads = 8)
+    const unsigned long long bound = sh_lo;
+    uint64_t mine[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = threadIdx.x + e * blockDim.x;
+      mine[e] = i < ns ? s[i] : 0ull;
+    }
+    if (threadIdx.x == 0) n_surv = 0;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const bool keep = mine[e] != 0ull && mine[e] >= bound;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+      int base = 0;
+      if (lane == 0 && b) base = atomicAdd(&n_surv, __popc(b));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (keep) s[base + __popc(b & ((1u << lane) - 1u))] = mine[e];
+    }
+    __syncthreads();
+    ns = n_surv;
+    __syncthreads();
+  }
   const int n = pow2_ge(ns > p.k ? ns : p.k);
   for (int i = ns + threadIdx.x; i < n; i += blockDim.x) s[i] = 0ull;
   __syncthreads();
@@ -284,7 +352,14 @@ __global__ void __launch_bounds__(kSortThreads) rank_rows_kernel(const float* __
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
                        uint32_t* tau_out, cudaStream_t stream) {
   if (p.nq == 0) return KNN_OK;
-  merge_units_kernel<<<(unsigned)p.nq, kSortThreads, 0, stream>>>(p, index_base, out_val, out_idx, tau_out);
+  // size the CTA and its sort buffer to the input: few short lists per row (small galleries, many queries) get
+  // small CTAs so that many rows are merged per SM at once
+  const int64_t max_keys = (int64_t)p.splits * p.groups * 2 * p.kp;
+  int cap = 2 * p.kp;  // >= k, power of two
+  while (cap < max_keys && cap < kSortCap) cap <<= 1;
+  const int threads = cap <= 1024 ? 128 : (cap <= 2048 ? 256 : kSortThreads);
+  merge_units_kernel<<<(unsigned)p.nq, threads, (size_t)cap * sizeof(uint64_t), stream>>>(p, index_base, out_val,
+                                                                                        out_idx, tau_out, cap);
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
 }

@@ -92,10 +92,16 @@ KNN_API int knn_search(const void* q, const void* g, const float* q_sqnorm, cons
                void* workspace, size_t workspace_bytes, void* stream);
 KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k);
 
-/* Opt-in, per calling thread: knn_search records CUDA events on its stream around (a) the distance+select
- * kernel and (b) the unit-merge kernel; knn_profile_last synchronises on them and returns the two durations of
- * the most recent knn_search call (measurement harness only; host pointers). */
+/* Opt-in, per calling thread: knn_search records CUDA events on its stream around (s) the threshold-seeding
+ * pre-pass + seeding merge, (a) the main distance+select kernel and (b) the unit-merge kernel.  Recording does not
+ * synchronise, so a
+ * measurement harness can leave it on during a timed region and read the per-call durations afterwards:
+ * knn_profile_enable(1) resets the call counter, knn_profile_count() = calls recorded since, knn_profile_read(i)
+ * synchronises on call i's last event and returns its durations (the last 64 calls are kept; host pointers,
+ * each nullable); knn_profile_last = (a), (b) of the most recent call. */
 KNN_API int knn_profile_enable(int on);
+KNN_API int knn_profile_count(void);
+KNN_API int knn_profile_read(int call, float* seed_ms_host, float* distance_ms_host, float* merge_ms_host);
 KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
 /* Diagnostics, off unless the process was started with KNN_PAIR_STATS=1: the tcgen05 kernels then add the cycles
  * their TMA / MMA / selection roles spend waiting on each other to 32 device counters (layout: DESIGN.md
