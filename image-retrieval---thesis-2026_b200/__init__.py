@@ -7,9 +7,10 @@ Drop-in for the query x gallery similarity-search hot path of CrispyChillies/Ima
 from ._lib import KnnError, LIB_PATH, load as load_library
 from .search import FlatIndex, merge_topk, normalize, rank_rows, row_sqnorm, scores_dense, search
 from . import metrics
+from . import fusion
 from .sharded import ShardedFlatIndex
 
 __all__ = [
     "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
-    "rank_rows", "row_sqnorm", "scores_dense", "search", "metrics",
+    "rank_rows", "row_sqnorm", "scores_dense", "search", "metrics", "fusion",
 ]

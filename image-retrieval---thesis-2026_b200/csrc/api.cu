@@ -340,6 +340,73 @@ extern "C" int knn_debug_stats(unsigned long long* out32, int reset) {
   return KNN_OK;
 }
 
+extern "C" size_t knn_score_stats_workspace(int64_t nq, int64_t ng) {
+  if (nq <= 0 || ng <= 0) return 0;
+  const int64_t qblocks = (nq + kRowsPerUnit - 1) / kRowsPerUnit;
+  const int64_t ntiles = (ng + 127) / 128;
+  int64_t want = ((int64_t)2 * 2 * sm_count() + qblocks - 1) / qblocks;
+  if (want > ntiles) want = ntiles;
+  if (want < 1) want = 1;
+  const int64_t tps = (ntiles + want - 1) / want;
+  const int64_t splits = (ntiles + tps - 1) / tps;
+  return (size_t)splits * qblocks * kRowsPerUnit * 4 * sizeof(double);
+}
+
+extern "C" int knn_score_stats(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm, int64_t nq,
+                               int64_t ng, int d, int dtype, int metric, int self_mode, int64_t self_offset,
+                               double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
+  if (rc != KNN_OK) return rc;
+  if (dtype != KNN_F32) {
+    set_error("knn_score_stats: fp32 inputs only");
+    return KNN_E_UNSUPPORTED;
+  }
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(out, "null output pointer");
+  KNN_REQUIRE(ng > 0, "knn_score_stats: empty gallery");
+  const size_t need = knn_score_stats_workspace(nq, ng);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("knn_score_stats: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return KNN_E_WORKSPACE;
+  }
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.g = g; p.qsq = q_sqnorm; p.gsq = g_sqnorm;
+  p.nq = nq; p.ng = ng; p.d = d; p.k = 1; p.kp = 32;
+  p.metric = metric; p.self_mode = self_mode; p.self_offset = self_offset;
+  p.groups = 1;
+  p.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
+  const int64_t ntiles = (ng + 127) / 128;
+  int64_t want = ((int64_t)2 * 2 * sm_count() + p.qblocks - 1) / p.qblocks;
+  if (want > ntiles) want = ntiles;
+  if (want < 1) want = 1;
+  const int64_t tps = (ntiles + want - 1) / want;
+  p.split_len = tps * 128;
+  p.splits = (int)((ntiles + tps - 1) / tps);
+  p.stats_out = reinterpret_cast<double*>(workspace);
+  rc = launch_search_f32(p, false, (cudaStream_t)stream);
+  if (rc != KNN_OK) return rc;
+  return launch_stats_reduce(p.stats_out, p.splits, p.qblocks, nq, out, (cudaStream_t)stream);
+}
+
+extern "C" int knn_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table,
+                                int64_t table_rows, int table_cols, const int64_t* qcol, float alpha, float beta,
+                                int first_m, int64_t self_offset, int mask_self, float* out_vals, void* stream) {
+  KNN_REQUIRE(nq >= 0 && k >= 1 && table_rows >= 0 && table_cols >= 1, "knn_rescore_topk: bad sizes");
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(vals && idx && table && qcol && out_vals, "knn_rescore_topk: null pointer");
+  return launch_rescore_topk(vals, idx, nq, k, table, table_rows, table_cols, qcol, alpha, beta, first_m, self_offset,
+                             mask_self, out_vals, (cudaStream_t)stream);
+}
+
+extern "C" int knn_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
+                             int64_t* out_idx, void* stream) {
+  KNN_REQUIRE(nq >= 0 && k >= 1 && k <= 4096, "knn_sort_topk: k must be in [1, 4096], got %d", k);
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(vals && idx && out_vals && out_idx, "knn_sort_topk: null pointer");
+  return launch_sort_topk(vals, idx, nq, k, largest, out_vals, out_idx, (cudaStream_t)stream);
+}
+
 extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
                                 int64_t nq, int64_t ng, int d, int dtype, int metric, int self_mode,
                                 int64_t self_offset, float* out, void* stream) {

@@ -25,6 +25,7 @@ struct SearchParams {
   int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
   float* dense_out;      // dense mode only
+  double* stats_out;     // statistics mode only: [splits][qblocks][128][4] = sum, sum of squares, min, max
 };
 
 int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream);
@@ -33,6 +34,16 @@ int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream);  // cta
 int bf16_tile_cols();  // gallery rows per tile of the shared-memory-A tcgen05 kernels
 int launch_search_bf16_ts(const SearchParams& p, cudaStream_t stream);    // query tile in TMEM, csrc/search_ts.cu
 int ts_tile_cols(int d);  // gallery rows per tile of the TMEM-resident kernel, 0 = d does not fit
+
+// out[q][0..3] = sum, sum of squares, min, max over the splits' partials (splits summed in ascending order)
+int launch_stats_reduce(const double* partials, int splits, int qblocks, int64_t nq, double* out, cudaStream_t stream);
+// vals[q][j] <- rn(rn(alpha*vals[q][j]) + rn(beta*table[idx[q][j]][qcol[q]])) for j < first_m, idx != self (test.py:612-621)
+int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table, int64_t table_rows,
+                        int table_cols, const int64_t* qcol, float alpha, float beta, int first_m, int64_t self_offset,
+                        int mask_self, float* out_vals, cudaStream_t stream);
+// order k (value, index) candidates per row best-first, ties by ascending index
+int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
+                     int64_t* out_idx, cudaStream_t stream);
 
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();

@@ -30,7 +30,7 @@ __device__ __forceinline__ void smem_bitonic(uint64_t* s, int n, int size_from, 
   }
 }
 
-__device__ __forceinline__ int pow2_ge(int x) {
+__host__ __device__ __forceinline__ int pow2_ge(int x) {
   int p = 2;
   while (p < x) p <<= 1;
   return p;
@@ -348,6 +348,103 @@ __global__ void __launch_bounds__(kSortThreads) rank_rows_kernel(const float* __
 }
 
 }  // namespace
+
+__global__ void stats_reduce_kernel(const double* __restrict__ partials, int splits, int qblocks, int64_t nq,
+                                    double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nq) return;
+  double sum = 0.0, sq = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int sp = 0; sp < splits; ++sp) {
+    const double* pp = partials + ((int64_t)sp * qblocks * kRowsPerUnit + r) * 4;
+    sum += pp[0];
+    sq += pp[1];
+    mn = fmin(mn, pp[2]);
+    mx = fmax(mx, pp[3]);
+  }
+  out[r * 4 + 0] = sum; out[r * 4 + 1] = sq; out[r * 4 + 2] = mn; out[r * 4 + 3] = mx;
+}
+
+__global__ void rescore_topk_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int64_t nq, int k,
+                                    const float* __restrict__ table, int64_t table_rows, int table_cols,
+                                    const int64_t* __restrict__ qcol, float alpha, float beta, int first_m,
+                                    int64_t self_offset, int mask_self, float* __restrict__ out_vals) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * k) return;
+  const int64_t q = t / k;
+  const int j = (int)(t % k);
+  float v = vals[t];
+  const int64_t g = idx[t];
+  const int64_t c = qcol[q];
+  const bool is_self = self_offset >= 0 && g == self_offset + q;
+  if (j < first_m && g >= 0 && g < table_rows && !is_self && c >= 0 && c < table_cols)
+    v = __fadd_rn(__fmul_rn(alpha, v), __fmul_rn(beta, __ldg(table + g * table_cols + c)));
+  if (is_self && mask_self) v = -INFINITY;  // dists.fill_diagonal_(-inf) after the re-scoring (test.py:623)
+  out_vals[t] = v;
+}
+
+// One CTA per row: order k (value, index) candidates best-first, ties by ascending index (64-bit keys as everywhere).
+__global__ void sort_topk_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int64_t nq, int k,
+                                 int largest, float* __restrict__ out_vals, int64_t* __restrict__ out_idx) {
+  extern __shared__ __align__(16) uint8_t sort_smem[];
+  uint64_t* s = reinterpret_cast<uint64_t*>(sort_smem);
+  const int64_t r = blockIdx.x;
+  const int n = pow2_ge(k);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    uint64_t key = 0ull;
+    if (j < k) {
+      const int64_t g = idx[r * k + j];
+      const float v = vals[r * k + j];
+      if (g >= 0) key = make_key(largest ? v : (0.0f - v), (uint32_t)g);
+    }
+    s[j] = key;
+  }
+  __syncthreads();
+  smem_bitonic(s, n, 2, n, n, 0);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const uint64_t key = s[j];
+    float v; int64_t id;
+    if (key == 0ull) {
+      v = largest ? -INFINITY : INFINITY;
+      id = -1;
+    } else {
+      const float sc = key_score(key);
+      v = largest ? sc : (0.0f - sc);
+      id = (int64_t)key_row(key);
+    }
+    out_vals[r * k + j] = v;
+    out_idx[r * k + j] = id;
+  }
+}
+
+int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
+                     int64_t* out_idx, cudaStream_t stream) {
+  if (nq == 0) return KNN_OK;
+  const int n = pow2_ge(k);
+  const int threads = n >= 512 ? 256 : (n >= 128 ? 64 : 32);
+  sort_topk_kernel<<<(unsigned)nq, threads, (size_t)n * sizeof(uint64_t), stream>>>(vals, idx, nq, k, largest, out_vals,
+                                                                                  out_idx);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+int launch_stats_reduce(const double* partials, int splits, int qblocks, int64_t nq, double* out, cudaStream_t stream) {
+  if (nq == 0) return KNN_OK;
+  stats_reduce_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(partials, splits, qblocks, nq, out);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table, int64_t table_rows,
+                        int table_cols, const int64_t* qcol, float alpha, float beta, int first_m, int64_t self_offset,
+                        int mask_self, float* out_vals, cudaStream_t stream) {
+  const int64_t n = nq * k;
+  if (n == 0) return KNN_OK;
+  rescore_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(vals, idx, nq, k, table, table_rows, table_cols,
+                                                                      qcol, alpha, beta, first_m, self_offset, mask_self,
+                                                                      out_vals);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
 
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
                        uint32_t* tau_out, cudaStream_t stream) {

@@ -56,8 +56,14 @@ __device__ __forceinline__ void store_tile(float* __restrict__ T, int tid, const
   }
 }
 
-template <int E, bool kL2, bool kDense, bool kVec>
+// kMode: 0 = fused top-k selection, 1 = dense score matrix, 2 = per-row score statistics (sum, sum of squares, min,
+// max over the unit's gallery rows, accumulated in double by the row owners; fusion_eval/evaluate.py:152-177)
+constexpr int kModeSelect = 0, kModeDense = 1, kModeStats = 2;
+
+template <int E, bool kL2, int kMode, bool kVec>
 __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p) {
+  constexpr bool kDense = kMode == kModeDense;
+  constexpr bool kStats = kMode == kModeStats;
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                     // [2][BK][LDA]
   float* Bs = As + 2 * BK * LDA;        // [2][BK][LDA]
@@ -82,9 +88,11 @@ __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p)
   uint32_t self_row = 0xFFFFFFFFu;
   float qn = 0.f;
   uint32_t* tau_row = nullptr;
+  double st_sum = 0.0, st_sq = 0.0;
+  float st_min = INFINITY, st_max = -INFINITY;
   if (!kDense && owner) {
     const int64_t unit = (int64_t)sp * p.qblocks + qb;
-    rowstate_init(st, p.lists + ((unit * BM + tid) * (int64_t)L));
+    if (!kStats) rowstate_init(st, p.lists + ((unit * BM + tid) * (int64_t)L));
     if (row_valid) {
       const int64_t sr = p.self_offset + row0 + tid;
       if (p.self_mode != KNN_SELF_KEEP && sr >= 0 && sr < p.ng) self_row = (uint32_t)sr;
@@ -180,7 +188,25 @@ __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p)
         }
       }
       __syncthreads();
-      if (owner) {
+      if (owner && kStats) {
+        if (row_valid) {
+          const float* srow = Ss + tid * LDS;
+          const int64_t rem = c_end - col0;
+          const int ncols = rem >= BN ? BN : (int)rem;
+          for (int j = 0; j < ncols; ++j) {
+            float v = srow[j];
+            if (kL2) v = __fsqrt_rn(fmaxf(-fmaf(2.0f, v, -(qn + gs[j])), 0.0f));
+            if ((uint32_t)(col0 + j) == self_row) {
+              if (p.self_mode == KNN_SELF_EXCLUDE) continue;
+              if (p.self_mode == KNN_SELF_MINUS1) v = -1.0f;
+            }
+            st_sum += (double)v;
+            st_sq = fma((double)v, (double)v, st_sq);
+            st_min = fminf(st_min, v);
+            st_max = fmaxf(st_max, v);
+          }
+        }
+      } else if (owner) {
         refresh_tau<kL2>(st, tau_row);
         const float* srow = Ss + tid * LDS;
 #pragma unroll 1
@@ -202,15 +228,22 @@ __global__ void __launch_bounds__(kThreads, 2) search_f32_kernel(SearchParams p)
     }
   }
 
+  if (kStats) {
+    if (owner) {
+      double* o = p.stats_out + (((int64_t)sp * p.qblocks + qb) * BM + tid) * 4;
+      o[0] = st_sum; o[1] = st_sq; o[2] = (double)st_min; o[3] = (double)st_max;
+    }
+    return;
+  }
   // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
   if (!kDense && owner) p.counts[((int64_t)sp * p.qblocks + qb) * BM + tid] = row_valid ? st.cnt : 0;
 }
 
 size_t f32_smem_bytes() { return sizeof(float) * (size_t)(4 * BK * LDA + BM * LDS + BN); }
 
-template <int E, bool kL2, bool kDense, bool kVec>
+template <int E, bool kL2, int kMode, bool kVec>
 int launch_one(const SearchParams& p, cudaStream_t stream) {
-  auto kern = search_f32_kernel<E, kL2, kDense, kVec>;
+  auto kern = search_f32_kernel<E, kL2, kMode, kVec>;
   const size_t smem = f32_smem_bytes();
   KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);
@@ -219,11 +252,11 @@ int launch_one(const SearchParams& p, cudaStream_t stream) {
   return KNN_OK;
 }
 
-template <int E, bool kDense>
+template <int E, int kMode>
 int launch_e(const SearchParams& p, bool vec, cudaStream_t stream) {
   const bool l2 = p.metric == KNN_L2;
-  if (l2) return vec ? launch_one<E, true, kDense, true>(p, stream) : launch_one<E, true, kDense, false>(p, stream);
-  return vec ? launch_one<E, false, kDense, true>(p, stream) : launch_one<E, false, kDense, false>(p, stream);
+  if (l2) return vec ? launch_one<E, true, kMode, true>(p, stream) : launch_one<E, true, kMode, false>(p, stream);
+  return vec ? launch_one<E, false, kMode, true>(p, stream) : launch_one<E, false, kMode, false>(p, stream);
 }
 
 }  // namespace
@@ -231,12 +264,13 @@ int launch_e(const SearchParams& p, bool vec, cudaStream_t stream) {
 int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream) {
   const bool vec = (p.d % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.q) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.g) & 15) == 0);
-  if (dense) return launch_e<2, true>(p, vec, stream);
+  if (p.stats_out != nullptr) return launch_e<2, kModeStats>(p, vec, stream);
+  if (dense) return launch_e<2, kModeDense>(p, vec, stream);
   switch (p.kp) {
-    case 32: return launch_e<2, false>(p, vec, stream);
-    case 64: return launch_e<4, false>(p, vec, stream);
-    case 128: return launch_e<8, false>(p, vec, stream);
-    case 256: return launch_e<16, false>(p, vec, stream);
+    case 32: return launch_e<2, kModeSelect>(p, vec, stream);
+    case 64: return launch_e<4, kModeSelect>(p, vec, stream);
+    case 128: return launch_e<8, kModeSelect>(p, vec, stream);
+    case 256: return launch_e<16, kModeSelect>(p, vec, stream);
     default: set_error("unsupported padded k %d", p.kp); return KNN_E_UNSUPPORTED;
   }
 }

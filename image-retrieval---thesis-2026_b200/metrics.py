@@ -353,17 +353,15 @@ def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.
     return metrics
 
 
-def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Optional[Sequence] = None,
-                               k_values: Iterable[int] = (1, 5, 10)) -> Dict[str, float]:
-    """fusion_eval/metrics.py:26-94 (labels may be strings; image paths are assumed unique, as the reference's
-    aligned embedding sets are)."""
-    emb = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not isinstance(embeddings, torch.Tensor) \
-        else embeddings
-    emb = emb.cuda() if not emb.is_cuda else emb
+def retrieval_metrics_from_ranking(idx: torch.Tensor, labels: Sequence,
+                                   k_values: Iterable[int] = (1, 5, 10)) -> Dict[str, float]:
+    """fusion_eval/metrics.py:41-94 from a FULL self-retrieval ranking ``idx`` [N, N-1] (self removed): standard AP
+    over the ranking / (#same-label - 1), ``mP@k = hits/k``, ``R@k`` any-hit, 0.0 for queries without relevant items.
+    Image paths are assumed unique (the reference's aligned embedding sets are), so dropping the self entry is the
+    reference's by-path filter."""
     _, inv = np.unique(np.asarray(labels), return_inverse=True)
-    lab = torch.as_tensor(inv, dtype=torch.int64, device=emb.device)
+    lab = torch.as_tensor(inv, dtype=torch.int64, device=idx.device)
     k_values = sorted(set(int(k) for k in k_values))
-    _, idx = _self_retrieval_full(emb)
     rel, _ = relevance_single(idx, lab, lab)
     hits, _, _, prec_sum = ranked_stats(rel)
     hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
@@ -375,6 +373,17 @@ def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Option
         metrics[f"mP@{k}"] = float(np.mean(hk / k) * 100.0)
         metrics[f"R@{k}"] = float(np.mean((hk > 0).astype(np.float64)) * 100.0)
     return metrics
+
+
+def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Optional[Sequence] = None,
+                               k_values: Iterable[int] = (1, 5, 10)) -> Dict[str, float]:
+    """fusion_eval/metrics.py:26-94 (labels may be strings; image paths are assumed unique, as the reference's
+    aligned embedding sets are)."""
+    emb = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not isinstance(embeddings, torch.Tensor) \
+        else embeddings
+    emb = emb.cuda() if not emb.is_cuda else emb
+    _, idx = _self_retrieval_full(emb)
+    return retrieval_metrics_from_ranking(idx, labels, k_values)
 
 
 def is_retrieval_correct(query_label, retrieved_labels: Sequence, top_k: int = 1) -> bool:

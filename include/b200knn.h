@@ -108,6 +108,29 @@ KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
  * "stall counters").  Synchronises the device, copies the counters to out32 (host), optionally clears them. */
 KNN_API int knn_debug_stats(unsigned long long* out32_host, int reset);
 
+/* Per-query statistics of the scores against the WHOLE gallery without materialising them: out [nq,4] double =
+ * sum, sum of squares, min, max of score(q, g) over g (KNN_SELF_EXCLUDE leaves the query's own row out).  Replaces
+ * the row-wise mean / std / min / max of a full similarity matrix in `normalize_similarity_matrix`,
+ * fusion_eval/evaluate.py:152-177.  fp32 inputs, exact-fp32 scores (same definition as knn_scores_dense). */
+KNN_API int knn_score_stats(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
+                    int64_t nq, int64_t ng, int d, int dtype, int metric, int self_mode, int64_t self_offset,
+                    double* out, void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_score_stats_workspace(int64_t nq, int64_t ng);
+
+/* Re-score the first `first_m` candidates of every query with a per-(candidate, query column) table, the text
+ * re-ranking of test.py:612-621 / 769-777: out[q][j] = rn(rn(alpha * vals[q][j]) + rn(beta * table[idx[q][j]][qcol[q]]))
+ * for j < first_m and idx[q][j] != self_offset + q (self_offset < 0: no self), else vals[q][j] unchanged;
+ * mask_self != 0 writes -inf for the query's own entry (the `fill_diagonal_(-inf)` that follows, test.py:623).
+ * The caller re-sorts the row afterwards (knn_sort_topk). */
+KNN_API int knn_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table,
+                     int64_t table_rows, int table_cols, const int64_t* qcol, float alpha, float beta,
+                     int first_m, int64_t self_offset, int mask_self, float* out_vals, void* stream);
+/* Order k <= 4096 (value, index) candidates per row best-first (largest != 0: descending values), ties by ascending
+ * index, entries with index < 0 last; indices must be < 2^32 - 1.  The deterministic form of the `argsort` that
+ * follows a re-scoring (test.py:633). */
+KNN_API int knn_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest,
+                  float* out_vals, int64_t* out_idx, void* stream);
+
 /* Dense score matrix (small problems only; compatibility with callers that want the full `dists`
  * matrix of test.py:1080 / fusion_eval/metrics.py:15).  out [nq,ng] fp32, same score definition and
  * self handling as knn_search (KNN_SELF_EXCLUDE writes -inf for similarity, +inf for L2). */

@@ -293,3 +293,47 @@ def test_row_sharded_result_is_independent_of_shard_count(knn, precision, metric
             pi.append(i)
         v, i = knn.merge_topk(torch.stack(pv), torch.stack(pi), metric)
         assert torch.equal(i, i1) and torch.equal(v, v1), world
+
+
+# ------------------------------------------------------------------------------------------ kernel variants by env
+_VARIANT_SNIPPET = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import b200knn, oracle
+from oracle import synth
+x = synth.exact_grid(900, 256, 5, 32)                      # exactly representable: every kernel must be bit-exact
+v, i = b200knn.search(torch.from_numpy(x).cuda(), torch.from_numpy(x).cuda(), 100, "ip", exclude_self=True, precision="bf16")
+ov, oi = oracle.search(x, x, 100, "ip", "exclude", 0)
+assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(v.cpu().numpy(), ov), "grid"
+rs = np.random.RandomState(3)
+g = oracle.normalize(rs.standard_normal((40000, {d})).astype(np.float32), to_bf16=True)
+q = oracle.normalize(rs.standard_normal(({nq}, {d})).astype(np.float32), to_bf16=True)
+for metric in ("cosine", "l2"):
+    v, i = b200knn.search(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), 50, metric, precision="bf16")
+    ov, oi = oracle.search(q, g, 50, metric)
+    i = i.cpu().numpy()
+    rec = np.mean([len(set(i[r]) & set(oi[r])) / 50 for r in range({nq})])
+    assert rec >= 0.999, (metric, rec)
+    assert np.allclose(v.cpu().numpy(), ov, rtol=1e-4, atol=2e-5), metric
+print("VARIANT-OK")
+"""
+
+
+@pytest.mark.parametrize("env,nq,d", [
+    ({"KNN_BF16_TS": "1"}, 300, 512),     # TMEM-resident-query kernel on CTA pairs, two accumulator stages
+    ({"KNN_BF16_TS": "1"}, 300, 768),     # ... one accumulator stage
+    ({"KNN_BF16_TS": "0"}, 64, 768),      # one-CTA shared-memory-A kernel where the TMEM-resident one is the default
+    ({"KNN_SEED_ROWS": "0"}, 300, 512),   # no threshold-seeding pre-pass
+    ({"KNN_WAVES": "1"}, 64, 768),        # fewest splits
+])
+def test_bf16_kernel_variants_selected_by_environment(env, nq, d):
+    """The dispatch switches are read once per process, so every non-default kernel variant is exercised in a
+    subprocess: bit-exact on exactly-representable data, recall/score bars otherwise."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root, nq=nq, d=d)],
+                         env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "VARIANT-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
