@@ -8,9 +8,11 @@ from ._lib import KnnError, LIB_PATH, load as load_library
 from .search import FlatIndex, merge_topk, normalize, rank_rows, row_sqnorm, scores_dense, search
 from . import metrics
 from . import fusion
+from . import collection
+from . import formats
 from .sharded import ShardedFlatIndex
 
 __all__ = [
     "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
-    "rank_rows", "row_sqnorm", "scores_dense", "search", "metrics", "fusion",
+    "rank_rows", "row_sqnorm", "scores_dense", "search", "metrics", "fusion", "collection", "formats",
 ]
