@@ -340,6 +340,83 @@ extern "C" int knn_debug_stats(unsigned long long* out32, int reset) {
   return KNN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- Hamming
+static SearchGeom hamming_geom(int64_t nq, int64_t ng, int k) {
+  SearchGeom g;
+  memset(&g, 0, sizeof(g));
+  g.kp = kpad_for(k);
+  g.L = 2 * g.kp;
+  g.groups = 1;
+  g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
+  if (g.qblocks < 1) g.qblocks = 1;
+  const int64_t nchunks = (ng + 31) / 32;
+  int64_t want = ((int64_t)8 * sm_count() + g.qblocks - 1) / g.qblocks;   // 4 CTAs per SM, ~2 waves
+  const int64_t by_len = nchunks / 64 > 0 ? nchunks / 64 : 1;            // >= 2048 gallery rows per unit
+  if (want > by_len) want = by_len;
+  if (want < 1) want = 1;
+  const int64_t cps = nchunks > 0 ? (nchunks + want - 1) / want : 1;
+  g.split_len = cps * 32;
+  g.splits = nchunks > 0 ? (int)((nchunks + cps - 1) / cps) : 0;
+  g.seed_splits = 0;
+  g.seed_len = 0;
+  return g;
+}
+
+extern "C" size_t knn_search_hamming_workspace(int64_t nq, int64_t ng, int k) {
+  if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
+  const WsLayout w = ws_layout(hamming_geom(nq, ng < 0 ? 0 : ng, k));
+  return w.tau_bytes + w.counts_bytes + w.lists_bytes;
+}
+
+extern "C" int knn_pack_bits(const void* x, int64_t n, int bits, int in_dtype, void* out_words, void* stream) {
+  KNN_REQUIRE(n >= 0 && bits >= 1, "knn_pack_bits: bad shape n=%lld bits=%d", (long long)n, bits);
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(x && out_words, "knn_pack_bits: null pointer");
+  return launch_pack_bits(x, in_dtype, n, bits, (bits + 63) / 64, reinterpret_cast<uint64_t*>(out_words),
+                          (cudaStream_t)stream);
+}
+
+extern "C" int knn_search_hamming(const void* q_words, const void* g_words, int64_t nq, int64_t ng, int words, int k,
+                                  int self_mode, int64_t self_offset, int64_t index_base, float* out_val,
+                                  int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  KNN_REQUIRE(nq >= 0 && ng >= 0 && words >= 1, "bad shape nq=%lld ng=%lld words=%d", (long long)nq, (long long)ng, words);
+  KNN_REQUIRE(ng < 0xFFFFFFFEll, "gallery shard too large for 32-bit local rows: %lld", (long long)ng);
+  KNN_REQUIRE(self_mode == KNN_SELF_KEEP || self_mode == KNN_SELF_EXCLUDE, "bad self_mode %d", self_mode);
+  KNN_REQUIRE(k >= 1, "k must be >= 1, got %d", k);
+  if (k > kMaxFusedK) {
+    set_error("knn_search_hamming: k=%d exceeds the fused limit %d", k, kMaxFusedK);
+    return KNN_E_UNSUPPORTED;
+  }
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(out_val && out_idx && (ng == 0 || (q_words && g_words)), "null pointer");
+  const size_t need = knn_search_hamming_workspace(nq, ng, k);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("knn_search_hamming: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return KNN_E_WORKSPACE;
+  }
+  KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const SearchGeom geo = hamming_geom(nq, ng, k);
+  SearchParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q_words; p.g = g_words;
+  p.nq = nq; p.ng = ng; p.d = words * 64; p.k = k; p.kp = geo.kp;
+  p.metric = KNN_L2;  // distances: smaller = better, emitted as positive values by the unit merge
+  p.self_mode = self_mode;
+  p.self_offset = self_offset - index_base;
+  p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = 1;
+  const WsLayout wl = ws_layout(geo);
+  p.tau_global = reinterpret_cast<uint32_t*>(workspace);
+  p.counts = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes);
+  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes + wl.counts_bytes);
+  KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, wl.tau_bytes, s));
+  if (geo.splits > 0) {
+    int rc = launch_search_hamming(p, words, s);
+    if (rc != KNN_OK) return rc;
+  }
+  return launch_merge_units(p, index_base, out_val, out_idx, nullptr, s);
+}
+
 extern "C" size_t knn_score_stats_workspace(int64_t nq, int64_t ng) {
   if (nq <= 0 || ng <= 0) return 0;
   const int64_t qblocks = (nq + kRowsPerUnit - 1) / kRowsPerUnit;

@@ -45,6 +45,10 @@ int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k
 int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
                      int64_t* out_idx, cudaStream_t stream);
 
+// Hamming distance over packed 64-bit code words (csrc/search_hamming.cu); p.q / p.g point at uint64 [rows, words]
+int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream);
+int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, uint64_t* out, cudaStream_t stream);
+
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();
 

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .search import _ptr, _require_cuda, _stream, rank_rows, search
+from .search import search_hamming, _ptr, _require_cuda, _stream, rank_rows, search
 
 _NAN = float("nan")
 
@@ -244,12 +244,14 @@ def compute_classification_metrics(labels: torch.Tensor, dists: torch.Tensor, k_
 # --------------------------------------------------------------------------------------------------
 def compute_metrics(query_codes, query_labels, gallery_codes, gallery_labels, query_logits=None,
                     topk_values=(1, 5, 10), binary_codes: bool = False, precision: str = "fp32"):
-    """mHR, mAP@k, mRR, mP@k, R@k and majority-vote accuracy per cut-off, L2 ranking (ascending distance)."""
-    if binary_codes:
-        raise L.KnnError("Hamming ranking is a 'next' row (SURVEY 8(f).4); use L2 codes")
+    """mHR, mAP@k, mRR, mP@k, R@k and majority-vote accuracy per cut-off; ranking by ascending L2 distance, or by
+    Hamming distance over 0/1 codes with ``binary_codes`` (``pairwise_distance``, test_ath.py:80-87)."""
     _require_cuda(query_codes, gallery_codes)
     kmax = max(topk_values)
-    _, idx = search(query_codes.float(), gallery_codes.float(), kmax, "l2", precision=precision)
+    if binary_codes:
+        _, idx = search_hamming(query_codes, gallery_codes, kmax)
+    else:
+        _, idx = search(query_codes.float(), gallery_codes.float(), kmax, "l2", precision=precision)
     dev = idx.device
     ql, gl = _dev_i64(query_labels, dev).view(-1), _dev_i64(gallery_labels, dev).view(-1)
     rel, lab = relevance_single(idx, ql, gl)

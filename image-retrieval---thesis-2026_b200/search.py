@@ -290,6 +290,54 @@ def scores_dense(queries: torch.Tensor, gallery: torch.Tensor, metric: str = "co
     return _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, int(query_offset))
 
 
+def pack_bits(codes: torch.Tensor) -> torch.Tensor:
+    """Pack 0/1 codes ``[N, bits]`` (any float/int dtype; a position is set iff non-zero) into ``[N, ceil(bits/64)]``
+    int64 words for the Hamming search (``knn_pack_bits``)."""
+    _require_cuda(codes)
+    x = _as2d(codes, "codes").float().contiguous()
+    n, bits = x.shape
+    words = (bits + 63) // 64
+    out = torch.empty((n, words), dtype=torch.int64, device=x.device)
+    if n == 0:
+        return out
+    with torch.cuda.device(x.device):
+        rc = L.load().knn_pack_bits(_ptr(x), n, bits, L.KNN_F32, _ptr(out), _stream(x))
+    L.check(rc, "knn_pack_bits")
+    return out
+
+
+def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: int, *, exclude_self: bool = False,
+                   query_offset: int = 0, packed: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Hamming ranking of binary codes: the fused form of ``(q[:, None, :] != g[None, :, :]).sum(2).float()`` +
+    ``argsort(dim=1)[:, :k]`` (test_ath.py:80-100) -> (distances [Q,k] fp32 ascending, indices [Q,k] int64), ties by
+    ascending gallery row.  Codes are 0/1 tensors ``[N, bits]`` (as ``(codes >= 0).float()``, test_ath.py:68), or
+    already packed words with ``packed=True``."""
+    _require_cuda(query_codes, gallery_codes)
+    qw = query_codes.contiguous() if packed else pack_bits(query_codes)
+    gw = gallery_codes.contiguous() if packed else (qw if gallery_codes is query_codes else pack_bits(gallery_codes))
+    if qw.dtype != torch.int64 or gw.dtype != torch.int64 or qw.shape[1] != gw.shape[1]:
+        raise ValueError("packed codes must be int64 words with the same number of words per row")
+    nq, words = qw.shape
+    ng = gw.shape[0]
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    if k > L.MAX_FUSED_K:
+        raise L.KnnError(f"Hamming search supports k <= {L.MAX_FUSED_K}")
+    dev = qw.device
+    out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return out_val, out_idx
+    lib = L.load()
+    with torch.cuda.device(dev):
+        nbytes = lib.knn_search_hamming_workspace(nq, ng, k)
+        ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+        rc = lib.knn_search_hamming(_ptr(qw), _ptr(gw), nq, ng, words, k, _SELF["exclude" if exclude_self else "keep"],
+                                    int(query_offset), 0, _ptr(out_val), _ptr(out_idx), _ptr(ws), ws.numel(), _stream(qw))
+    L.check(rc, "knn_search_hamming")
+    return out_val, out_idx
+
+
 def rank_rows(scores: torch.Tensor, largest_first: bool = True) -> torch.Tensor:
     """Stable full ranking of every row: best first, ties by ascending column (the deterministic form of
     ``torch.argsort(dists, dim=1, descending=True)``, test.py:1018).  -> int64 [Q, N]."""

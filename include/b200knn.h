@@ -108,6 +108,17 @@ KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
  * "stall counters").  Synchronises the device, copies the counters to out32 (host), optionally clears them. */
 KNN_API int knn_debug_stats(unsigned long long* out32_host, int reset);
 
+/* Hamming distance over binary codes + fused top-k: the replacement of
+ * `(q[:, None, :] != g[None, :, :]).sum(dim=2).float()` + `argsort(dim=1)`, test_ath.py:80-100, train_ath.py:162-175.
+ * knn_pack_bits: x [n, bits] fp32 (a position is set iff the value is non-zero) -> out [n, ceil(bits/64)] uint64.
+ * knn_search_hamming: q/g packed words [rows, words] (words in 1, 2, 3, 4, 8); out_val = distance as fp32 ascending,
+ * out_idx = gallery row (+index_base), ties by ascending gallery row; KNN_SELF_KEEP / KNN_SELF_EXCLUDE. */
+KNN_API int knn_pack_bits(const void* x, int64_t n, int bits, int in_dtype, void* out_words, void* stream);
+KNN_API int knn_search_hamming(const void* q_words, const void* g_words, int64_t nq, int64_t ng, int words, int k,
+                       int self_mode, int64_t self_offset, int64_t index_base,
+                       float* out_val, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_search_hamming_workspace(int64_t nq, int64_t ng, int k);
+
 /* Per-query statistics of the scores against the WHOLE gallery without materialising them: out [nq,4] double =
  * sum, sum of squares, min, max of score(q, g) over g (KNN_SELF_EXCLUDE leaves the query's own row out).  Replaces
  * the row-wise mean / std / min / max of a full similarity matrix in `normalize_similarity_matrix`,
