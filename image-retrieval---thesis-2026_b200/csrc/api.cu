@@ -163,8 +163,10 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
   if (len < kSeedUnitMin) len = kSeedUnitMin;
   if (g.L - 32 < kSeedUnitMin && len < 4096) len = 4096;  // small k: short lists compact anyway, keep units long
   (void)tile;
-  while (units > 1 && units * len > ng / 8) --units;       // the sample stays a small prefix of the gallery
-  if (units * len > ng / 8) return;
+  // the sample stays a small prefix of the gallery: at most 2 % of it (the minimum useful sample, 4096 rows, is
+  // not worth scanning twice in a gallery of 100 k rows)
+  while (units > 1 && units * len > ng / 50) --units;
+  if (units * len > ng / 50) return;
   g.seed_splits = (int)units;
   g.seed_len = len;
 }
