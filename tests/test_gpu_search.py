@@ -337,3 +337,48 @@ def test_bf16_kernel_variants_selected_by_environment(env, nq, d):
     res = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET.format(root=root, nq=nq, d=d)],
                          env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "VARIANT-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def _gen_rows(knn, n, d, seed, dtype=torch.bfloat16):
+    gen = torch.Generator(device="cuda")
+    out = torch.empty((n, d), dtype=dtype, device="cuda")
+    for s in range(0, n, 1 << 20):
+        e = min(n, s + (1 << 20))
+        gen.manual_seed(seed + s)
+        out[s:e] = knn.normalize(torch.randn((e - s, d), generator=gen, device="cuda"), out_dtype=dtype)
+    return out
+
+
+@pytest.mark.parametrize("nq,ng,d,k", [
+    (64, 10_000_000, 768, 100),      # BASELINE config 4 at full size (one GPU): TMEM-resident-query kernel
+    (8192, 2_000_000, 512, 100),     # BASELINE config 5's shape on a gallery slice: CTA-pair kernel, many splits
+])
+def test_full_size_properties(knn, nq, ng, d, k):
+    """Size-independent properties where the oracle cannot run: (1) rows sorted best-first with unique indices,
+    (2) the returned scores are the scores of the returned rows (re-scored through the exact fp32 engine),
+    (3) exactness on a superset: the exact top-k over {random subsample} U {returned rows} is the returned set,
+    (4) shard invariance: searching two halves and merging the candidates gives the identical result."""
+    g = _gen_rows(knn, ng, d, 1234)
+    q = _gen_rows(knn, nq, d, 99)
+    index = knn.FlatIndex(d, "cosine", "bf16").adopt(g)
+    v, i = index.search(q, k)
+    assert bool((v[:, :-1] >= v[:, 1:]).all()) and bool((i >= 0).all()) and bool((i < ng).all())
+    assert all(len(set(r)) == k for r in host(i[:: max(1, nq // 16)]).tolist())
+    rows = torch.randperm(nq, device="cuda")[:16]
+    sub = torch.randint(0, ng, (200_000,), device="cuda")
+    for r in rows.tolist():
+        cand = torch.unique(torch.cat([sub, i[r]]))                      # sorted ascending -> tie order preserved
+        gv = g[cand].float()
+        ev, ei = knn.search(q[r:r + 1].float(), gv, k, "ip", precision="fp32")
+        got = cand[ei[0]]
+        assert set(host(got).tolist()) == set(host(i[r]).tolist()), r
+        assert torch.allclose(ev[0], v[r], rtol=1e-4, atol=2e-5)         # (2): fp32 re-scoring of bf16 rows
+    half = ng // 2
+    parts_v, parts_i = [], []
+    for s, e in ((0, half), (half, ng)):
+        pv, pi = knn.FlatIndex(d, "cosine", "bf16", index_base=s).adopt(g[s:e]).search(q, k)
+        parts_v.append(pv)
+        parts_i.append(pi)
+    mv, mi = knn.merge_topk(torch.stack(parts_v), torch.stack(parts_i), "cosine")
+    assert torch.equal(mi, i) and torch.equal(mv, v)
