@@ -69,8 +69,8 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   g.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   if (g.qblocks < 1) g.qblocks = 1;
   const bool ts = use_ts(dtype, d, g.qblocks);
-  // the CTA-pair kernel and the TMEM-resident kernel run two selection threads (two lists) per row
-  g.groups = (dtype == KNN_BF16 && (ts || g.qblocks > 1)) ? 2 : 1;
+  // every tcgen05 kernel runs two selection threads (two candidate lists) per query row
+  g.groups = dtype == KNN_BF16 ? 2 : 1;
   // bf16: more than one 128-row block -> CTA pairs own 256 query rows (cta_group::2 kernels); a single block
   // (small-batch, HBM-bound regime) runs one CTA per unit: every SM streams its own gallery tiles
   if (dtype == KNN_BF16 && g.qblocks > 1 && (g.qblocks & 1)) g.qblocks += 1;
@@ -86,7 +86,10 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   // them, and over longer units their random drift turned 2/3 of the L2 hits into HBM re-reads (measured).
   // Upper end: ~4 waves' worth for many query blocks, ~2 waves for a single block (every extra split adds a
   // candidate list per query to the final merge), at least twice the lower end.
-  constexpr int64_t kMaxUnitTiles = 6144;
+  static const int64_t kMaxUnitTiles = [] {
+    const char* e = getenv("KNN_MAX_UNIT_TILES");   // experiment knob
+    return e ? (int64_t)atoll(e) : (int64_t)6144;
+  }();
   const int waves = env_waves > 0 ? env_waves : (g.qblocks <= 2 ? 2 : 4);
   int64_t lo = (slots + g.qblocks - 1) / g.qblocks;
   const int64_t lo_len = (ntiles + kMaxUnitTiles - 1) / kMaxUnitTiles;
@@ -120,6 +123,38 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [rows, d] bf16 row-major -> 2-D tensor map with a {64 elements, box_rows} box and 128-byte swizzle (the layout
+// the UMMA shared-memory descriptors of ptx.cuh expect).  Rows past the end read as zeros.
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    KNN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return KNN_E_CUDA;
+    }
+    enc = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);
+    return KNN_E_CUDA;
+  }
+  return KNN_OK;
+}
 
 unsigned long long* debug_stats_buffer() {
   static unsigned long long* buf = [] {

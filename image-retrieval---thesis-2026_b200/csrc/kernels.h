@@ -49,6 +49,9 @@ int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, i
 int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream);
 int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, uint64_t* out, cudaStream_t stream);
 
+// [rows, d] bf16 row-major -> tensor map with a {64, box_rows} box, 128-byte swizzle (api.cu)
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows);
+
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();
 

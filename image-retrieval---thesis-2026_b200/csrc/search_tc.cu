@@ -1,16 +1,14 @@
-// bf16 distance + fused top-k on the 5th-generation tensor cores (sm_100a).
+// bf16 distance + fused top-k on ONE CTA per unit with the query tile streamed through shared memory.
 //
+// Serves a single 128-row query block whose rows do not fit tensor memory next to an accumulator (d > 768); the
+// common small-batch case (d <= 768) runs search_ts.cu, several query blocks run the CTA-pair kernel search_tc2.cu.
 //   S[q, g] = sum_d Q[q,d] * G[g,d]      Q, G bf16 row-major ("K-major" for both UMMA operands)
-//
-// One CTA owns 128 query rows (UMMA M = 128 = the 128 TMEM lanes) and streams its gallery split in
-// tiles of 256 rows (UMMA N = 256).  Warp roles:
-//   warp 0      TMA producer  : cp.async.bulk.tensor (128B swizzle) of Q and G k-blocks into a 4-stage ring
-//   warp 1      MMA issuer    : one thread issues tcgen05.mma.kind::f16, accumulators in TMEM
-//                               (2 stages x 256 fp32 columns = all 512 TMEM columns)
-//   warps 2..5  epilogue      : tcgen05.ld 32 columns at a time, thread i owns TMEM lane i = query row i and
-//                               runs the threshold filter / candidate lists of select.cuh
-// The selection of tile t overlaps the MMAs of tile t+1 through the two TMEM stages, so the Q x N score
-// matrix never exists outside TMEM.
+// UMMA M = 128 (the 128 TMEM lanes = query rows), N = 256 gallery rows per tile, K = 16; a 4-slot ring of
+// {Q 16 KB, G 32 KB} k-blocks filled by TMA (128-byte swizzle); fp32 accumulators in TMEM (2 stages x 256 columns).
+// Warp roles and the selection are the same as in the other tcgen05 kernels: warp 0 = TMA producer, warp 1 = MMA
+// issuer (lean single-lane issue loops), warps 2..9 = selection (two threads per query row taking alternate
+// 32-column chunks, separate candidate lists; hits are queued while the accumulator stage is held and appended
+// after it has been released).
 #include <stdlib.h>
 #include "select.cuh"
 #include "ptx.cuh"
@@ -27,8 +25,9 @@ constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr uint32_t A_STAGE_BYTES = TM * BKE * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = TN * BKE * 2;   // 32 KB
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -42,19 +41,17 @@ struct alignas(8) TcBarriers {
   uint32_t pad;
 };
 
-constexpr size_t kSmemBytes = 1024 /*alignment slack*/ + (size_t)kStages * STAGE_BYTES + kDumpBytes +
-                              sizeof(float) * kAccStages * TN + sizeof(TcBarriers);
+constexpr size_t kSmemBytes = (size_t)kStages * STAGE_BYTES + sizeof(float) * kAccStages * TN + sizeof(TcBarriers);
 
-template <int E, bool kL2>
+// kDiag = false is the production build: the stall counters compile away.
+template <int E, bool kL2, bool kDiag>
 __global__ void __launch_bounds__(kThreads, 1)
 search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
-                   SearchParams p, unsigned long long* stats, int debug, int prefetch) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                       // [kStages][128][64] bf16, swizzled
-  uint8_t* smem_b = smem + (size_t)kStages * A_STAGE_BYTES;     // [kStages][256][64] bf16, swizzled
-  float* dump = reinterpret_cast<float*>(smem + (size_t)kStages * STAGE_BYTES);  // slow-path staging, 16 KB
-  float* gs = dump + kDumpBytes / 4;                                             // [kAccStages][TN]
+                   SearchParams p, unsigned long long* stats) {
+  const bool stats_on = kDiag && stats != nullptr;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;                                                        // [kStages]{B 32 KB, A 16 KB}
+  float* gs = reinterpret_cast<float*>(ring + (size_t)kStages * STAGE_BYTES);  // [kAccStages][TN] (L2 metric)
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(gs + kAccStages * TN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,6 +63,10 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int nkb = (p.d + BKE - 1) / BKE;
 
   if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("b200knn: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_g);
     for (int s = 0; s < kStages; ++s) {
@@ -74,7 +75,7 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&bars->tmem_full[s], 1);
-      ptx::mbar_init(&bars->tmem_empty[s], kEpiThreads / 32);
+      ptx::mbar_init(&bars->tmem_empty[s], kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -88,88 +89,83 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (one thread, lean loop)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
-      int pf_t = prefetch / nkb, pf_kb = prefetch % nkb;
-      if (prefetch > 0) {
-        for (int i = 0; i < prefetch && i < ntiles * nkb; ++i)
-          ptx::tma_prefetch_2d(&tmap_g, (i % nkb) * BKE, (int32_t)(c_begin + (int64_t)(i / nkb) * TN));
-      }
-      for (int t = 0; t < ntiles; ++t) {
-        const int32_t col0 = (int32_t)(c_begin + (int64_t)t * TN);
+      const uint32_t ring_u32 = ptx::smem_u32(ring);
+      const uint32_t full0 = ptx::smem_u32(&bars->full[0]);
+      int32_t col0 = (int32_t)c_begin;
+      for (int t = 0; t < ntiles; ++t, col0 += TN) {
         for (int kb = 0; kb < nkb; ++kb) {
-          if (prefetch > 0) {
-            if (pf_t < ntiles) ptx::tma_prefetch_2d(&tmap_g, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN));
-            if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
-          }
-          const long long c0 = stats ? clock64() : 0;
+          const long long c0 = stats_on ? clock64() : 0;
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
-          if (stats) w_empty += clock64() - c0;
-          ptx::mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
-          ptx::tma_load_2d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_q, &bars->full[stage], kb * BKE,
-                           (int32_t)row0, ptx::kEvictLast);
-          ptx::tma_load_2d(smem_b + (size_t)stage * B_STAGE_BYTES, &tmap_g, &bars->full[stage], kb * BKE, col0,
-                           ptx::kEvictNormal);
+          if (stats_on) w_empty += clock64() - c0;
+          const uint32_t dst = ring_u32 + (uint32_t)stage * STAGE_BYTES;
+          const uint32_t full_bar = full0 + (uint32_t)stage * 8u;
+          ptx::mbar_arrive_expect_tx_u32(full_bar, STAGE_BYTES);
+          ptx::tma_load_2d_u32(dst, &tmap_g, full_bar, kb * BKE, col0, ptx::kEvictFirst);
+          ptx::tma_load_2d_u32(dst + B_STAGE_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      if (stats) atomicAdd(stats + 7, (unsigned long long)w_empty);
+      if (stats_on) atomicAdd(stats + 7, (unsigned long long)w_empty);
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(TM, TN);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_tmem = 0, w_full = 0;
-      const long long m_begin = stats ? clock64() : 0;
-      for (int t = 0; t < ntiles; ++t) {
-        const int as = t & 1;
-        const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
-        long long c0 = stats ? clock64() : 0;
-        ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
-        if (stats) w_tmem += clock64() - c0;
-        ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * TN);
-        for (int kb = 0; kb < nkb; ++kb) {
-          c0 = stats ? clock64() : 0;
-          ptx::mbar_wait(&bars->full[stage], phase);
-          if (stats) w_full += clock64() - c0;
-          ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * B_STAGE_BYTES);
-          if (!(debug & 1)) {
+    // ===================================================================== MMA issuer (whole warp walks, one lane issues)
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(TM, TN);
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_tmem = 0, w_full = 0;
+    const long long m_begin = stats_on ? clock64() : 0;
+    const uint32_t b_lo0 = ptx::sw128_desc_lo(ptx::smem_u32(ring));
+    uint32_t b_lo = b_lo0;
+    const bool issuer = ptx::elect_one();
+    for (int t = 0; t < ntiles; ++t) {
+      const int as = t & 1;
+      const uint32_t aphase = (uint32_t)(t >> 1) & 1u;
+      long long c0 = stats_on ? clock64() : 0;
+      ptx::mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+      if (stats_on) w_tmem += clock64() - c0;
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * TN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        c0 = stats_on ? clock64() : 0;
+        ptx::mbar_wait(&bars->full[stage], phase);
+        if (stats_on) w_full += clock64() - c0;
+        if (issuer) {
+          const uint32_t a_lo = b_lo + (B_STAGE_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < BKE / UMMA_K; ++k) {
-              const uint64_t da = ptx::make_sw128_kmajor_desc(a_addr + k * UMMA_K * 2);
-              const uint64_t db = ptx::make_sw128_kmajor_desc(b_addr + k * UMMA_K * 2);
-              ptx::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+          for (int k = 0; k < BKE / UMMA_K; ++k) {
+            const uint64_t da = ptx::sw128_desc(a_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+            const uint64_t db = ptx::sw128_desc(b_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+            ptx::mma_bf16_ss(tmem_d, da, db, idesc, (k != 0 || kb != 0) ? 1u : 0u);
           }
           ptx::tc_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::tc_commit(&bars->tmem_full[as]);   // accumulator tile complete
+        b_lo += STAGE_BYTES >> 4;
+        if (++stage == kStages) { stage = 0; phase ^= 1; b_lo = b_lo0; }
       }
-      if (stats) {
-        atomicAdd(stats + 0, (unsigned long long)(clock64() - m_begin));
-        atomicAdd(stats + 1, (unsigned long long)w_tmem);
-        atomicAdd(stats + 2, (unsigned long long)w_full);
-        atomicAdd(stats + 8, 1ull);
-      }
+      if (issuer) ptx::tc_commit(&bars->tmem_full[as]);   // accumulator tile complete
+      __syncwarp();
+    }
+    if (stats_on && issuer) {
+      atomicAdd(stats + 0, (unsigned long long)(clock64() - m_begin));
+      atomicAdd(stats + 1, (unsigned long long)w_tmem);
+      atomicAdd(stats + 2, (unsigned long long)w_full);
+      atomicAdd(stats + 8, 1ull);
     }
   } else {
-    // ===================================================================== epilogue / selection
+    // ===================================================================== selection (8 warps)
     constexpr int L = 32 * E;
+    const int grp = (warp - 2) >> 2;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int rloc = quarter * 32 + lane;         // query row inside the unit
     const bool row_valid = row0 + rloc < p.nq;
-    const int64_t unit = (int64_t)sp * p.qblocks + qb;
+    const int64_t vunit = ((int64_t)sp * 2 + grp) * p.qblocks + qb;
     RowState st;
-    rowstate_init(st, p.lists + ((unit * TM + rloc) * (int64_t)L));
+    rowstate_init(st, p.lists + ((vunit * TM + rloc) * (int64_t)L));
     uint32_t self_row = 0xFFFFFFFFu;
     float qn = 0.f;
     uint32_t* tau_row = nullptr;
@@ -179,10 +175,10 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       if (kL2) qn = __ldg(p.qsq + row0 + rloc);
       tau_row = p.tau_global + row0 + rloc;
     }
-    const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;  // 0..255 among the selection threads
     long long e_wait = 0, e_slow = 0;
     unsigned long long n_slow = 0;
-    const long long e_begin = stats ? clock64() : 0;
+    const long long e_begin = stats_on ? clock64() : 0;
 
     for (int t = 0; t < ntiles; ++t) {
       const int as = t & 1;
@@ -190,52 +186,37 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int64_t col0 = c_begin + (int64_t)t * TN;
       float* gst = gs + as * TN;
       if (kL2) {
-#pragma unroll
-        for (int h = 0; h < TN / kEpiThreads; ++h) {
-          int64_t c = col0 + et + h * kEpiThreads;
-          if (c >= p.ng) c = p.ng - 1;
-          gst[et + h * kEpiThreads] = __ldg(p.gsq + c);
-        }
+        int64_t c = col0 + et;
+        if (c >= p.ng) c = p.ng - 1;
+        gst[et] = __ldg(p.gsq + c);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      refresh_tau<kL2>(st, tau_row);
-      const long long cw = stats ? clock64() : 0;
+      const uint32_t tau_peek = peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
+      const long long cw = stats_on ? clock64() : 0;
       ptx::mbar_wait(&bars->tmem_full[as], aphase);
-      if (stats) e_wait += clock64() - cw;
+      if (stats_on) e_wait += clock64() - cw;
       ptx::tc_fence_after();
+      apply_tau<kL2>(st, tau_peek);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
-#pragma unroll 1
-      for (int cb = 0; cb < TN; cb += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
-        ptx::tmem_ld_fence(v);
-        const int64_t cg = col0 + cb;
-        const int64_t rem = c_end - cg;
-        const uint32_t nvalid = rem <= 0 ? 0u : (rem >= 32 ? 32u : (uint32_t)rem);
-        const int cnt0 = st.cnt;
-        const long long c0 = stats ? clock64() : 0;
-        select_chunk_regs<kL2>(st, v, dump + et * 4, qn, gst + cb, (uint32_t)cg, nvalid, self_row, p.self_mode,
-                               row_valid && !(debug & 2));
-        warp_compact_if_needed<E, 32, kL2>(st, p.k, lane, tau_row);
-        if (stats && __any_sync(kFullMask, st.cnt != cnt0)) {
-          e_slow += clock64() - c0;
-          ++n_slow;
-        }
-      }
+      PendingHits pend;
+      pend.n = 0;
+      select_tile_tmem<E, kL2>(st, pend, taddr, grp, 2, TN / 32, col0, c_end, gst, qn, self_row, p.self_mode, p.k, lane,
+                               tau_row, row_valid, stats_on, e_slow, n_slow);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->tmem_empty[as]);
+      flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
-    if (stats && lane == 0) {
+    if (stats_on && lane == 0) {
       atomicAdd(stats + 3, (unsigned long long)(clock64() - e_begin));
       atomicAdd(stats + 4, (unsigned long long)e_wait);
       atomicAdd(stats + 5, (unsigned long long)e_slow);
       atomicAdd(stats + 6, n_slow);
       atomicAdd(stats + 9, 1ull);
-      atomicAdd(stats + 10, (unsigned long long)ntiles * (TN / 32));
+      atomicAdd(stats + 10, (unsigned long long)ntiles * (TN / 64));
     }
     // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
-    p.counts[unit * TM + rloc] = row_valid ? st.cnt : 0;
+    p.counts[vunit * TM + rloc] = row_valid ? st.cnt : 0;
   }
 
   ptx::tc_fence_before();
@@ -246,66 +227,27 @@ search_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode_fn(EncodeTiledFn* out) {
-  static EncodeTiledFn cached = nullptr;
-  if (!cached) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    KNN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-      set_error("cuTensorMapEncodeTiled not available from the driver");
-      return KNN_E_CUDA;
-    }
-    cached = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  *out = cached;
-  return KNN_OK;
-}
-
-// [rows, d] bf16 row-major -> 2-D tensor map with a {64, box_rows} box and 128-byte swizzle.
-int make_tmap_bf16(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
-  EncodeTiledFn enc;
-  int rc = get_encode_fn(&enc);
-  if (rc != KNN_OK) return rc;
-  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);
-    return KNN_E_CUDA;
-  }
-  return KNN_OK;
-}
-
-int env_int(const char* name) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : 0;
-}
-
 template <int E>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
   CUtensorMap tq, tg;
-  int rc = make_tmap_bf16(&tq, p.q, p.nq, p.d, TM);
+  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, p.d, TM);
   if (rc != KNN_OK) return rc;
-  rc = make_tmap_bf16(&tg, p.g, p.ng, p.d, TN);
+  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, p.d, TN);
   if (rc != KNN_OK) return rc;
+  unsigned long long* stats = debug_stats_buffer();
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);
   if (p.metric == KNN_L2) {
-    auto kern = search_bf16_kernel<E, true>;
+    auto kern = search_bf16_kernel<E, true, false>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, debug_stats_buffer(), env_int("KNN_TC_DEBUG"), env_int("KNN_TC_PREFETCH"));
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, stats);
+  } else if (stats != nullptr && E == 8) {  // diagnostics build exists for the k <= 128, similarity instantiation only
+    auto kern = search_bf16_kernel<8, false, true>;
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, stats);
   } else {
-    auto kern = search_bf16_kernel<E, false>;
+    auto kern = search_bf16_kernel<E, false, false>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, debug_stats_buffer(), env_int("KNN_TC_DEBUG"), env_int("KNN_TC_PREFETCH"));
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, stats);
   }
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
@@ -324,7 +266,11 @@ int launch_search_bf16(const SearchParams& p, cudaStream_t stream) {
     set_error("bf16 search needs 16-byte aligned q and g");
     return KNN_E_INVALID;
   }
-  if (p.qblocks > 1) return launch_search_bf16_pair(p, stream);  // one query block: the one-CTA kernel below
+  if (p.groups != 2) {
+    set_error("internal: the tcgen05 kernels write 2 candidate lists per row and split");
+    return KNN_E_INVALID;
+  }
+  if (p.qblocks > 1) return launch_search_bf16_pair(p, stream);  // one query block: the one-CTA kernel of this file
   switch (p.kp) {
     case 32: return launch_e<2>(p, stream);
     case 64: return launch_e<4>(p, stream);

@@ -289,50 +289,12 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode_fn2(EncodeTiledFn* out) {
-  static EncodeTiledFn cached = nullptr;
-  if (!cached) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    KNN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-      set_error("cuTensorMapEncodeTiled not available from the driver");
-      return KNN_E_CUDA;
-    }
-    cached = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  *out = cached;
-  return KNN_OK;
-}
-
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
-  EncodeTiledFn enc;
-  int rc = get_encode_fn2(&enc);
-  if (rc != KNN_OK) return rc;
-  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);
-    return KNN_E_CUDA;
-  }
-  return KNN_OK;
-}
-
 template <int E>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
   CUtensorMap tq, tg;
-  int rc = make_tmap(&tq, p.q, p.nq, p.d, TM);
+  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, p.d, TM);
   if (rc != KNN_OK) return rc;
-  rc = make_tmap(&tg, p.g, p.ng, p.d, TNH);
+  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, p.d, TNH);
   if (rc != KNN_OK) return rc;
 
   PairCfg cfg;

@@ -321,37 +321,6 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// [rows, d] bf16 row-major -> 2-D tensor map with a {64, box_rows} box and 128-byte swizzle.
-int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    KNN_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
-      set_error("cuTensorMapEncodeTiled not available from the driver");
-      return KNN_E_CUDA;
-    }
-    enc = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);
-    return KNN_E_CUDA;
-  }
-  return KNN_OK;
-}
-
 int env_int_ts(const char* name) {
   const char* e = getenv(name);
   return e ? atoi(e) : 0;

@@ -290,7 +290,9 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
     const int rc = __shfl_sync(kFullMask, st.cnt, r);
     __syncwarp();
     CompactOut co = compact_row_select<E>(rl, rc, k, lane);
-    if (co.cnt > (L + k) / 2) co = compact_row<E>(rl, rc, k, k, lane);  // too little progress: sort, keep exactly k
+    // too little progress: sort, keep exactly k.  The selection may already have rewritten the list (survivors moved
+    // to the front, stale copies behind them), so the sort must read co.cnt entries, not the old count.
+    if (co.cnt > (L + k) / 2) co = compact_row<E>(rl, co.cnt, k, k, lane);
     const int nc = co.cnt;
     const uint64_t nk = co.taukey;
     if (lane == r) {

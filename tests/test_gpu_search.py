@@ -159,6 +159,29 @@ def test_adversarial_orders_and_mass_ties(knn):
     _check_exact(knn, qv, blocks, 128, "l2")
 
 
+def test_list_compaction_falls_back_to_the_sort_without_duplicates(knn):
+    """Regression (found by the shard-invariance property at 8192 x 2M): when the selection-based list compaction
+    makes too little progress it has already rewritten the list, and the sorting fallback must read the NEW count.
+    The first unit's list is filled in gallery order (fp32 kernel, d = 1), so the 32 keys the compaction samples
+    (position (l % 8) * 32 + l for lane l, list capacity 256 for k = 100) can be made the 32 worst of the first
+    256 rows: the pivot keeps 225 of 256 entries -> fallback.  Rows 225..255 hold the best scores, so stale copies
+    of them would surface as duplicate indices in the top-k.  8192 queries x 10 000 rows: 5 gallery splits of 2048
+    rows (the first starts at row 0) and no threshold-seeding pre-pass, so unit 0 really accepts its first 256 rows."""
+    nq, ng, k = 8192, 10_000, 100
+    rs = np.random.RandomState(11)
+    score = rs.permutation(ng).astype(np.float32)            # distinct integers: exact in fp32
+    head = np.sort(score[:256].copy())
+    sampled = sorted({(l % 8) * 32 + l for l in range(32)})
+    rest = [p for p in range(256) if p not in sampled]
+    score[sampled] = head[:32]                               # the sample = the 32 lowest of the first list
+    score[rest] = head[32:]                                  # ascending: positions 225..255 are the best of the list
+    score[:256] += 2.0 * ng                                  # ... and all of them belong to the final top-k region
+    g = (score / 2.0 ** 20).reshape(ng, 1).astype(np.float32)
+    qv = (1.0 + (np.arange(nq) % 7)).reshape(nq, 1).astype(np.float32) / 4.0
+    v, i = _check_exact(knn, qv, g, k, "ip")
+    assert all(len(set(r)) == k for r in i[::257].tolist())
+
+
 def test_self_modes_with_offset(knn):
     rs = np.random.RandomState(5)
     g = oracle.normalize(rs.standard_normal((700, 40)).astype(np.float32))
