@@ -289,10 +289,19 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
     uint64_t* rl = (uint64_t*)__shfl_sync(kFullMask, (unsigned long long)st.list, r);
     const int rc = __shfl_sync(kFullMask, st.cnt, r);
     __syncwarp();
-    CompactOut co = compact_row_select<E>(rl, rc, k, lane);
-    // too little progress: sort, keep exactly k.  The selection may already have rewritten the list (survivors moved
-    // to the front, stale copies behind them), so the sort must read co.cnt entries, not the old count.
-    if (co.cnt > (L + k) / 2) co = compact_row<E>(rl, co.cnt, k, k, lane);
+    // The list must end up with room for a whole chunk (cnt <= L - CH is the invariant every append relies on) and
+    // should end up well below capacity.  The selection leaves k .. k + ~L/32 keys; when that cannot meet the target
+    // (k close to L - CH: the shortest lists, L = 64), or did not, sort and keep exactly k.  The selection may have
+    // rewritten the list (survivors in front, stale copies behind): the sort reads co.cnt entries, not the old count.
+    constexpr int kRoom = L - CH;
+    const int keep_max = (L + k) / 2 < kRoom ? (L + k) / 2 : kRoom;
+    CompactOut co;
+    if (k + L / 32 > keep_max) {
+      co = compact_row<E>(rl, rc, k, k, lane);
+    } else {
+      co = compact_row_select<E>(rl, rc, k, lane);
+      if (co.cnt > keep_max) co = compact_row<E>(rl, co.cnt, k, k, lane);
+    }
     const int nc = co.cnt;
     const uint64_t nk = co.taukey;
     if (lane == r) {

@@ -13,6 +13,7 @@ Everything runs in the CUDA library behind include/b200knn.h; torch only owns th
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -135,6 +136,7 @@ class FlatIndex:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.rows: Optional[torch.Tensor] = None
         self.sqnorm: Optional[torch.Tensor] = None
+        self._filter: Optional[ExactFilterRows] = None   # bf16 split of fp32 rows (tensor-core exact engine), lazy
 
     @property
     def ntotal(self) -> int:
@@ -150,6 +152,7 @@ class FlatIndex:
         self.rows = rows if self.rows is None else torch.cat([self.rows, rows], 0)
         if sq is not None:
             self.sqnorm = sq if self.sqnorm is None else torch.cat([self.sqnorm, sq], 0)
+        self._filter = None
         return self
 
     def adopt(self, rows: torch.Tensor, sqnorm: Optional[torch.Tensor] = None) -> "FlatIndex":
@@ -160,6 +163,7 @@ class FlatIndex:
             raise ValueError("adopt() needs contiguous rows already in the search dtype")
         self.rows = rows
         self.sqnorm = sqnorm if sqnorm is not None else (row_sqnorm(rows) if self.metric == "l2" else None)
+        self._filter = None
         return self
 
     def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
@@ -174,8 +178,136 @@ class FlatIndex:
         q, qsq = _prepare(queries.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
                           self.metric == "l2")
         mode = self_mode or ("exclude" if exclude_self else "keep")
+        if self.precision == "fp32" and exact_engine(q.shape[0], self.ntotal, self.dim, int(k)) == "tensor":
+            if self._filter is None:
+                self._filter = ExactFilterRows.build(self.rows, self.sqnorm)
+            return _search_exact_tensor(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
+                                        self.index_base, self._filter)
         return _search_prepared(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
                                 self.index_base)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Exact fp32 search on the tensor cores (csrc/exact_tc.cu): bf16x3 split filter -> exact fp32 re-scoring of kc > k
+# candidates per query -> per-query proof that nothing outside the candidate set can be in the answer -> FFMA
+# re-run of the (rare) queries the proof does not cover.  The result is bit-identical to the FFMA engine's.
+# ---------------------------------------------------------------------------------------------------------------
+_EXACT_MIN_FLOP = 4.0e10   # below ~1 ms of FFMA work the detour through the tensor cores does not pay
+
+
+def _filter_k(k: int) -> int:
+    """Candidates per query the filter returns: k plus a slack of max(8, k/8), rounded up to the list geometry."""
+    want = k + max(8, k // 8)
+    kc = 32
+    while kc < want:
+        kc <<= 1
+    return kc
+
+
+def exact_engine(nq: int, ng: int, d: int, k: int) -> str:
+    """Which kernel family serves precision="fp32": "ffma" (search_f32.cu) or "tensor" (filter + re-score).
+    KNN_EXACT_ENGINE=ffma|tensor forces one (tests, measurements)."""
+    forced = os.environ.get("KNN_EXACT_ENGINE", "")
+    feasible = k <= L.MAX_FUSED_K and _filter_k(k) <= L.MAX_FUSED_K and nq > 0 and ng > 0
+    if forced == "ffma" or not feasible:
+        return "ffma"
+    if forced == "tensor":
+        return "tensor"
+    return "tensor" if 2.0 * nq * ng * d >= _EXACT_MIN_FLOP else "ffma"
+
+
+def split_bf16x3(x: torch.Tensor, role: str) -> torch.Tensor:
+    """fp32 rows [n, d] -> bf16 [n, 3 * dpad]: ``[hi | lo | hi]`` for role "queries", ``[hi | hi | lo]`` for
+    "gallery" (hi = bf16(x), lo = bf16(x - hi), dpad = d rounded up to 8)."""
+    _require_cuda(x)
+    x = _as2d(x, "x")
+    if x.dtype != torch.float32:
+        raise ValueError("split_bf16x3 takes fp32 rows")
+    n, d = x.shape
+    out = torch.empty((n, 3 * ((d + 7) // 8 * 8)), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.load().knn_split_bf16x3(_ptr(x), n, d, {"queries": 0, "gallery": 1}[role], _ptr(out), _stream(x))
+    L.check(rc, "knn_split_bf16x3")
+    return out
+
+
+class ExactFilterRows:
+    """What the tensor-core exact engine keeps per gallery besides the fp32 rows: the bf16 split rows, the squared
+    norms and their maximum (a device scalar; enters the error bound of the filter)."""
+
+    def __init__(self, split: torch.Tensor, sqnorm: torch.Tensor, max_sqnorm: torch.Tensor):
+        self.split, self.sqnorm, self.max_sqnorm = split, sqnorm, max_sqnorm
+
+    @staticmethod
+    def build(rows: torch.Tensor, sqnorm: Optional[torch.Tensor]) -> "ExactFilterRows":
+        sq = sqnorm if sqnorm is not None else row_sqnorm(rows)
+        return ExactFilterRows(split_bf16x3(rows, "gallery"), sq, sq.max() if sq.numel() else sq.new_zeros(()))
+
+
+def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric: str) -> torch.Tensor:
+    """eps[q] >= |filter value - exact-mode value| for every gallery row (fp32 [Q], rounded up).
+
+    dot product: split (3.02 * 2^-18) + tensor-core accumulation (2^-21 of the magnitude sum per K=16 step --
+    assumption, checked by tests/test_gpu_exact_tensor.py against observed errors) + the exact fp32 chain's own
+    rounding (d * 2^-24), all times |q| * max|g| (Cauchy-Schwarz).  L2 filter value -(|q|^2+|g|^2-2q.g): twice
+    that plus the two fp32 roundings of the formula."""
+    dpad = (d + 7) // 8 * 8
+    steps = 3 * dpad // 16 + 1
+    u = 3.02 * 2.0 ** -18 + steps * 2.0 ** -21 * 1.012 + d * 2.0 ** -24 * 1.001
+    qn2 = qsq.double()
+    gn2 = max_gsq.double()
+    eps = u * torch.sqrt(qn2 * gn2) * (1.0 + 1e-6) + 1e-30
+    if metric == "l2":
+        eps = 2.0 * eps + 2.0 ** -21 * 1.01 * (qn2 + gn2)
+    return (eps * (1.0 + 2.0 ** -22)).float()
+
+
+def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base,
+                         filt: Optional[ExactFilterRows] = None):
+    """precision="fp32" through the tensor cores; same contract and same bits as _search_prepared on fp32 rows."""
+    nq, d = q.shape
+    ng = g.shape[0]
+    dev = q.device
+    kc = _filter_k(k)
+    if filt is None:
+        filt = ExactFilterRows.build(g, gsq)
+    q_sq = qsq if qsq is not None else row_sqnorm(q)
+    eps = filter_error_bound(q_sq, filt.max_sqnorm, d, metric)
+    cand_val, cand_idx = _search_prepared(split_bf16x3(q, "queries"), qsq, filt.split, gsq if metric == "l2" else None,
+                                          kc, metric, self_mode, query_offset, index_base)
+    out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    flags = torch.empty((nq,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().knn_rescore_exact(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _METRICS[metric],
+                                        _SELF[self_mode], query_offset, index_base, _ptr(cand_val), _ptr(cand_idx),
+                                        kc, k, _ptr(eps), _ptr(out_val), _ptr(out_idx), _ptr(flags), _stream(q))
+    L.check(rc, "knn_rescore_exact")
+    # queries whose candidate set could not be proven complete (ties / near-duplicates wider than the slack):
+    # re-run their 128-row blocks through the FFMA engine (contiguous runs keep the self-row arithmetic)
+    bad = torch.nonzero(flags).flatten()
+    if bad.numel():
+        blocks = torch.unique(bad // 128).tolist()
+        if 2 * len(blocks) >= (nq + 127) // 128:
+            runs = [(0, nq)]
+        else:
+            runs, s0, prev = [], blocks[0], blocks[0]
+            for b in blocks[1:]:
+                if b != prev + 1:
+                    runs.append((s0 * 128, min(nq, (prev + 1) * 128)))
+                    s0 = b
+                prev = b
+            runs.append((s0 * 128, min(nq, (prev + 1) * 128)))
+        for s, e in runs:
+            v, i = _search_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, k, metric, self_mode,
+                                    query_offset + s, index_base)
+            out_val[s:e] = v
+            out_idx[s:e] = i
+    _search_exact_tensor.last_unverified = int(bad.numel())
+    return out_val, out_idx
+
+
+_search_exact_tensor.last_unverified = 0
 
 
 def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base):
@@ -272,7 +404,10 @@ def search(
         else:
             g, gsq = _prepare(gallery, normalize, precision, eps, eps_mode, want_sq)
         mode = self_mode or ("exclude" if exclude_self else "keep")
-        vals, idx = _search_prepared(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
+        if precision == "fp32" and exact_engine(q.shape[0], g.shape[0], q.shape[1], int(k)) == "tensor":
+            vals, idx = _search_exact_tensor(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
+        else:
+            vals, idx = _search_prepared(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
     if negated and metric == "l2":
         vals = -vals
     return vals, idx

@@ -92,6 +92,25 @@ KNN_API int knn_search(const void* q, const void* g, const float* q_sqnorm, cons
                void* workspace, size_t workspace_bytes, void* stream);
 KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k);
 
+/* Exact fp32 search on the tensor cores (the KNN_F32 definition of knn_search, reached through a bounded-error
+ * filter; csrc/exact_tc.cu).  Same reference calls as knn_search (test.py:44,1006,1080; train.py:405-409).
+ * knn_split_bf16x3: error-free split of fp32 rows x [n,d] into bf16 parts hi = bf16(x), lo = bf16(x - hi), written
+ *   as ONE row of 3*dpad bf16 (dpad = d rounded up to 8, zero padded): role 0 (queries) [hi|lo|hi], role 1 (gallery)
+ *   [hi|hi|lo], so that knn_search(KNN_BF16) over the split rows computes qhi.ghi + qlo.ghi + qhi.glo, which differs
+ *   from q.g by at most 3.02 * 2^-18 * |q||g| plus the accumulation error of the tensor cores.
+ * knn_rescore_exact: cand_val / cand_idx [nq,kc] = the filter's top-kc (kc > k, best first, global rows, -1 = empty).
+ *   Every candidate is re-scored with the exact fp32 chain of the KNN_F32 path, the best k are written to
+ *   out_val / out_idx exactly as knn_search(KNN_F32) would, and unverified[q] = 0 iff the result is PROVEN to be the
+ *   exact top-k: either the filter returned fewer than kc rows (the set is the whole gallery), or the k-th best exact
+ *   score beats (worst approximate score in the set) + eps[q], where eps[q] >= |approximate - exact| of the filter
+ *   value (the dot product; -(|q|^2 + |g|^2 - 2 q.g) for KNN_L2) for every gallery row.  Queries flagged 1 must be
+ *   re-run through knn_search(KNN_F32). */
+KNN_API int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* out, void* stream);
+KNN_API int knn_rescore_exact(const float* q, const float* g, const float* q_sqnorm, const float* g_sqnorm,
+                      int64_t nq, int64_t ng, int d, int metric, int self_mode, int64_t self_offset,
+                      int64_t index_base, const float* cand_val, const int64_t* cand_idx, int kc, int k,
+                      const float* eps, float* out_val, int64_t* out_idx, int32_t* unverified, void* stream);
+
 /* Opt-in, per calling thread: knn_search records CUDA events on its stream around (s) the threshold-seeding
  * pre-pass + seeding merge, (a) the main distance+select kernel and (b) the unit-merge kernel.  Recording does not
  * synchronise, so a

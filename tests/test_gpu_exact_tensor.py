@@ -1,0 +1,170 @@
+"""GPU parity tests of the tensor-core exact engine (csrc/exact_tc.cu): precision="fp32" served by the bf16x3 split
+filter + exact fp32 re-scoring + completeness proof + FFMA re-run.  Bar: bit-identical to the CPU oracle (and hence
+to the FFMA engine) -- indices AND distances -- on every input, including ties and mass duplicates."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def knn():
+    import b200knn
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    b200knn.load_library()
+    return b200knn
+
+
+@pytest.fixture()
+def tensor_engine(monkeypatch):
+    monkeypatch.setenv("KNN_EXACT_ENGINE", "tensor")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def _check(knn, q, g, k, metric, self_mode="keep", offset=0):
+    S = importlib.import_module("b200knn.search")
+
+    assert S.exact_engine(q.shape[0], g.shape[0], q.shape[1], k) == "tensor"
+    v, i = knn.search(dev(q), dev(g), k, metric, self_mode=self_mode, query_offset=offset, precision="fp32")
+    ov, oi = oracle.search(q, g, k, metric, self_mode, offset)
+    assert np.array_equal(host(i), oi), f"indices differ at {np.argwhere(host(i) != oi)[:5]}"
+    assert np.array_equal(host(v), ov)
+    return S._search_exact_tensor.last_unverified
+
+
+@pytest.mark.parametrize("d", [1, 5, 36, 100, 1024])
+@pytest.mark.parametrize("role", ["queries", "gallery"])
+def test_split_is_error_free_and_laid_out_as_documented(knn, d, role):
+    split_bf16x3 = importlib.import_module("b200knn.search").split_bf16x3
+
+    rs = np.random.RandomState(d)
+    x = (rs.standard_normal((77, d)) * np.exp(rs.uniform(-6, 6, (77, 1)))).astype(np.float32)
+    x[3] = 0.0
+    y = host(split_bf16x3(dev(x), role).float())
+    dpad = (d + 7) // 8 * 8
+    hi = oracle.bf16_round(x)
+    lo = oracle.bf16_round(x - hi)
+    assert np.all(np.abs(x - hi - lo) <= 2.0 ** -16 * np.abs(x))      # two bf16 parts carry >= 16 significand bits
+    parts = (hi, lo, hi) if role == "queries" else (hi, hi, lo)
+    for p, want in enumerate(parts):
+        assert np.array_equal(y[:, p * dpad:p * dpad + d], want)
+        assert not y[:, p * dpad + d:(p + 1) * dpad].any()
+
+
+@pytest.mark.parametrize("nq,ng,d,k,metric", [
+    (300, 5000, 64, 10, "cosine"), (300, 5000, 64, 50, "l2"), (129, 3000, 100, 100, "ip"), (64, 4000, 36, 128, "l2"),
+    (700, 20000, 1024, 50, "cosine"), (40, 900, 256, 200, "cosine"), (5, 40, 8, 10, "l2"), (3, 7, 16, 10, "ip"),
+    (1, 2000, 768, 1, "cosine"),
+])
+def test_tensor_engine_is_bit_identical_to_the_oracle(knn, tensor_engine, nq, ng, d, k, metric):
+    rs = np.random.RandomState(nq + ng + d)
+    g = rs.standard_normal((ng, d)).astype(np.float32)
+    q = rs.standard_normal((nq, d)).astype(np.float32)
+    if metric == "cosine":
+        g, q = oracle.normalize(g), oracle.normalize(q)
+    else:  # un-normalised rows with very different norms: the error bound scales with |q| * max|g|
+        g *= np.exp(rs.uniform(-2, 2, (ng, 1))).astype(np.float32)
+        q *= np.exp(rs.uniform(-2, 2, (nq, 1))).astype(np.float32)
+    _check(knn, q, g, k, metric)
+
+
+def test_self_modes_offsets_and_clustered_data(knn, tensor_engine):
+    x, _ = synth.clustered(2000, 128, 3, seed=7, noise=0.8)
+    e = oracle.normalize(x)
+    _check(knn, e, e, 10, "cosine", "exclude")
+    _check(knn, e, e, 10, "l2", "exclude")
+    _check(knn, e, e, 50, "cosine", "minus1")
+    _check(knn, e[500:900], e, 20, "cosine", "exclude", 500)          # a chunk of the gallery queries itself
+    _check(knn, e[1900:], e[:1950], 20, "l2", "exclude", 1900)        # self rows partly outside the gallery
+
+
+def test_ties_and_mass_duplicates_take_the_ffma_rerun(knn, tensor_engine):
+    """Exactly-representable rows with duplicates: ties are real, the completeness proof must refuse whenever a tie
+    group straddles the candidate set, and the flagged blocks must come back exact from the FFMA engine."""
+    x = synth.exact_grid(3000, 96, 3, 64)
+    _check(knn, x, x, 10, "ip", "exclude")
+    rs = np.random.RandomState(8)
+    base = oracle.normalize(rs.standard_normal((40, 64)).astype(np.float32))
+    g = np.repeat(base, 300, axis=0)                                   # 300-fold duplicates: 300 > kc for k = 100
+    q = oracle.normalize(rs.standard_normal((260, 64)).astype(np.float32))
+    assert _check(knn, q, g, 100, "cosine") > 0
+    assert _check(knn, q, g, 100, "l2") > 0
+    same = np.repeat(base[:1], 5000, axis=0)                           # everything ties: rows 0..k-1 win
+    _check(knn, q[:3], same, 100, "cosine")
+    # only SOME query blocks are flagged: queries of block 1 sit on a duplicated row, the others see distinct rows
+    g2 = oracle.normalize(rs.standard_normal((6000, 64)).astype(np.float32))
+    g2[1000:1200] = g2[999]
+    q2 = oracle.normalize(rs.standard_normal((640, 64)).astype(np.float32))
+    q2[130:140] = g2[999]
+    n_bad = _check(knn, q2, g2, 100, "cosine")
+    assert 10 <= n_bad < 640
+
+
+def test_observed_filter_error_is_far_inside_the_bound(knn):
+    """The one assumption behind the completeness proof is the tensor cores' accumulation error (2^-21 of the magnitude
+    sum per K=16 step).  Measure |filter value - exact value| on the worst case for accumulation -- all-positive rows,
+    no cancellation -- and on Gaussian rows: it must stay below a QUARTER of the bound."""
+    S = importlib.import_module("b200knn.search")
+
+    rs = np.random.RandomState(21)
+    for d, positive in ((1024, True), (1024, False), (2048, True), (96, True)):
+        g = rs.standard_normal((20000, d)).astype(np.float32)
+        q = rs.standard_normal((256, d)).astype(np.float32)
+        if positive:
+            g, q = np.abs(g), np.abs(q)
+        gd, qd = dev(g), dev(q)
+        kc = 64
+        av, ai = S._search_prepared(S.split_bf16x3(qd, "queries"), None, S.split_bf16x3(gd, "gallery"), None, kc,
+                                    "ip", "keep", 0, 0)
+        exact = knn.scores_dense(qd, gd, "ip")                         # the fp32 chain of the exact mode
+        ev = torch.gather(exact, 1, ai)
+        eps = S.filter_error_bound(S.row_sqnorm(qd), S.row_sqnorm(gd).max(), d, "ip")
+        ratio = ((av - ev).abs() / eps[:, None]).max().item()
+        assert ratio < 0.25, (d, positive, ratio)
+
+
+def test_flat_index_caches_the_split_rows_and_shards_merge_exactly(knn, tensor_engine):
+    rs = np.random.RandomState(5)
+    g = oracle.normalize(rs.standard_normal((9000, 128)).astype(np.float32))
+    q = oracle.normalize(rs.standard_normal((300, 128)).astype(np.float32))
+    ov, oi = oracle.search(q, g, 50, "l2")
+    index = knn.FlatIndex(128, "l2", "fp32").add(dev(g[:4000])).add(dev(g[4000:]))
+    for _ in range(2):
+        v, i = index.search(dev(q), 50)
+        assert np.array_equal(host(i), oi) and np.array_equal(host(v), ov)
+    assert index._filter is not None and index._filter.split.shape == (9000, 3 * 128)
+    parts = [knn.FlatIndex(128, "l2", "fp32", index_base=s).add(dev(g[s:e])).search(dev(q), 50)
+             for s, e in ((0, 3000), (3000, 9000))]
+    mv, mi = knn.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), "l2")
+    assert np.array_equal(host(mi), oi) and np.array_equal(host(mv), ov)
+
+
+def test_c3_full_size_tensor_engine_equals_ffma_engine(knn, monkeypatch):
+    """BASELINE config 3 at full size (25 000 x 112 000 x 1024, top-50, cosine): the default engine for this size is
+    the tensor-core one; it must reproduce the FFMA engine bit for bit."""
+    S = importlib.import_module("b200knn.search")
+
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    g = knn.normalize(torch.randn((112_000, 1024), generator=gen, device="cuda"))
+    q = knn.normalize(torch.randn((25_000, 1024), generator=gen, device="cuda"))
+    assert S.exact_engine(25_000, 112_000, 1024, 50) == "tensor"
+    v, i = knn.search(q, g, 50, "cosine", precision="fp32")
+    assert S._search_exact_tensor.last_unverified < 25          # Gaussian rows: (almost) every query is proven
+    monkeypatch.setenv("KNN_EXACT_ENGINE", "ffma")
+    fv, fi = knn.search(q, g, 50, "cosine", precision="fp32")
+    assert torch.equal(i, fi) and torch.equal(v, fv)

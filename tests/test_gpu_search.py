@@ -182,6 +182,27 @@ def test_list_compaction_falls_back_to_the_sort_without_duplicates(knn):
     assert all(len(set(r)) == k for r in i[::257].tolist())
 
 
+@pytest.mark.parametrize("precision,nq,d", [("fp32", 5, 2), ("fp32", 300, 2), ("bf16", 5, 8), ("bf16", 300, 8),
+                                            ("bf16", 5, 1024)])
+def test_every_row_beats_the_threshold_for_every_list_geometry(knn, precision, nq, d):
+    """Regression: with the shortest lists (k <= 32: capacity 64) the selection-based compaction left more than
+    capacity - 32 keys, and the next chunk's hits were written past the end of the list into the neighbouring row's
+    (lost candidates; bf16 at k = 32 missed a neighbour in 10 % of the rows).  Worst case for every list geometry:
+    scores ascend with the gallery row, so EVERY new row beats the threshold.  score_j = j / 65536 exactly, built
+    from bf16-representable parts so both precisions are bit-exact; negative queries see the descending order."""
+    ng = 60_000
+    j = np.arange(ng)
+    g = np.zeros((ng, d), dtype=np.float32)
+    g[:, 0] = (j // 256) / 256.0
+    g[:, 1] = (j % 256).astype(np.float32)
+    qv = np.zeros((nq, d), dtype=np.float32)
+    scale = (2.0 ** (np.arange(nq) % 5)) * np.where(np.arange(nq) % 3 == 2, -1.0, 1.0)
+    qv[:, 0] = scale
+    qv[:, 1] = scale * 2.0 ** -16
+    for k in (1, 10, 20, 31, 32, 33, 64, 100, 128, 256):
+        _check_exact(knn, qv, g, k, "ip", precision=precision)
+
+
 def test_self_modes_with_offset(knn):
     rs = np.random.RandomState(5)
     g = oracle.normalize(rs.standard_normal((700, 40)).astype(np.float32))
