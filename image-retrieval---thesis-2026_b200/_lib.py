@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200knn.so")
 
 # constants mirrored from include/b200knn.h
-KNN_F32, KNN_BF16 = 0, 1
+KNN_F32, KNN_BF16, KNN_BF16X3 = 0, 1, 2
 KNN_COSINE, KNN_IP, KNN_L2 = 0, 1, 2
 KNN_EPS_CLAMP, KNN_EPS_NONE, KNN_EPS_ADD, KNN_CAST_ONLY = 0, 1, 2, 3
 KNN_SELF_KEEP, KNN_SELF_EXCLUDE, KNN_SELF_MINUS1 = 0, 1, 2

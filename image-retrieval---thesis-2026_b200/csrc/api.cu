@@ -130,7 +130,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // [rows, d] bf16 row-major -> 2-D tensor map with a {64 elements, box_rows} box and 128-byte swizzle (the layout
 // the UMMA shared-memory descriptors of ptx.cuh expect).  Rows past the end read as zeros.
-int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows) {
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch) {
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -143,7 +143,7 @@ int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d,
     enc = reinterpret_cast<EncodeTiledFn>(fn);
   }
   cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+  cuuint64_t gstride[1] = {(cuuint64_t)(pitch > 0 ? pitch : d) * 2};
   cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -231,6 +231,7 @@ static WsLayout ws_layout(const SearchGeom& g) {
 
 extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
+  if (dtype == KNN_BF16X3) dtype = KNN_BF16;  // same geometry: the split rows are bf16 rows of 3 * dpad columns
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
   const WsLayout w = ws_layout(g);
   return w.tau_bytes + w.counts_bytes + w.lists_bytes;
@@ -255,6 +256,11 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
                           int64_t ng, int d, int dtype, int k, int metric, int self_mode, int64_t self_offset,
                           int64_t index_base, float* out_val, int64_t* out_idx, void* workspace,
                           size_t workspace_bytes, void* stream) {
+  const bool split3 = dtype == KNN_BF16X3;
+  if (split3) {
+    KNN_REQUIRE(d % 24 == 0, "KNN_BF16X3 rows are 3 parts of a multiple of 8 columns, got d=%d", d);
+    dtype = KNN_BF16;
+  }
   int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
   if (rc != KNN_OK) return rc;
   KNN_REQUIRE(k >= 1, "k must be >= 1, got %d", k);
@@ -281,6 +287,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.metric = metric; p.self_mode = self_mode;
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
+  p.split3 = split3 ? 1 : 0;
   const WsLayout wl = ws_layout(geo);
   const size_t tau_bytes = wl.tau_bytes;
   p.tau_global = reinterpret_cast<uint32_t*>(workspace);

@@ -19,7 +19,9 @@
 // accumulation + the fp32 chain's own rounding; computed by the host layer from the row norms).  If the k-th best
 // exact score t satisfies t > m + eps the emitted top-k is the exact one, bit for bit; otherwise the query is
 // flagged and the host layer re-runs it through the FFMA kernel (ties / near-duplicates wider than the slack).
+#include <stdlib.h>
 #include "common.cuh"
+#include "ptx.cuh"
 #include "kernels.h"
 
 namespace knn {
@@ -76,73 +78,31 @@ __device__ __forceinline__ void bitonic_desc(uint64_t* s, int n) {
   }
 }
 
-// One CTA per query.  Thread t re-scores candidates t, t + 128, ... with the exact chain
-//   dot = fmaf(q[0], g[0], +0) ... fmaf(q[d-1], g[d-1], dot)      (search_f32.cu's definition)
-template <bool kL2, bool kVec>
-__global__ void __launch_bounds__(kRescoreThreads)
-rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ qsq,
-                     const float* __restrict__ gsq, int64_t ng, int d, int self_mode, int64_t self_offset,
-                     int64_t index_base, const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
-                     int kc, int k, int npad, const float* __restrict__ eps, float* __restrict__ out_val,
-                     int64_t* __restrict__ out_idx, int32_t* __restrict__ unverified) {
-  extern __shared__ __align__(16) uint8_t rs_smem[];
-  uint64_t* keys = reinterpret_cast<uint64_t*>(rs_smem);             // [npad]
-  float* qs = reinterpret_cast<float*>(rs_smem + (size_t)npad * 8);  // [d rounded up to 4]
-  __shared__ int s_nvalid;
-  const int64_t r = blockIdx.x;
-  const float* qrow = q + r * (int64_t)d;
-  if (threadIdx.x == 0) s_nvalid = 0;
-  for (int e = threadIdx.x; e < ((d + 3) & ~3); e += blockDim.x) qs[e] = e < d ? __ldg(qrow + e) : 0.0f;
-  __syncthreads();
-
-  const int64_t self_row = (self_mode != KNN_SELF_KEEP) ? self_offset + r : -1;  // local gallery row of this query
-  const float qn = kL2 ? __ldg(qsq + r) : 0.0f;
-  int nvalid = 0;
-  for (int j = threadIdx.x; j < npad; j += blockDim.x) {
-    uint64_t key = 0ull;
-    if (j < kc) {
-      const int64_t gi = cand_idx[r * kc + j];
-      const int64_t row = gi - index_base;
-      if (gi >= 0 && row >= 0 && row < ng) {
-        ++nvalid;
-        const float* grow = g + row * (int64_t)d;
-        float dot = 0.0f;
-        if (kVec) {
-          const float4* g4 = reinterpret_cast<const float4*>(grow);
-          const float4* q4 = reinterpret_cast<const float4*>(qs);
-#pragma unroll 4
-          for (int e = 0; e < (d >> 2); ++e) {
-            const float4 b = __ldg(g4 + e);
-            const float4 a = q4[e];
-            dot = fmaf(a.x, b.x, dot);
-            dot = fmaf(a.y, b.y, dot);
-            dot = fmaf(a.z, b.z, dot);
-            dot = fmaf(a.w, b.w, dot);
-          }
-        } else {
-          for (int e = 0; e < d; ++e) dot = fmaf(qs[e], __ldg(grow + e), dot);
-        }
-        float s;
-        if (kL2) {
-          const float f = fmaf(2.0f, dot, -(qn + __ldg(gsq + row)));
-          s = -__fsqrt_rn(fmaxf(-f, 0.0f));
-        } else {
-          s = dot;
-        }
-        bool take = true;
-        if (row == self_row) {
-          if (self_mode == KNN_SELF_EXCLUDE) take = false;
-          else if (self_mode == KNN_SELF_MINUS1) s = -1.0f;
-        }
-        if (take) key = make_key(s, (uint32_t)row);
-      }
-    }
-    keys[j] = key;
+// Exact-mode score of one candidate from its fp32 chain `dot` -> sortable key (0 = not a candidate).
+template <bool kL2>
+__device__ __forceinline__ uint64_t exact_key(float dot, float qn, const float* __restrict__ gsq, int64_t row,
+                                              int64_t self_row, int self_mode) {
+  float s;
+  if (kL2) {
+    const float f = fmaf(2.0f, dot, -(qn + __ldg(gsq + row)));
+    s = -__fsqrt_rn(fmaxf(-f, 0.0f));
+  } else {
+    s = dot;
   }
-  if (nvalid) atomicAdd(&s_nvalid, nvalid);
-  __syncthreads();
-  bitonic_desc(keys, npad);
+  if (row == self_row) {
+    if (self_mode == KNN_SELF_EXCLUDE) return 0ull;
+    if (self_mode == KNN_SELF_MINUS1) s = -1.0f;
+  }
+  return make_key(s, (uint32_t)row);
+}
 
+// Sort the re-scored keys, emit the best k, and decide whether the candidate set provably contains the answer.
+template <bool kL2>
+__device__ __forceinline__ void emit_and_verify(uint64_t* keys, int npad, int nvalid_cands, int64_t r, int kc, int k,
+                                                int64_t index_base, const float* __restrict__ cand_val,
+                                                const float* __restrict__ eps, float* __restrict__ out_val,
+                                                int64_t* __restrict__ out_idx, int32_t* __restrict__ unverified) {
+  bitonic_desc(keys, npad);
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const uint64_t key = j < npad ? keys[j] : 0ull;
     float v;
@@ -160,7 +120,7 @@ rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, c
   }
   if (threadIdx.x == 0) {
     bool ok;
-    if (s_nvalid < kc) {
+    if (nvalid_cands < kc) {
       ok = true;  // the filter returned every admissible row of the gallery: nothing is outside the candidate set
     } else {
       const uint64_t kk = keys[k - 1];
@@ -180,6 +140,135 @@ rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, c
     }
     unverified[r] = ok ? 0 : 1;
   }
+}
+
+// Generic form: one CTA per query, thread t re-scores candidates t, t + 128, ... reading its rows straight from
+// global memory.  Any d, any kc <= 4096.  The exact chain (search_f32.cu's definition):
+//   dot = fmaf(q[0], g[0], +0) ... fmaf(q[d-1], g[d-1], dot)
+template <bool kL2>
+__global__ void __launch_bounds__(kRescoreThreads)
+rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ qsq,
+                     const float* __restrict__ gsq, int64_t ng, int d, int self_mode, int64_t self_offset,
+                     int64_t index_base, const float* __restrict__ cand_val, const int64_t* __restrict__ cand_idx,
+                     int kc, int k, int npad, const float* __restrict__ eps, float* __restrict__ out_val,
+                     int64_t* __restrict__ out_idx, int32_t* __restrict__ unverified) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(rs_smem);             // [npad]
+  float* qs = reinterpret_cast<float*>(rs_smem + (size_t)npad * 8);  // [d]
+  __shared__ int s_nvalid;
+  const int64_t r = blockIdx.x;
+  const float* qrow = q + r * (int64_t)d;
+  if (threadIdx.x == 0) s_nvalid = 0;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) qs[e] = __ldg(qrow + e);
+  __syncthreads();
+  const int64_t self_row = (self_mode != KNN_SELF_KEEP) ? self_offset + r : -1;  // local gallery row of this query
+  const float qn = kL2 ? __ldg(qsq + r) : 0.0f;
+  int nvalid = 0;
+  for (int j = threadIdx.x; j < npad; j += blockDim.x) {
+    uint64_t key = 0ull;
+    if (j < kc) {
+      const int64_t row = cand_idx[r * kc + j] - index_base;
+      if (cand_idx[r * kc + j] >= 0 && row >= 0 && row < ng) {
+        ++nvalid;
+        const float* grow = g + row * (int64_t)d;
+        float dot = 0.0f;
+        for (int e = 0; e < d; ++e) dot = fmaf(qs[e], __ldg(grow + e), dot);
+        key = exact_key<kL2>(dot, qn, gsq, row, self_row, self_mode);
+      }
+    }
+    keys[j] = key;
+  }
+  if (nvalid) atomicAdd(&s_nvalid, nvalid);
+  __syncthreads();
+  emit_and_verify<kL2>(keys, npad, s_nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified);
+}
+
+// Streaming form (d % 4 == 0, kc <= 256): one CTA per query, ONE THREAD PER CANDIDATE.  The candidates' gallery rows
+// are scattered over HBM; read 16 bytes at a time by 64 independent threads they arrive as 64-byte fragments of 64
+// different DRAM pages (measured 1.2 TB/s).  Here every thread asks the TMA engine for `cf` floats (256 B at kc = 64)
+// of ITS row per step -- cp.async.bulk, three steps in flight, all landing on one mbarrier per stage -- and runs the
+// chain from shared memory (row pitch cf + 4 floats: conflict-free float4 reads).
+constexpr int kRsStages = 3;
+
+template <bool kL2>
+__global__ void __launch_bounds__(256)
+rescore_exact_stream_kernel(const float* __restrict__ q, const float* __restrict__ g, const float* __restrict__ qsq,
+                            const float* __restrict__ gsq, int64_t ng, int d, int self_mode, int64_t self_offset,
+                            int64_t index_base, const float* __restrict__ cand_val,
+                            const int64_t* __restrict__ cand_idx, int kc, int k, int cf, const float* __restrict__ eps,
+                            float* __restrict__ out_val, int64_t* __restrict__ out_idx,
+                            int32_t* __restrict__ unverified) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  const int npad = blockDim.x;                                        // pow2 >= max(kc, 32)
+  const int pitch = cf + 4;                                           // floats
+  uint64_t* keys = reinterpret_cast<uint64_t*>(rs_smem);              // [npad]
+  float* qs = reinterpret_cast<float*>(rs_smem + (size_t)npad * 8);   // [d]
+  float* ring = qs + d;                                               // [kRsStages][npad][pitch]
+  __shared__ uint64_t bars[kRsStages];
+  const int64_t r = blockIdx.x;
+  const int c = threadIdx.x;
+  if (c == 0) {
+    for (int s = 0; s < kRsStages; ++s) ptx::mbar_init(&bars[s], (uint32_t)npad);
+    ptx::fence_barrier_init();
+  }
+  int64_t row = -1;
+  if (c < kc) {
+    const int64_t gi = cand_idx[r * kc + c];
+    if (gi >= 0 && gi - index_base >= 0 && gi - index_base < ng) row = gi - index_base;
+  }
+  const bool active = row >= 0;
+  const float* grow = g + (active ? row : 0) * (int64_t)d;
+  const float* qrow = q + r * (int64_t)d;
+  for (int e = c * 4; e < d; e += npad * 4)
+    *reinterpret_cast<float4*>(qs + e) = __ldg(reinterpret_cast<const float4*>(qrow + e));
+  const int nvalid = __syncthreads_count(active ? 1 : 0);            // also: barriers initialised, qs complete
+
+  const int nchunks = (d + cf - 1) / cf;
+  const uint32_t bar0 = ptx::smem_u32(&bars[0]);
+  const uint32_t my_slot0 = ptx::smem_u32(ring + (size_t)c * pitch);
+  const uint32_t stage_bytes = (uint32_t)npad * (uint32_t)pitch * 4u;
+  auto issue = [&](int i, int s) {
+    const uint32_t bar = bar0 + (uint32_t)s * 8u;
+    if (active) {
+      const int rem = d - i * cf;
+      const uint32_t bytes = (uint32_t)(rem < cf ? rem : cf) * 4u;
+      ptx::mbar_arrive_expect_tx_u32(bar, bytes);
+      ptx::bulk_load_1d(my_slot0 + (uint32_t)s * stage_bytes, grow + (size_t)i * cf, bytes, bar);
+    } else {
+      ptx::mbar_arrive_u32(bar);
+    }
+  };
+  for (int s = 0; s < kRsStages && s < nchunks; ++s) issue(s, s);
+
+  float dot = 0.0f;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < nchunks; ++i) {
+    ptx::mbar_wait(&bars[s], phase);
+    if (active) {
+      const float4* b4 = reinterpret_cast<const float4*>(ring + ((size_t)s * npad + c) * pitch);
+      const float4* a4 = reinterpret_cast<const float4*>(qs + (size_t)i * cf);
+      const int rem = d - i * cf;
+      const int n4 = (rem < cf ? rem : cf) >> 2;
+#pragma unroll 8
+      for (int e = 0; e < n4; ++e) {
+        const float4 b = b4[e];
+        const float4 a = a4[e];
+        dot = fmaf(a.x, b.x, dot);
+        dot = fmaf(a.y, b.y, dot);
+        dot = fmaf(a.z, b.z, dot);
+        dot = fmaf(a.w, b.w, dot);
+      }
+    }
+    __syncthreads();                                   // every reader of stage s is done: it may be refilled
+    if (i + kRsStages < nchunks) issue(i + kRsStages, s);
+    if (++s == kRsStages) { s = 0; phase ^= 1; }
+  }
+  const int64_t self_row = (self_mode != KNN_SELF_KEEP) ? self_offset + r : -1;
+  const float qn = kL2 ? __ldg(qsq + r) : 0.0f;
+  keys[c] = active ? exact_key<kL2>(dot, qn, gsq, row, self_row, self_mode) : 0ull;
+  __syncthreads();
+  emit_and_verify<kL2>(keys, npad, nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified);
 }
 
 }  // namespace
@@ -214,27 +303,37 @@ extern "C" int knn_rescore_exact(const float* q, const float* g, const float* q_
   if (nq == 0) return KNN_OK;
   KNN_REQUIRE(q && g && cand_val && cand_idx && eps && out_val && out_idx && unverified, "null pointer");
   KNN_REQUIRE(metric != KNN_L2 || (q_sqnorm && g_sqnorm), "KNN_L2 needs q_sqnorm and g_sqnorm");
-  int npad = 2;
-  while (npad < kc) npad <<= 1;
-  const size_t smem = (size_t)npad * 8 + (size_t)((d + 3) & ~3) * 4;
-  const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
   const int64_t self_local = self_offset - index_base;
   cudaStream_t s = (cudaStream_t)stream;
-#define KNN_LAUNCH_RESCORE(L2, VEC)                                                                              \
-  do {                                                                                                           \
-    auto kern = rescore_exact_kernel<L2, VEC>;                                                                   \
-    if (smem > 48 * 1024)                                                                                        \
-      KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-    kern<<<(unsigned)nq, kRescoreThreads, smem, s>>>(q, g, q_sqnorm, g_sqnorm, ng, d, self_mode, self_local,     \
-                                                     index_base, cand_val, cand_idx, kc, k, npad, eps, out_val,  \
-                                                     out_idx, unverified);                                       \
-  } while (0)
-  if (metric == KNN_L2) {
-    if (vec) KNN_LAUNCH_RESCORE(true, true); else KNN_LAUNCH_RESCORE(true, false);
+  const bool l2 = metric == KNN_L2;
+  const bool stream_ok = (d & 3) == 0 && kc <= 256 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
+  if (stream_ok) {
+    int npad = 32;
+    while (npad < kc) npad <<= 1;
+    // floats per row and step: 256 B per row (measured at 25 000 x 64 candidates x 1024-d: 5.2 TB/s of gathered rows;
+    // 512 B: 4.4 TB/s -- fewer CTAs per SM to hide each CTA's prologue / sort; 128 B: 4.7 TB/s), less for wide CTAs
+    static const int cf_max = [] {
+      const char* e = getenv("KNN_RESCORE_CF");  // experiment knob
+      const int v = e ? atoi(e) : 0;
+      return (v == 32 || v == 64 || v == 128) ? v : 64;
+    }();
+    int cf = cf_max;
+    while (cf > 32 && (size_t)kRsStages * npad * (cf + 4) * 4 > 104 * 1024) cf >>= 1;
+    const size_t smem = (size_t)npad * 8 + (size_t)d * 4 + (size_t)kRsStages * npad * (cf + 4) * 4;
+    auto kern = l2 ? rescore_exact_stream_kernel<true> : rescore_exact_stream_kernel<false>;
+    KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nq, npad, smem, s>>>(q, g, q_sqnorm, g_sqnorm, ng, d, self_mode, self_local, index_base, cand_val,
+                                          cand_idx, kc, k, cf, eps, out_val, out_idx, unverified);
   } else {
-    if (vec) KNN_LAUNCH_RESCORE(false, true); else KNN_LAUNCH_RESCORE(false, false);
+    int npad = 2;
+    while (npad < kc) npad <<= 1;
+    const size_t smem = (size_t)npad * 8 + (size_t)d * 4;
+    auto kern = l2 ? rescore_exact_kernel<true> : rescore_exact_kernel<false>;
+    if (smem > 48 * 1024)
+      KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)nq, kRescoreThreads, smem, s>>>(q, g, q_sqnorm, g_sqnorm, ng, d, self_mode, self_local, index_base,
+                                                    cand_val, cand_idx, kc, k, npad, eps, out_val, out_idx, unverified);
   }
-#undef KNN_LAUNCH_RESCORE
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
 }

@@ -21,6 +21,7 @@ struct SearchParams {
   int splits;
   int groups;            // candidate lists per (split, row): 2 for the TMEM-resident kernel, else 1
   int qblocks;
+  int split3;            // rows are knn_split_bf16x3 output (3 parts of d/3 columns): q [hi|lo|hi], g [hi|hi|lo]
   uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys (unordered)
   int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
@@ -50,7 +51,8 @@ int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream)
 int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, uint64_t* out, cudaStream_t stream);
 
 // [rows, d] bf16 row-major -> tensor map with a {64, box_rows} box, 128-byte swizzle (api.cu)
-int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows);
+// pitch = elements between consecutive rows (0: d) -- a map over a column range of wider rows reads zeros past d
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch = 0);
 
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();

@@ -102,6 +102,16 @@ __device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const void* t
 __device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// 1-D bulk asynchronous copy global -> shared (TMA engine, no tensor map): src, dst and bytes are multiples of 16;
+// completes `bytes` of transaction count on `bar`.
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // One lane of a converged warp.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

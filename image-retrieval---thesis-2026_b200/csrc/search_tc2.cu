@@ -57,9 +57,14 @@ struct PairCfg {
 };
 
 // kDiag = false is the production build: the stall counters and timing-experiment switches compile away.
-template <int E, bool kL2, bool kDiag>
+// kSplit: the rows are bf16x3 split rows (knn_split_bf16x3; the filter of the tensor-core exact mode).  The score is
+// qhi.ghi + qlo.ghi + qhi.glo: every ring stage holds the hi AND lo k-blocks of both operands (4 x 16 KB per CTA,
+// tmap_q / tmap_g = hi parts, tmap_q2 / tmap_g2 = lo parts) and feeds 12 MMAs, so each part crosses L2 -> SM once
+// per tile instead of once per product (as plain bf16 rows of 3x the width the kernel is L2 -> SM bound: 64 B/cycle/SM).
+template <int E, bool kL2, bool kDiag, bool kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                        const __grid_constant__ CUtensorMap tmap_q2, const __grid_constant__ CUtensorMap tmap_g2,
                         SearchParams p, PairCfg cfg) {
   const bool stats_on = kDiag && cfg.stats != nullptr;
   const int debug = kDiag ? cfg.debug : 0;
@@ -88,6 +93,10 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_g);
+    if (kSplit) {
+      ptx::prefetch_tensormap(&tmap_q2);
+      ptx::prefetch_tensormap(&tmap_g2);
+    }
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&bars->full[s], 2);
       ptx::mbar_init(&bars->empty[s], 1);
@@ -148,7 +157,11 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           const uint32_t dst = ring_u32 + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t full_bar = full0 + (uint32_t)stage * 8u;
           ptx::tma_load_2d_2sm_u32(dst, &tmap_g, full_bar, kb * BKE, col0, ptx::kEvictNormal);
-          if (!cfg.resident)
+          if (kSplit) {  // stage = {G hi, G lo, Q hi, Q lo}
+            ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_g2, full_bar, kb * BKE, col0, ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm_u32(dst + 2 * KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
+            ptx::tma_load_2d_2sm_u32(dst + 3 * KB_BYTES, &tmap_q2, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
+          } else if (!cfg.resident)
             ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
           if (leader) ptx::mbar_arrive_expect_tx_u32(full_bar, tx_bytes);
           else ptx::mbar_arrive_cluster(full_bar);
@@ -190,12 +203,33 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           ptx::mbar_wait(&bars->full[stage], phase);
           if (stats_on) w_full += clock64() - c0;
           if (issuer) {
-            const uint32_t a_lo = cfg.resident ? a_res : b_lo + (KB_BYTES >> 4);
+            if (kSplit) {
+              constexpr uint32_t kPart = KB_BYTES >> 4;  // descriptor units between the parts of a stage
 #pragma unroll
-            for (int k = 0; k < BKE / UMMA_K; ++k) {
-              const uint64_t da = ptx::sw128_desc(a_lo + (uint32_t)(k * UMMA_K * 2 / 16));
-              const uint64_t db = ptx::sw128_desc(b_lo + (uint32_t)(k * UMMA_K * 2 / 16));
-              ptx::mma_bf16_ss_2sm(tmem_d, da, db, idesc, (k != 0 || kb != 0) ? 1u : 0u);
+              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_hi . g_hi
+                const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
+                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 2 * kPart + ko), ptx::sw128_desc(b_lo + ko), idesc,
+                                     (k != 0 || kb != 0) ? 1u : 0u);
+              }
+#pragma unroll
+              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_lo . g_hi
+                const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
+                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 3 * kPart + ko), ptx::sw128_desc(b_lo + ko), idesc, 1u);
+              }
+#pragma unroll
+              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_hi . g_lo
+                const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
+                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 2 * kPart + ko), ptx::sw128_desc(b_lo + kPart + ko), idesc,
+                                     1u);
+              }
+            } else {
+              const uint32_t a_lo = cfg.resident ? a_res : b_lo + (KB_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < BKE / UMMA_K; ++k) {
+                const uint64_t da = ptx::sw128_desc(a_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+                const uint64_t db = ptx::sw128_desc(b_lo + (uint32_t)(k * UMMA_K * 2 / 16));
+                ptx::mma_bf16_ss_2sm(tmem_d, da, db, idesc, (k != 0 || kb != 0) ? 1u : 0u);
+              }
             }
             ptx::tc_commit_2sm(&bars->empty[stage], 3);  // frees this slot in BOTH CTAs when the MMAs retire
           }
@@ -289,20 +323,32 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-template <int E>
+template <int E, bool kSplit>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
-  CUtensorMap tq, tg;
-  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, p.d, TM);
+  CUtensorMap tq, tg, tq2, tg2;
+  const int dpart = kSplit ? p.d / 3 : p.d;  // columns of one operand part
+  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, dpart, TM, p.d);
   if (rc != KNN_OK) return rc;
-  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, p.d, TNH);
+  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, dpart, TNH, p.d);
   if (rc != KNN_OK) return rc;
+  if (kSplit) {  // queries [hi | lo | hi], gallery [hi | hi | lo]: the lo parts
+    const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(p.q);
+    const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(p.g);
+    rc = make_tmap_bf16_rows(&tq2, qb + dpart, p.nq, dpart, TM, p.d);
+    if (rc != KNN_OK) return rc;
+    rc = make_tmap_bf16_rows(&tg2, gb + 2 * dpart, p.ng, dpart, TNH, p.d);
+    if (rc != KNN_OK) return rc;
+  } else {
+    tq2 = tq;
+    tg2 = tg;
+  }
 
   PairCfg cfg;
-  cfg.nkb = (p.d + BKE - 1) / BKE;
+  cfg.nkb = (dpart + BKE - 1) / BKE;
   const size_t fixed = sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
-  cfg.resident = ((size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
+  cfg.resident = (!kSplit && (size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
   cfg.a_bytes = cfg.resident ? (uint32_t)cfg.nkb * KB_BYTES : 0u;
-  cfg.stage_bytes = cfg.resident ? KB_BYTES : 2 * KB_BYTES;
+  cfg.stage_bytes = kSplit ? 4 * KB_BYTES : (cfg.resident ? KB_BYTES : 2 * KB_BYTES);
   int stages = (int)((kSmemBudget - fixed - cfg.a_bytes) / cfg.stage_bytes);
   cfg.stages = stages > kMaxStages ? kMaxStages : stages;
   cfg.debug = 0;
@@ -319,20 +365,25 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);  // qblocks is even: consecutive CTAs form the pair
   const bool diag = cfg.stats != nullptr || cfg.debug != 0;
   if (p.metric == KNN_L2) {
-    auto kern = search_bf16_pair_kernel<E, true, false>;
+    auto kern = search_bf16_pair_kernel<E, true, false, kSplit>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, tq2, tg2, p, cfg);
   } else if (diag && E == 8) {  // diagnostics build exists for the k <= 128, similarity instantiation only
-    auto kern = search_bf16_pair_kernel<8, false, true>;
+    auto kern = search_bf16_pair_kernel<8, false, true, kSplit>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, tq2, tg2, p, cfg);
   } else {
-    auto kern = search_bf16_pair_kernel<E, false, false>;
+    auto kern = search_bf16_pair_kernel<E, false, false, kSplit>;
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, stream>>>(tq, tg, p, cfg);
+    kern<<<grid, kThreads, smem, stream>>>(tq, tg, tq2, tg2, p, cfg);
   }
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
+}
+
+template <int E>
+int launch_e(const SearchParams& p, cudaStream_t stream) {
+  return p.split3 ? launch_e<E, true>(p, stream) : launch_e<E, false>(p, stream);
 }
 
 }  // namespace

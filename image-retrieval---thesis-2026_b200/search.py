@@ -274,7 +274,7 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
     q_sq = qsq if qsq is not None else row_sqnorm(q)
     eps = filter_error_bound(q_sq, filt.max_sqnorm, d, metric)
     cand_val, cand_idx = _search_prepared(split_bf16x3(q, "queries"), qsq, filt.split, gsq if metric == "l2" else None,
-                                          kc, metric, self_mode, query_offset, index_base)
+                                          kc, metric, self_mode, query_offset, index_base, split_rows=True)
     out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
     flags = torch.empty((nq,), dtype=torch.int32, device=dev)
@@ -310,7 +310,8 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
 _search_exact_tensor.last_unverified = 0
 
 
-def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base):
+def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base, split_rows=False):
+    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3: same scores, each part loaded once per tile)."""
     nq, d = q.shape
     ng = g.shape[0]
     if g.shape[1] != d or g.dtype != q.dtype:
@@ -325,9 +326,10 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     lib = L.load()
     with torch.cuda.device(dev):
         if k <= L.MAX_FUSED_K:
-            nbytes = lib.knn_search_workspace(nq, ng, d, _DT[q.dtype], k)
+            dt = L.KNN_BF16X3 if split_rows else _DT[q.dtype]
+            nbytes = lib.knn_search_workspace(nq, ng, d, dt, k)
             ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
-            rc = lib.knn_search(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _DT[q.dtype], k, _METRICS[metric],
+            rc = lib.knn_search(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, dt, k, _METRICS[metric],
                                 _SELF[self_mode], query_offset, index_base, _ptr(out_val), _ptr(out_idx),
                                 _ptr(ws), ws.numel(), _stream(q))
             L.check(rc, "knn_search")

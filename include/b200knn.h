@@ -42,6 +42,8 @@ extern "C" {
 /* element types */
 #define KNN_F32   0
 #define KNN_BF16  1
+#define KNN_BF16X3 2  /* knn_search only: bf16 rows written by knn_split_bf16x3 (d = 3 * dpad); same result as KNN_BF16
+                         over those rows, but the kernels may load each hi / lo part once for the three products */
 
 /* metrics: score ordering is always "best first" in the outputs */
 #define KNN_COSINE 0   /* inner product of (already normalised) rows, larger = better (test.py:1006, train.py:405) */
