@@ -34,6 +34,8 @@ WORKLOADS = {
     "c5": (8192, 50_000_000, 512, 100),
     "c4": (64, 10_000_000, 768, 100),
     "c3": (25_000, 112_000, 1024, 50),
+    # exact fp32 mode (BASELINE config 3 as quoted: bit-exact indices / metrics), tensor-core exact engine
+    "c3-fp32": (25_000, 112_000, 1024, 50),
 }
 
 
@@ -192,34 +194,41 @@ def main():
     nq, ng = args.queries or nq, args.gallery_rows or ng
     start, count = shard_rows(ng, world)[rank]
     lib = b200knn.load_library()
+    exact = args.workload.endswith("-fp32")
+    precision = "fp32" if exact else "bf16"
+    store_dtype = torch.float32 if exact else torch.bfloat16
 
-    # ---- gallery shard: generated on the device chunk by chunk, fused normalise + bf16 cast ----------------
-    rows = torch.empty((count, d), dtype=torch.bfloat16, device=dev)
+    # ---- gallery shard: generated on the device chunk by chunk, fused normalise + cast ---------------------
+    rows = torch.empty((count, d), dtype=store_dtype, device=dev)
     gen = torch.Generator(device=dev)
     chunk = 1 << 20
     for s in range(0, count, chunk):
         e = min(count, s + chunk)
         gen.manual_seed(1234567 + start + s)
         x = torch.randn((e - s, d), generator=gen, device=dev, dtype=torch.float32)
-        rows[s:e] = b200knn.normalize(x, out_dtype=torch.bfloat16)
+        rows[s:e] = b200knn.normalize(x, out_dtype=store_dtype)
     del x
-    index = b200knn.FlatIndex(d, "cosine", "bf16", normalize=True, index_base=start, device=dev).adopt(rows)
+    index = b200knn.FlatIndex(d, "cosine", precision, normalize=True, index_base=start, device=dev).adopt(rows)
     sharded = ShardedFlatIndex(index)
 
     # ---- queries: perturbed gallery rows of rank 0 (so true neighbours exist), replicated on every rank ----
     gen.manual_seed(99)
     qsrc = torch.randn((nq, d), generator=gen, device=dev, dtype=torch.float32)
     q_host = qsrc.cpu().pin_memory()                      # the user's host buffer (fp32)
-    q_dev = b200knn.normalize(qsrc, out_dtype=torch.bfloat16)
+    q_dev = b200knn.normalize(qsrc, out_dtype=store_dtype)
+    index_prepared = b200knn.FlatIndex(d, "cosine", precision, normalize=False, index_base=start, device=dev).adopt(rows)
     out_val_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     out_idx_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
 
     def step_resident():
         # queries already normalised/bf16 in HBM; FlatIndex.search with normalize=True would renormalise, so call
         # the prepared path directly (what FlatIndex.search does after _prepare)
-        from b200knn.search import _search_prepared
+        if exact:  # FlatIndex.search on already-normalised rows: split filter + exact re-scoring + proof
+            v, i = index_prepared.search(q_dev, k)
+        else:
+            from b200knn.search import _search_prepared
 
-        v, i = _search_prepared(q_dev, None, index.rows, None, k, "cosine", "keep", 0, index.index_base)
+            v, i = _search_prepared(q_dev, None, index.rows, None, k, "cosine", "keep", 0, index.index_base)
         if world > 1:
             from b200knn.sharded import pack_candidates, unpack_candidates
 
@@ -281,24 +290,28 @@ def main():
     dist_ms = sum(a for a, _, _ in kern_ms) / len(kern_ms)     # the dominant kernel alone
     merge_ms = sum(b for _, b, _ in kern_ms) / len(kern_ms)
     seed_ms = sum(c for _, _, c in kern_ms) / len(kern_ms)     # threshold-seeding pre-pass + seeding merge
-    flops = 2.0 * nq * count * d
+    flops = 2.0 * nq * count * d                               # algorithmic: every (q, g, d) product counted once
     achieved = flops / (dist_ms / 1e3) / 1e12
-    gallery_gbs = count * d * 2 / (dist_ms / 1e3) / 1e9
+    esize = 4 if exact else 2
+    gallery_gbs = count * d * esize / (dist_ms / 1e3) / 1e9
     # regime: arithmetic intensity 2Q/2 FLOP/B for bf16 against the measured ridge
     ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
     hbm_bound = nq < ridge
-    algo_bytes = count * d * 2 + nq * d * 2 + nq * k * 12
+    algo_bytes = count * d * esize + nq * d * esize + nq * k * 12
     # dispatch rule of knn_search (csrc/api.cu): one 128-row query block and d <= 768 -> TMEM-resident-query kernel,
     # several query blocks -> CTA-pair kernel
     kernel_name = ("search_bf16_ts_kernel" if d <= 768 else "search_bf16_kernel") if nq <= 128 else "search_bf16_pair_kernel"
+    if exact:
+        kernel_name = "search_bf16_pair_kernel<kSplit> (bf16x3 filter of the exact mode)" if nq > 128 else kernel_name
 
     # recall sanity of the timed configuration is covered by tests; here only the top-1 self-consistency
     line = {
         "metric": "queries/sec @top-100", "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if exact else "bf16",
+        "data": "synthetic",
         "config": {
-            "workload": f"{args.workload}: {nq} queries x {ng} gallery x {d}-d bf16, top-{k}, cosine",
+            "workload": f"{args.workload}: {nq} queries x {ng} gallery x {d}-d {precision}, top-{k}, cosine",
             "gallery_rows_per_gpu": count, "sharding": f"rows/{world}", "l2_flush": "inputs larger than L2 "
             f"({count * d * 2 / 1e9:.1f} GB gallery shard streamed per step)",
         },
@@ -323,6 +336,18 @@ def main():
         "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
         "clocks": clocks.summary(),
     }
+    if exact:
+        import importlib
+
+        S = importlib.import_module("b200knn.search")
+        line["roofline"]["note"] = (
+            "exact fp32 mode on the tensor cores: the dominant kernel is the bf16x3 split filter (3 MMAs per product, "
+            "csrc/search_tc2.cu kSplit); 'achieved' counts every product ONCE (SURVEY 8d), mma_TFLOPs is the bf16 "
+            "tensor work actually issued; the exact fp32 re-scoring + proof kernel runs after it")
+        line["roofline"]["mma_TFLOPs"] = 3.0 * achieved
+        line["roofline"]["mma_frac_of_peak"] = 3.0 * achieved / peaks["tflops"]
+        line["config"]["unverified_queries_rerun_on_ffma"] = S._search_exact_tensor.last_unverified
+        line["gpu_launches"] = args.steps * (4 + 3)            # + split of the queries, re-scoring, (norms)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             _, _, info = cpu_reference_numbers(nq, ng, d, k)
