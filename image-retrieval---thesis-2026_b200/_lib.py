@@ -30,6 +30,8 @@ SIGNATURES = {
     "knn_search": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
     "knn_search_workspace": (_sz, [_i64, _i64, _i, _i, _i]),
     "knn_split_bf16x3": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "knn_max_sqnorm": (_i, [_p, _i64, _p, _p]),
+    "knn_filter_error_bound": (_i, [_p, _i64, _p, _i, _i, _p, _p]),
     "knn_rescore_exact": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i64, _i64, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "knn_profile_enable": (_i, [_i]),
     "knn_profile_count": (_i, []),

@@ -271,6 +271,31 @@ rescore_exact_stream_kernel(const float* __restrict__ q, const float* __restrict
   emit_and_verify<kL2>(keys, npad, nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified);
 }
 
+// ---------------------------------------------------------------------------------------------- error bound
+// max of non-negative floats (squared norms): their bit patterns order like unsigned integers.  NaN-free input assumed.
+__global__ void __launch_bounds__(256) max_nonneg_kernel(const float* __restrict__ x, int64_t n, uint32_t* out) {
+  uint32_t m = 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fmaxf(__ldg(x + i), 0.0f)));
+  m = __reduce_max_sync(0xFFFFFFFFu, m);
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// eps[q] >= |filter value - exact-mode value| for every gallery row; see knn_filter_error_bound in b200knn.h.
+__global__ void __launch_bounds__(256) error_bound_kernel(const float* __restrict__ qsq, const float* __restrict__ gmax,
+                                                          int64_t nq, int d, int l2, float* __restrict__ eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int dpad = (d + 7) & ~7;
+  const double steps = (double)(3 * dpad / 16 + 1);
+  const double u = 3.02 * 3.814697265625e-06 /*2^-18*/ + steps * 4.76837158203125e-07 /*2^-21*/ * 1.012 +
+                   (double)d * 5.9604644775390625e-08 /*2^-24*/ * 1.001;
+  const double qn2 = (double)__ldg(qsq + i), gn2 = (double)__ldg(gmax);
+  double e = u * sqrt(qn2 * gn2) * (1.0 + 1e-6) + 1e-30;
+  if (l2) e = 2.0 * e + 4.76837158203125e-07 * 1.01 * (qn2 + gn2);
+  eps[i] = __double2float_ru(e);
+}
+
 }  // namespace
 }  // namespace knn
 
@@ -334,6 +359,31 @@ extern "C" int knn_rescore_exact(const float* q, const float* g, const float* q_
     kern<<<(unsigned)nq, kRescoreThreads, smem, s>>>(q, g, q_sqnorm, g_sqnorm, ng, d, self_mode, self_local, index_base,
                                                     cand_val, cand_idx, kc, k, npad, eps, out_val, out_idx, unverified);
   }
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+extern "C" int knn_max_sqnorm(const float* sqnorm, int64_t n, float* out, void* stream) {
+  KNN_REQUIRE(n >= 0 && out, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  KNN_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(sqnorm, "null pointer");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  max_nonneg_kernel<<<blocks, 256, 0, s>>>(sqnorm, n, reinterpret_cast<uint32_t*>(out));
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
+extern "C" int knn_filter_error_bound(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max, int d, int metric,
+                                      float* eps, void* stream) {
+  KNN_REQUIRE(nq >= 0 && d >= 1, "bad shape nq=%lld d=%d", (long long)nq, d);
+  KNN_REQUIRE(metric == KNN_COSINE || metric == KNN_IP || metric == KNN_L2, "bad metric %d", metric);
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(q_sqnorm && g_sqnorm_max && eps, "null pointer");
+  error_bound_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_sqnorm, g_sqnorm_max, nq, d,
+                                                                                     metric == KNN_L2 ? 1 : 0, eps);
   KNN_CHECK_CUDA(cudaGetLastError());
   return KNN_OK;
 }

@@ -216,6 +216,25 @@ def exact_engine(nq: int, ng: int, d: int, k: int) -> str:
     return "tensor" if 2.0 * nq * ng * d >= _EXACT_MIN_FLOP else "ffma"
 
 
+def rerun_ranges(bad_rows, nq: int, block: int = 128):
+    """Query ranges to re-run through the FFMA engine for the unproven rows `bad_rows`: whole 128-row blocks merged
+    into contiguous runs (a contiguous range keeps the ``query_offset + i`` self-row arithmetic; re-running proven
+    rows is harmless -- both engines return the same bits); everything at once when half the blocks are affected."""
+    if not bad_rows:
+        return []
+    blocks = sorted({int(r) // block for r in bad_rows})
+    if 2 * len(blocks) >= (nq + block - 1) // block:
+        return [(0, nq)]
+    runs, s0, prev = [], blocks[0], blocks[0]
+    for b in blocks[1:]:
+        if b != prev + 1:
+            runs.append((s0 * block, min(nq, (prev + 1) * block)))
+            s0 = b
+        prev = b
+    runs.append((s0 * block, min(nq, (prev + 1) * block)))
+    return runs
+
+
 def split_bf16x3(x: torch.Tensor, role: str) -> torch.Tensor:
     """fp32 rows [n, d] -> bf16 [n, 3 * dpad]: ``[hi | lo | hi]`` for role "queries", ``[hi | hi | lo]`` for
     "gallery" (hi = bf16(x), lo = bf16(x - hi), dpad = d rounded up to 8)."""
@@ -241,25 +260,24 @@ class ExactFilterRows:
     @staticmethod
     def build(rows: torch.Tensor, sqnorm: Optional[torch.Tensor]) -> "ExactFilterRows":
         sq = sqnorm if sqnorm is not None else row_sqnorm(rows)
-        return ExactFilterRows(split_bf16x3(rows, "gallery"), sq, sq.max() if sq.numel() else sq.new_zeros(()))
+        mx = torch.empty((1,), dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            rc = L.load().knn_max_sqnorm(_ptr(sq), sq.numel(), _ptr(mx), _stream(rows))
+        L.check(rc, "knn_max_sqnorm")
+        return ExactFilterRows(split_bf16x3(rows, "gallery"), sq, mx)
 
 
 def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric: str) -> torch.Tensor:
-    """eps[q] >= |filter value - exact-mode value| for every gallery row (fp32 [Q], rounded up).
-
-    dot product: split (3.02 * 2^-18) + tensor-core accumulation (2^-21 of the magnitude sum per K=16 step --
-    assumption, checked by tests/test_gpu_exact_tensor.py against observed errors) + the exact fp32 chain's own
-    rounding (d * 2^-24), all times |q| * max|g| (Cauchy-Schwarz).  L2 filter value -(|q|^2+|g|^2-2q.g): twice
-    that plus the two fp32 roundings of the formula."""
-    dpad = (d + 7) // 8 * 8
-    steps = 3 * dpad // 16 + 1
-    u = 3.02 * 2.0 ** -18 + steps * 2.0 ** -21 * 1.012 + d * 2.0 ** -24 * 1.001
-    qn2 = qsq.double()
-    gn2 = max_gsq.double()
-    eps = u * torch.sqrt(qn2 * gn2) * (1.0 + 1e-6) + 1e-30
-    if metric == "l2":
-        eps = 2.0 * eps + 2.0 ** -21 * 1.01 * (qn2 + gn2)
-    return (eps * (1.0 + 2.0 ** -22)).float()
+    """eps[q] >= |filter value - exact-mode value| for every gallery row (fp32 [Q], rounded up): split error +
+    tensor-core accumulation + the exact fp32 chain's own rounding, times |q| * max|g| (``knn_filter_error_bound``,
+    formula in include/b200knn.h)."""
+    _require_cuda(qsq, max_gsq)
+    eps = torch.empty_like(qsq)
+    with torch.cuda.device(qsq.device):
+        rc = L.load().knn_filter_error_bound(_ptr(qsq), qsq.numel(), _ptr(max_gsq), int(d), _METRICS[metric],
+                                             _ptr(eps), _stream(qsq))
+    L.check(rc, "knn_filter_error_bound")
+    return eps
 
 
 def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base,
@@ -286,23 +304,11 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
     # queries whose candidate set could not be proven complete (ties / near-duplicates wider than the slack):
     # re-run their 128-row blocks through the FFMA engine (contiguous runs keep the self-row arithmetic)
     bad = torch.nonzero(flags).flatten()
-    if bad.numel():
-        blocks = torch.unique(bad // 128).tolist()
-        if 2 * len(blocks) >= (nq + 127) // 128:
-            runs = [(0, nq)]
-        else:
-            runs, s0, prev = [], blocks[0], blocks[0]
-            for b in blocks[1:]:
-                if b != prev + 1:
-                    runs.append((s0 * 128, min(nq, (prev + 1) * 128)))
-                    s0 = b
-                prev = b
-            runs.append((s0 * 128, min(nq, (prev + 1) * 128)))
-        for s, e in runs:
-            v, i = _search_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, k, metric, self_mode,
-                                    query_offset + s, index_base)
-            out_val[s:e] = v
-            out_idx[s:e] = i
+    for s, e in rerun_ranges(bad.tolist(), nq):
+        v, i = _search_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, k, metric, self_mode,
+                                query_offset + s, index_base)
+        out_val[s:e] = v
+        out_idx[s:e] = i
     _search_exact_tensor.last_unverified = int(bad.numel())
     return out_val, out_idx
 

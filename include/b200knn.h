@@ -108,6 +108,15 @@ KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, in
  *   value (the dot product; -(|q|^2 + |g|^2 - 2 q.g) for KNN_L2) for every gallery row.  Queries flagged 1 must be
  *   re-run through knn_search(KNN_F32). */
 KNN_API int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* out, void* stream);
+/* The error bound knn_rescore_exact needs.  knn_max_sqnorm: out[0] = max of the gallery's squared row norms (device
+ * scalar).  knn_filter_error_bound: eps[q] (rounded up) = u * |q| * max|g|  with
+ *   u = 3.02 * 2^-18 (dropped terms of the split) + (3 * dpad / 16 + 1) * 2^-21 * 1.012 (tensor-core accumulation:
+ *   at most 2^-21 of the magnitude sum per K = 16 MMA step -- the one hardware assumption, checked against observed
+ *   errors by tests/test_gpu_exact_tensor.py) + d * 2^-24 * 1.001 (rounding of the exact fp32 chain itself);
+ * KNN_L2: 2 * that + 2^-21 * 1.01 * (|q|^2 + max|g|^2) for the two fp32 roundings of -(|q|^2 + |g|^2 - 2 q.g). */
+KNN_API int knn_max_sqnorm(const float* sqnorm, int64_t n, float* out, void* stream);
+KNN_API int knn_filter_error_bound(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max, int d, int metric,
+                           float* eps, void* stream);
 KNN_API int knn_rescore_exact(const float* q, const float* g, const float* q_sqnorm, const float* g_sqnorm,
                       int64_t nq, int64_t ng, int d, int metric, int self_mode, int64_t self_offset,
                       int64_t index_base, const float* cand_val, const int64_t* cand_idx, int kc, int k,

@@ -68,3 +68,20 @@ def test_cpu_tensors_are_rejected_loudly():
         b200knn.search(torch.zeros(2, 8), torch.zeros(4, 8), 1)
     with pytest.raises(b200knn.KnnError):
         b200knn.normalize(torch.zeros(2, 8))
+
+
+def test_exact_engine_host_logic():
+    """Host-side decisions of the tensor-core exact engine (no device needed)."""
+    import importlib
+
+    S = importlib.import_module("b200knn.search")
+    assert [S._filter_k(k) for k in (1, 10, 24, 25, 50, 100, 113, 128, 228, 229)] == [32, 32, 32, 64, 64, 128, 128, 256,
+                                                                                      256, 512]
+    assert S.exact_engine(25_000, 112_000, 1024, 50) == "tensor"      # BASELINE config 3
+    assert S.exact_engine(400, 400, 1024, 10) == "ffma"                # config 1: sub-GFLOP, launch bound
+    assert S.exact_engine(600, 2000, 256, 10) == "ffma"                # config 2
+    assert S.exact_engine(25_000, 112_000, 1024, 250) == "ffma"        # no room for slack candidates below 256
+    assert S.rerun_ranges([], 1000) == []
+    assert S.rerun_ranges([5, 130, 131, 600], 2000) == [(0, 256), (512, 640)]
+    assert S.rerun_ranges([1999], 2000) == [(1920, 2000)]
+    assert S.rerun_ranges(list(range(0, 2000, 128)), 2000) == [(0, 2000)]

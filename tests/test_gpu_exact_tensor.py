@@ -132,7 +132,7 @@ def test_observed_filter_error_is_far_inside_the_bound(knn):
                                     "ip", "keep", 0, 0)
         exact = knn.scores_dense(qd, gd, "ip")                         # the fp32 chain of the exact mode
         ev = torch.gather(exact, 1, ai)
-        eps = S.filter_error_bound(S.row_sqnorm(qd), S.row_sqnorm(gd).max(), d, "ip")
+        eps = S.filter_error_bound(S.row_sqnorm(qd), S.ExactFilterRows.build(gd, None).max_sqnorm, d, "ip")
         ratio = ((av - ev).abs() / eps[:, None]).max().item()
         assert ratio < 0.25, (d, positive, ratio)
 

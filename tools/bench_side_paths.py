@@ -50,28 +50,50 @@ def main():
         return pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
 
     # ---- exact fp32 ------------------------------------------------------------------------------------------
-    for name, nq, ng, d, k, metric in (("c1", 400, 400, 1024, 10, "cosine"), ("c2", 600, 2000, 256, 10, "l2"),
-                                       ("c3", 25000, 112000, 1024, 50, "cosine")):
+    import importlib
+
+    S = importlib.import_module("b200knn.search")
+    for name, nq, ng, d, k, metric, engine in (("c1", 400, 400, 1024, 10, "cosine", "ffma"),
+                                               ("c2", 600, 2000, 256, 10, "l2", "ffma"),
+                                               ("c3", 25000, 112000, 1024, 50, "cosine", "ffma"),
+                                               ("c3", 25000, 112000, 1024, 50, "cosine", "tensor"),
+                                               ("c3", 25000, 112000, 1024, 50, "l2", "tensor")):
         g = b200knn.normalize(torch.randn((ng, d), generator=gen, device=dev))
         q = g if name == "c1" else b200knn.normalize(torch.randn((nq, d), generator=gen, device=dev))
+        os.environ["KNN_EXACT_ENGINE"] = engine
+        assert S.exact_engine(nq, ng, d, k) == engine
+        index = b200knn.FlatIndex(d, metric, "fp32").adopt(g)     # the tensor engine keeps its split rows here
         mhz = []
 
         def step():
-            out = b200knn.search(q, g, k, metric, exclude_self=(name == "c1"))
+            out = index.search(q, k, exclude_self=(name == "c1"))
             mhz.append(clock())
             return out
 
         ms = timed(step, args.steps if name == "c3" else 50)
         flops = 2.0 * nq * ng * d
         clk = sorted(mhz)[len(mhz) // 2]
-        peak = sms * 128 * 2 * clk * 1e6 / 1e12          # FFMA lanes x 2 FLOP x observed SM clock
-        line = {"path": "exact-fp32", "workload": f"{name}: {nq} x {ng} x {d} fp32, top-{k}, {metric}",
-                "ms_per_call": ms, "queries_per_s": nq / (ms / 1e3), "kernel": "search_f32_kernel",
-                "roofline": {"bound": "fp32 FFMA", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                             "frac": flops / (ms / 1e3) / 1e12 / peak,
-                             "peak_source": f"{sms} SMs x 128 lanes x 2 FLOP x {clk} MHz observed (nominal; no measured fp32 peak)"},
-                "note": "whole call (normalised fp32 inputs resident): distance+select kernel + unit merge"}
+        if engine == "ffma":
+            peak = sms * 128 * 2 * clk * 1e6 / 1e12          # FFMA lanes x 2 FLOP x observed SM clock
+            roof = {"bound": "fp32 FFMA", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / (ms / 1e3) / 1e12 / peak,
+                    "peak_source": f"{sms} SMs x 128 lanes x 2 FLOP x {clk} MHz observed (nominal; no measured fp32 peak)"}
+            kern, note = "search_f32_kernel", "whole call (normalised fp32 rows resident): distance+select kernel + unit merge"
+        else:
+            peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                               "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / (ms / 1e3) / 1e12 / peak, "mma_TFLOPs": 3 * flops / (ms / 1e3) / 1e12,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained; every product counted once, the filter "
+                                   "issues 3 bf16 MMAs per product"}
+            kern = "search_bf16_pair_kernel<kSplit> + rescore_exact_stream_kernel"
+            note = ("whole call (normalised fp32 rows + their bf16x3 split resident): split of the queries, filter, "
+                    f"exact re-scoring + proof; {S._search_exact_tensor.last_unverified} queries re-run on FFMA")
+        line = {"path": f"exact-fp32/{engine}", "workload": f"{name}: {nq} x {ng} x {d} fp32, top-{k}, {metric}",
+                "ms_per_call": ms, "queries_per_s": nq / (ms / 1e3), "kernel": kern, "sm_mhz": clk, "roofline": roof,
+                "note": note}
         print(json.dumps(line), flush=True)
+    os.environ.pop("KNN_EXACT_ENGINE", None)
 
     # ---- hamming ---------------------------------------------------------------------------------------------
     nq, ng, bits, k = 1024, 10_000_000, 64, 100
