@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--gallery-rows", type=int, default=0, help="override the gallery size (debug only)")
     ap.add_argument("--queries", type=int, default=0, help="override the query batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
+                    help="N > 1: candidate exchange -- merge kernel reading the peers' symmetric-memory buffers over "
+                         "NVLink (falls back to the all-gather if symmetric memory is unavailable), or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -209,7 +212,22 @@ def main():
         rows[s:e] = b200knn.normalize(x, out_dtype=store_dtype)
     del x
     index = b200knn.FlatIndex(d, "cosine", precision, normalize=True, index_base=start, device=dev).adopt(rows)
-    sharded = ShardedFlatIndex(index)
+    exchange = args.exchange
+    if world > 1 and exchange == "peer":
+        try:  # collective: every rank succeeds or every rank falls back (the probe result is all-reduced)
+            from b200knn.sharded import PeerExchange
+
+            probe = PeerExchange(None, dev)
+            probe.slot(8, 8)
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # noqa: BLE001 - any failure means "no symmetric memory here"
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({exc!r}); using the all-gather exchange", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            exchange = "allgather"
+    sharded = ShardedFlatIndex(index, exchange=exchange)
 
     # ---- queries: perturbed gallery rows of rank 0 (so true neighbours exist), replicated on every rank ----
     gen.manual_seed(99)
@@ -217,27 +235,14 @@ def main():
     q_host = qsrc.cpu().pin_memory()                      # the user's host buffer (fp32)
     q_dev = b200knn.normalize(qsrc, out_dtype=store_dtype)
     index_prepared = b200knn.FlatIndex(d, "cosine", precision, normalize=False, index_base=start, device=dev).adopt(rows)
+    sharded_prepared = ShardedFlatIndex(index_prepared, exchange=exchange)
     out_val_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     out_idx_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
 
     def step_resident():
-        # queries already normalised/bf16 in HBM; FlatIndex.search with normalize=True would renormalise, so call
-        # the prepared path directly (what FlatIndex.search does after _prepare)
-        if exact:  # FlatIndex.search on already-normalised rows: split filter + exact re-scoring + proof
-            v, i = index_prepared.search(q_dev, k)
-        else:
-            from b200knn.search import _search_prepared
-
-            v, i = _search_prepared(q_dev, None, index.rows, None, k, "cosine", "keep", 0, index.index_base)
-        if world > 1:
-            from b200knn.sharded import pack_candidates, unpack_candidates
-
-            payload = pack_candidates(v, i)
-            gathered = torch.empty((world * payload.numel(),), dtype=payload.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, payload)
-            pv, pi = unpack_candidates(gathered, world, nq, k)
-            v, i = b200knn.merge_topk(pv, pi, "cosine")
-        return v, i
+        # queries already normalised / cast in HBM: the index over the same rows with normalize=False skips the
+        # normalisation FlatIndex.search would otherwise repeat; N > 1 adds the candidate exchange + shard merge
+        return sharded_prepared.search(q_dev, k)
 
     def step_e2e():
         qd = q_host.to(dev, non_blocking=True)
@@ -312,7 +317,8 @@ def main():
         "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: {nq} queries x {ng} gallery x {d}-d {precision}, top-{k}, cosine",
-            "gallery_rows_per_gpu": count, "sharding": f"rows/{world}", "l2_flush": "inputs larger than L2 "
+            "gallery_rows_per_gpu": count, "sharding": f"rows/{world}",
+            "exchange": "none" if world == 1 else exchange, "l2_flush": "inputs larger than L2 "
             f"({count * d * 2 / 1e9:.1f} GB gallery shard streamed per step)",
         },
         "roofline": ({
@@ -348,6 +354,14 @@ def main():
         line["roofline"]["mma_frac_of_peak"] = 3.0 * achieved / peaks["tflops"]
         line["config"]["unverified_queries_rerun_on_ffma"] = S._search_exact_tensor.last_unverified
         line["gpu_launches"] = args.steps * (4 + 3)            # + split of the queries, re-scoring, (norms)
+    if world > 1:  # per-rank view of the same timed region: which rank the max-over-ranks step time waits for
+        mine = torch.tensor([dist_ms, seed_ms, merge_ms, float(clocks.summary()["sm_mhz"] or 0)], device=dev)
+        allr = torch.empty((world, 4), device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        line["per_rank"] = {"kernel_ms": [round(x, 3) for x in allr[:, 0].tolist()],
+                            "seeding_ms": [round(x, 3) for x in allr[:, 1].tolist()],
+                            "unit_merge_ms": [round(x, 3) for x in allr[:, 2].tolist()],
+                            "sm_mhz": [int(x) for x in allr[:, 3].tolist()]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             _, _, info = cpu_reference_numbers(nq, ng, d, k)

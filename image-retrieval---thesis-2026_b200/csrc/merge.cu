@@ -235,20 +235,29 @@ __device__ __forceinline__ bool precedes(const Cand& x, int px, const Cand& a, i
   return px < pa;
 }
 
-__global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict__ vals,
-                                                        const int64_t* __restrict__ idx, int parts, int64_t nq,
-                                                        int k, int l2, float* __restrict__ out_val,
+// Part p's candidates live at idx[p] / val[p] ([nq, k] each): slices of one dense or all-gathered buffer, or -- the
+// fused exchange of the row-sharded search -- the symmetric-memory buffers of the PEER GPUs, read straight over
+// NVLink by this kernel (no all-gather, no staging copy: the transfer overlaps the merge of other queries).
+constexpr int kMaxMergeParts = 16;
+struct MergeParts {
+  const int64_t* idx[kMaxMergeParts];
+  const float* val[kMaxMergeParts];
+};
+
+__global__ void __launch_bounds__(256) merge_topk_kernel(MergeParts mp, int parts, int64_t nq, int k, int l2,
+                                                        float* __restrict__ out_val,
                                                         int64_t* __restrict__ out_idx) {
   extern __shared__ __align__(16) uint8_t sm[];
   int64_t* sid = reinterpret_cast<int64_t*>(sm);                 // [parts*k]
   uint32_t* so = reinterpret_cast<uint32_t*>(sid + parts * k);   // [parts*k]
+  float* sv = reinterpret_cast<float*>(so + parts * k);          // [parts*k]
   const int64_t r = blockIdx.x;
   const int n = parts * k;
   for (int c = threadIdx.x; c < n; c += blockDim.x) {
     const int pp = c / k, j = c % k;
-    const int64_t off = ((int64_t)pp * nq + r) * k + j;
-    const int64_t id = idx[off];
-    const float v = vals[off];
+    const int64_t id = __ldcg(mp.idx[pp] + r * k + j);           // .cg: peer / freshly gathered data, never via L1
+    const float v = __ldcg(mp.val[pp] + r * k + j);
+    sv[c] = v;
     if (id < 0) { so[c] = 0u; sid[c] = INT64_MAX; }
     else { so[c] = f2ord((l2 ? -v : v) + 0.0f); sid[c] = id; }
   }
@@ -268,11 +277,21 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const float* __restrict
       rank += lo;
     }
     if (rank < k) {
-      const int64_t off = ((int64_t)pa * nq + r) * k + j;
-      out_val[r * k + rank] = vals[off];
-      out_idx[r * k + rank] = idx[off];
+      out_val[r * k + rank] = sv[c];
+      out_idx[r * k + rank] = sid[c] == INT64_MAX ? -1 : sid[c];
     }
   }
+}
+
+static int launch_merge_parts(const MergeParts& mp, int parts, int64_t nq, int k, int metric, float* out_val,
+                              int64_t* out_idx, cudaStream_t stream) {
+  const size_t smem = (size_t)parts * k * 16;
+  KNN_REQUIRE(smem <= 200 * 1024, "knn_merge_topk: parts*k=%d too large (max %d)", parts * k, 200 * 1024 / 16);
+  if (nq == 0) return KNN_OK;
+  KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<(unsigned)nq, 256, smem, stream>>>(mp, parts, nq, k, metric == KNN_L2 ? 1 : 0, out_val, out_idx);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,16 +487,28 @@ using namespace knn;
 extern "C" int knn_merge_topk(const float* vals, const int64_t* idx, int parts, int64_t nq, int k, int metric,
                               float* out_val, int64_t* out_idx, void* stream) {
   KNN_REQUIRE(vals && idx && out_val && out_idx, "knn_merge_topk: null pointer");
-  KNN_REQUIRE(parts >= 1 && k >= 1 && nq >= 0, "knn_merge_topk: bad sizes parts=%d k=%d nq=%lld", parts, k,
-              (long long)nq);
-  const size_t smem = (size_t)parts * k * 12;
-  KNN_REQUIRE(smem <= 200 * 1024, "knn_merge_topk: parts*k=%d too large (max %d)", parts * k, 200 * 1024 / 12);
-  if (nq == 0) return KNN_OK;
-  KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(vals, idx, parts, nq, k,
-                                                                     metric == KNN_L2 ? 1 : 0, out_val, out_idx);
-  KNN_CHECK_CUDA(cudaGetLastError());
-  return KNN_OK;
+  KNN_REQUIRE(parts >= 1 && parts <= kMaxMergeParts && k >= 1 && nq >= 0,
+              "knn_merge_topk: bad sizes parts=%d (max %d) k=%d nq=%lld", parts, kMaxMergeParts, k, (long long)nq);
+  MergeParts mp;
+  for (int p = 0; p < parts; ++p) {
+    mp.idx[p] = idx + (int64_t)p * nq * k;
+    mp.val[p] = vals + (int64_t)p * nq * k;
+  }
+  return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream);
+}
+
+extern "C" int knn_merge_topk_parts(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
+                                    int64_t nq, int k, int metric, float* out_val, int64_t* out_idx, void* stream) {
+  KNN_REQUIRE(val_parts_host && idx_parts_host && out_val && out_idx, "knn_merge_topk_parts: null pointer");
+  KNN_REQUIRE(parts >= 1 && parts <= kMaxMergeParts && k >= 1 && nq >= 0,
+              "knn_merge_topk_parts: bad sizes parts=%d (max %d) k=%d nq=%lld", parts, kMaxMergeParts, k, (long long)nq);
+  MergeParts mp;
+  for (int p = 0; p < parts; ++p) {
+    KNN_REQUIRE(val_parts_host[p] && idx_parts_host[p], "knn_merge_topk_parts: null part %d", p);
+    mp.idx[p] = idx_parts_host[p];
+    mp.val[p] = val_parts_host[p];
+  }
+  return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream);
 }
 
 static int64_t rank_npad(int64_t ng) {

@@ -167,10 +167,11 @@ class FlatIndex:
         return self
 
     def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
-               query_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+               query_offset: int = 0, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """``scores, neighbors = index.search(xq, k)`` (ATH.py:410) -> (distances [Q,k] fp32, indices [Q,k] int64).
 
         query_offset: global gallery row of query 0 (self-retrieval over a chunk of the gallery).
+        out: optional (float32 [Q,k], int64 [Q,k]) tensors to write the result into (exchange buffers).
         """
         if self.rows is None:
             raise L.KnnError("FlatIndex is empty")
@@ -182,9 +183,9 @@ class FlatIndex:
             if self._filter is None:
                 self._filter = ExactFilterRows.build(self.rows, self.sqnorm)
             return _search_exact_tensor(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
-                                        self.index_base, self._filter)
+                                        self.index_base, self._filter, out=out)
         return _search_prepared(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
-                                self.index_base)
+                                self.index_base, out=out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -281,7 +282,7 @@ def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric:
 
 
 def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base,
-                         filt: Optional[ExactFilterRows] = None):
+                         filt: Optional[ExactFilterRows] = None, out=None):
     """precision="fp32" through the tensor cores; same contract and same bits as _search_prepared on fp32 rows."""
     nq, d = q.shape
     ng = g.shape[0]
@@ -293,8 +294,7 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
     eps = filter_error_bound(q_sq, filt.max_sqnorm, d, metric)
     cand_val, cand_idx = _search_prepared(split_bf16x3(q, "queries"), qsq, filt.split, gsq if metric == "l2" else None,
                                           kc, metric, self_mode, query_offset, index_base, split_rows=True)
-    out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_val, out_idx = _out_buffers(out, nq, k, dev)
     flags = torch.empty((nq,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = L.load().knn_rescore_exact(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _METRICS[metric],
@@ -316,7 +316,19 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
 _search_exact_tensor.last_unverified = 0
 
 
-def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base, split_rows=False):
+def _out_buffers(out, nq, k, dev):
+    """(distances, indices) to write into: fresh tensors, or the caller's (a send / symmetric-memory buffer)."""
+    if out is None:
+        return (torch.empty((nq, k), dtype=torch.float32, device=dev),
+                torch.empty((nq, k), dtype=torch.int64, device=dev))
+    ov, oi = out
+    if (ov.shape != (nq, k) or oi.shape != (nq, k) or ov.dtype != torch.float32 or oi.dtype != torch.int64
+            or not ov.is_contiguous() or not oi.is_contiguous() or ov.device != dev or oi.device != dev):
+        raise ValueError("out must be contiguous (float32 [Q,k], int64 [Q,k]) tensors on the search device")
+    return ov, oi
+
+
+def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base, split_rows=False, out=None):
     """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3: same scores, each part loaded once per tile)."""
     nq, d = q.shape
     ng = g.shape[0]
@@ -325,8 +337,7 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     if k < 1:
         raise ValueError("k must be >= 1")
     dev = q.device
-    out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_val, out_idx = _out_buffers(out, nq, k, dev)
     if nq == 0:
         return out_val, out_idx
     lib = L.load()
@@ -498,6 +509,23 @@ def rank_rows(scores: torch.Tensor, largest_first: bool = True) -> torch.Tensor:
                                _stream(scores))
     L.check(rc, "knn_rank_rows")
     return ranks
+
+
+def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k-way merge of separately placed per-shard lists given as raw DEVICE addresses (``knn_merge_topk_parts``):
+    slices of an all-gathered buffer, or the peers' symmetric-memory buffers (fused exchange + merge)."""
+    import ctypes
+
+    parts = len(val_ptrs)
+    out_val = torch.empty((nq, k), dtype=torch.float32, device=device)
+    out_idx = torch.empty((nq, k), dtype=torch.int64, device=device)
+    vp = (ctypes.c_void_p * parts)(*[int(p) for p in val_ptrs])
+    ip = (ctypes.c_void_p * parts)(*[int(p) for p in idx_ptrs])
+    with torch.cuda.device(device):
+        rc = L.load().knn_merge_topk_parts(vp, ip, parts, nq, k, _METRICS[metric], _ptr(out_val), _ptr(out_idx),
+                                           torch.cuda.current_stream(device).cuda_stream)
+    L.check(rc, "knn_merge_topk_parts")
+    return out_val, out_idx
 
 
 def merge_topk(vals: torch.Tensor, idx: torch.Tensor, metric: str = "cosine") -> Tuple[torch.Tensor, torch.Tensor]:

@@ -43,18 +43,75 @@ def unpack_candidates(buf: torch.Tensor, parts: int, nq: int, k: int) -> Tuple[t
     return vals, idx
 
 
-class ShardedFlatIndex:
-    """One process per GPU; this rank's shard is a :class:`FlatIndex` whose ``index_base`` is its first global row."""
+def candidate_views(buf: torch.Tensor, nq: int, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The (distances fp32 [Q,k], indices int64 [Q,k]) views of one packed candidate buffer of 3*Q*k int32 words
+    (indices first: 8-byte aligned) -- the search writes its result straight into the exchange buffer."""
+    n = nq * k
+    return buf[2 * n:3 * n].view(torch.float32).view(nq, k), buf[:2 * n].view(torch.int64).view(nq, k)
 
-    def __init__(self, local: FlatIndex, group: Optional[dist.ProcessGroup] = None):
+
+class PeerExchange:
+    """Candidate exchange over NVLink peer memory instead of an all-gather: every rank's search writes its ``[Q,k]``
+    candidates into ITS symmetric-memory buffer; after one device-side barrier every rank's merge kernel
+    (``knn_merge_topk_parts``) reads all W buffers directly through the peer mappings.  Two alternating slots make
+    ONE barrier per search sufficient: a slot is rewritten two searches later, i.e. after the next search's barrier,
+    which a rank's stream reaches only behind its own merge of this slot -- so every peer has finished reading it."""
+
+    def __init__(self, group, device: torch.device):
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = device
+        self.capacity = 0        # int32 words per slot
+        self.buf = None
+        self.hdl = None
+        self.turn = 0
+
+    def _ensure(self, words: int) -> None:
+        if words <= self.capacity:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+
+        # the capacity must be identical on every rank: it only depends on (Q, k), which are
+        cap = max(words, 1 << 16)
+        self.buf = symm_mem.empty((2 * cap,), dtype=torch.int32, device=self.device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.capacity = cap
+        self.turn = 0
+
+    def slot(self, nq: int, k: int) -> torch.Tensor:
+        """This rank's buffer for the next search (3*Q*k words of the current slot)."""
+        words = 3 * nq * k
+        self._ensure(words + (words & 1))
+        self.turn ^= 1
+        return self.buf[self.turn * self.capacity: self.turn * self.capacity + words]
+
+    def peer_pointers(self, nq: int, k: int):
+        """Device-side barrier (orders the merge after every peer's search), then the W (val, idx) addresses."""
+        self.hdl.barrier(channel=self.turn)
+        n = nq * k
+        base = [int(p) + self.turn * self.capacity * 4 for p in self.hdl.buffer_ptrs]
+        return [b + 8 * n for b in base], base
+
+
+class ShardedFlatIndex:
+    """One process per GPU; this rank's shard is a :class:`FlatIndex` whose ``index_base`` is its first global row.
+
+    exchange: "allgather" = one NCCL all-gather of the packed candidates, merged in place (no unpacking copy);
+    "peer" = symmetric-memory buffers read over NVLink by the merge kernel itself (:class:`PeerExchange`)."""
+
+    def __init__(self, local: FlatIndex, group: Optional[dist.ProcessGroup] = None, exchange: str = "allgather"):
+        if exchange not in ("allgather", "peer"):
+            raise ValueError("exchange must be 'allgather' or 'peer'")
         self.local = local
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = exchange
+        self._peer: Optional[PeerExchange] = None
 
     @classmethod
     def from_full(cls, gallery: torch.Tensor, metric: str = "cosine", precision: str = "fp32", *,
-                  normalize: bool = False, group: Optional[dist.ProcessGroup] = None) -> "ShardedFlatIndex":
+                  normalize: bool = False, group: Optional[dist.ProcessGroup] = None,
+                  exchange: str = "allgather") -> "ShardedFlatIndex":
         """Every rank passes the same full gallery tensor (or at least its own rows); keeps only its range."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -62,14 +119,19 @@ class ShardedFlatIndex:
         idx = FlatIndex(gallery.shape[1], metric, precision, normalize=normalize, index_base=start,
                         device=gallery.device)
         idx.add(gallery[start:start + count])
-        return cls(idx, group)
+        return cls(idx, group, exchange)
 
     # --- the two device steps; tests replace them to exercise the exchange logic without a GPU ---------
-    def _search_local(self, queries, k, self_mode, query_offset):
-        return self.local.search(queries, k, self_mode=self_mode, query_offset=query_offset)
+    def _search_local(self, queries, k, self_mode, query_offset, out=None):
+        return self.local.search(queries, k, self_mode=self_mode, query_offset=query_offset, out=out)
 
-    def _merge(self, vals, idx):
-        return merge_topk(vals, idx, self.local.metric)
+    def _merge_parts(self, bufs, nq, k):
+        """bufs: one packed candidate buffer (3*Q*k int32 words) per shard, in rank order."""
+        from .search import merge_topk_parts
+
+        n = nq * k
+        base = [b.data_ptr() for b in bufs]
+        return merge_topk_parts([p + 8 * n for p in base], base, nq, k, self.local.metric, bufs[0].device)
 
     def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
                query_offset: int = 0, broadcast_queries: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -77,12 +139,22 @@ class ShardedFlatIndex:
         if broadcast_queries and self.world_size > 1:
             dist.broadcast(queries, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
         mode = self_mode or ("exclude" if exclude_self else "keep")
-        vals, idx = self._search_local(queries, k, mode, query_offset)
         if self.world_size == 1:
-            return vals, idx
-        nq = vals.shape[0]
-        payload = pack_candidates(vals, idx)
-        gathered = torch.empty((self.world_size * payload.numel(),), dtype=payload.dtype, device=payload.device)
-        dist.all_gather_into_tensor(gathered, payload, group=self.group)
-        pv, pi = unpack_candidates(gathered, self.world_size, nq, k)
-        return self._merge(pv, pi)
+            return self._search_local(queries, k, mode, query_offset)
+        nq = queries.shape[0]
+        words = 3 * nq * k
+        if self.exchange == "peer":
+            if self._peer is None:
+                self._peer = PeerExchange(self.group, self.local.device)
+            send = self._peer.slot(nq, k)
+            self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k))
+            from .search import merge_topk_parts
+
+            val_ptrs, idx_ptrs = self._peer.peer_pointers(nq, k)
+            return merge_topk_parts(val_ptrs, idx_ptrs, nq, k, self.local.metric, self.local.device)
+        # the search writes straight into the send buffer; the gathered buffer is merged where it lies
+        send = torch.empty((words + (words & 1),), dtype=torch.int32, device=queries.device)
+        self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k))
+        gathered = torch.empty((self.world_size * send.numel(),), dtype=torch.int32, device=queries.device)
+        dist.all_gather_into_tensor(gathered, send, group=self.group)
+        return self._merge_parts(list(gathered.view(self.world_size, send.numel())), nq, k)

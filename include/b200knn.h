@@ -191,6 +191,13 @@ KNN_API size_t knn_rank_rows_workspace(int64_t nq, int64_t ng);
  * vals [parts,nq,k], idx [parts,nq,k] (global indices, -1 = empty) -> out [nq,k]; order as knn_search. */
 KNN_API int knn_merge_topk(const float* vals, const int64_t* idx, int parts, int64_t nq, int k, int metric,
                    float* out_val, int64_t* out_idx, void* stream);
+/* The same merge over `parts` (<= 16) separately placed lists: val_parts_host[p] / idx_parts_host[p] are DEVICE
+ * pointers to part p's [nq,k] candidates, the two arrays themselves live on the host.  The parts may be slices of an
+ * all-gathered buffer (no unpacking copy) or the symmetric-memory buffers of peer GPUs mapped into this process:
+ * then the kernel reads the other shards' candidates straight over NVLink -- exchange and merge in ONE kernel
+ * (the caller orders it after every peer's search with a device-side barrier). */
+KNN_API int knn_merge_topk_parts(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
+                         int64_t nq, int k, int metric, float* out_val, int64_t* out_idx, void* stream);
 
 /* Single-label relevance of retrieved lists: rel[i,j] = (glab[idx[i,j]] == qlab[i]), 0 for idx < 0.
  * Building block of retrieval_accuracy (test.py:38-54), compute_metrics (test_ath.py:90-172),

@@ -1,0 +1,61 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped on a one-GPU box): the row-sharded search over NCCL ranks with
+both candidate exchanges -- NCCL all-gather merged in place, and the merge kernel reading the peers' symmetric-memory
+buffers over NVLink -- must return, on every rank, exactly what one GPU returns over the whole gallery."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+
+    import b200knn
+    from b200knn.sharded import ShardedFlatIndex
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)                                   # same data on every rank
+    failures = []
+    for precision, nq, ng, d, k, metric in (("bf16", 300, 70_001, 128, 100, "cosine"), ("fp32", 64, 9_000, 96, 10, "l2"),
+                                            ("bf16", 1, 50_000, 768, 100, "cosine")):
+        g = b200knn.normalize(torch.randn((ng, d), generator=gen, device=dev))
+        q = b200knn.normalize(torch.randn((nq, d), generator=gen, device=dev))
+        g[17] = g[ng - 5]                                # a tie across the shard boundary
+        want_v, want_i = b200knn.search(q, g, k, metric, precision=precision)
+        for exchange in ("allgather", "peer"):
+            sh = ShardedFlatIndex.from_full(g, metric, precision, exchange=exchange)
+            for rep in range(3):                         # the peer exchange alternates between two slots
+                v, i = sh.search(q, k)
+                if not (torch.equal(i, want_i) and torch.equal(v, want_v)):
+                    failures.append((precision, exchange, rep, int((i != want_i).sum())))
+    torch.cuda.synchronize()
+    with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as fh:
+        fh.write(repr(failures))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_search_over_two_gpus_both_exchanges(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"r{r}.txt").read() == "[]"

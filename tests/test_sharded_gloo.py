@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from b200knn.sharded import pack_candidates, shard_rows, unpack_candidates
+from b200knn.sharded import candidate_views, pack_candidates, shard_rows, unpack_candidates
 
 
 def test_shard_rows_cover_everything():
@@ -30,6 +30,16 @@ def test_pack_unpack_roundtrip():
     assert torch.equal(v[0], vals) and torch.equal(i[1], idx + 1)
 
 
+def test_candidate_views_alias_the_packed_buffer():
+    vals = torch.randn(5, 7)
+    idx = torch.randint(0, 1 << 40, (5, 7))
+    buf = torch.zeros(3 * 35 + 1, dtype=torch.int32)
+    v, i = candidate_views(buf, 5, 7)
+    v.copy_(vals)
+    i.copy_(idx)
+    assert torch.equal(buf[:105], pack_candidates(vals, idx))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -41,7 +51,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import oracle
     from b200knn.search import FlatIndex
-    from b200knn.sharded import ShardedFlatIndex
+    from b200knn.sharded import ShardedFlatIndex, candidate_views
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -56,13 +66,18 @@ def _worker(rank, world, port, out_dir):
             self.local = FlatIndex.__new__(FlatIndex)
             self.local.metric = "cosine"
             self.group, self.world_size, self.rank = None, world, rank
+            self.exchange, self._peer = "allgather", None
 
-        def _search_local(self, queries, k, self_mode, query_offset):
+        def _search_local(self, queries, k, self_mode, query_offset, out=None):
             v, i = oracle.search(queries.numpy(), g[start:start + count], k, "cosine", self_mode, query_offset, start)
-            return torch.from_numpy(v), torch.from_numpy(i)
+            out[0].copy_(torch.from_numpy(v))      # straight into the exchange buffer, as the CUDA search does
+            out[1].copy_(torch.from_numpy(i))
+            return out
 
-        def _merge(self, vals, idx):
-            v, i = oracle.merge_topk(vals.numpy(), idx.numpy(), "cosine")
+        def _merge_parts(self, bufs, nq, k):
+            views = [candidate_views(b, nq, k) for b in bufs]
+            v, i = oracle.merge_topk(np.stack([v.numpy() for v, _ in views]), np.stack([i.numpy() for _, i in views]),
+                                     "cosine")
             return torch.from_numpy(v), torch.from_numpy(i)
 
     v, i = OracleShard().search(torch.from_numpy(q), 10, exclude_self=True)
