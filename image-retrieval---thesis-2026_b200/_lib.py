@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200knn.so")
+# KNN_LIB selects another build of the SAME library (the checked build of build.py --check); never a fallback
+LIB_PATH = os.environ.get("KNN_LIB") or os.path.join(_HERE, "libb200knn.so")
 
 # constants mirrored from include/b200knn.h
 KNN_F32, KNN_BF16, KNN_BF16X3 = 0, 1, 2

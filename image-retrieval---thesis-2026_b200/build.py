@@ -43,9 +43,20 @@ def needs_build() -> bool:
     return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+CHECK_LIB = os.path.join(HERE, "libb200knn_check.so")
+
+
+def build(force: bool = False, verbose: bool = False, check: bool = False) -> str:
+    """check=True builds libb200knn_check.so with -DKNN_BOUNDS_CHECK (device-side asserts on the candidate-list
+    invariants; select it with KNN_LIB=<path>): compute-sanitizer is not available on the GPU pool."""
+    if check:
+        return _build_variant(CHECK_LIB, os.path.join(CSRC, "build_check"), ["-DKNN_BOUNDS_CHECK"], verbose)
     if not force and not needs_build():
         return LIB
+    return _build_variant(LIB, BUILD, [], verbose, force)
+
+
+def _build_variant(LIB: str, BUILD: str, extra_flags, verbose: bool, force: bool = True) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
     hdr_mtime = max(
@@ -60,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         srcp = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(srcp), hdr_mtime):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", srcp, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -81,5 +92,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, check="--check" in sys.argv)
     print(path)

@@ -282,6 +282,13 @@ template <int E, int CH, bool kL2>
 __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int lane,
                                                        uint32_t* __restrict__ tau_global_row) {
   constexpr int L = 32 * E;
+#ifdef KNN_BOUNDS_CHECK  // checked build (build.py --check): the list invariants every append relies on
+  if (st.cnt < 0 || st.cnt > L) {
+    printf("b200knn check: candidate list overflow, cnt=%d capacity=%d (block %d,%d thread %d)\n", st.cnt, L,
+           blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+  }
+#endif
   unsigned need = __ballot_sync(kFullMask, st.cnt > L - CH);
   while (need) {
     const int r = __ffs(need) - 1;
@@ -315,6 +322,13 @@ __device__ __forceinline__ void warp_compact_if_needed(RowState& st, int k, int 
     }
     __syncwarp();
   }
+#ifdef KNN_BOUNDS_CHECK
+  if (st.cnt > L - CH) {
+    printf("b200knn check: list left with %d keys, more than capacity - chunk = %d (block %d,%d thread %d)\n", st.cnt,
+           L - CH, blockIdx.x, blockIdx.y, threadIdx.x);
+    __trap();
+  }
+#endif
 }
 
 // Pull the shared threshold (other CTAs working on the same query row may have tightened it).
