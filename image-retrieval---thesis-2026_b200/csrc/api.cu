@@ -213,19 +213,39 @@ using namespace knn;
 extern "C" int knn_version(void) { return KNN_ABI_VERSION; }
 extern "C" const char* knn_last_error(void) { return g_err; }
 
-// Workspace layout: tau_global [qblocks*128] u32 | counts [(splits+seed_splits)*groups][qblocks*128] i32 |
-//                   lists [(splits+seed_splits)*groups][qblocks*128][L] u64.  The extra splits are the scratch of
-//                   the threshold-seeding pre-pass.
+// Workspace layout: tau_global [qblocks*128] u32 | precount [qblocks*128] i32 (two-phase merge only) |
+//                   counts [(splits+seed_splits)*groups][qblocks*128] i32 |
+//                   lists [(splits+seed_splits)*groups][qblocks*128][L] u64 | pre [qblocks*128][pre_cap] u64 |
+//                   maxima [qblocks*128][seed_splits*groups] u32.  The extra splits are the scratch of the
+//                   threshold-seeding pre-pass; pre / precount / maxima exist for small query batches only.
+constexpr int kTwoPhaseMaxRows = 1024;  // up to 8 query blocks: one merge CTA per row cannot fill 148 SMs
+constexpr int kTwoPhaseMinLists = 16;
+constexpr int kPreCap = 2048;           // keys per row the pre-filter may gather (more: the merge re-reads the lists)
 struct WsLayout {
-  size_t tau_bytes, counts_bytes, lists_bytes;
+  size_t tau_bytes, precount_bytes, counts_bytes, lists_bytes, pre_bytes, maxima_bytes;
+  int pre_cap;        // 0: one-phase merge
+  bool seed_maxima;   // threshold seeding from list maxima
+  size_t total() const { return tau_bytes + precount_bytes + counts_bytes + lists_bytes + pre_bytes + maxima_bytes; }
 };
-static WsLayout ws_layout(const SearchGeom& g) {
+static WsLayout ws_layout(const SearchGeom& g, int k) {
   WsLayout w;
   const size_t rows = (size_t)g.qblocks * kRowsPerUnit;
   const size_t vsplits = (size_t)((g.splits > 0 ? g.splits : 1) + g.seed_splits) * g.groups;
   w.tau_bytes = align_up(rows * sizeof(uint32_t), 256);
   w.counts_bytes = align_up(vsplits * rows * sizeof(int32_t), 256);
-  w.lists_bytes = vsplits * rows * (size_t)g.L * sizeof(uint64_t);
+  w.lists_bytes = align_up(vsplits * rows * (size_t)g.L * sizeof(uint64_t), 256);
+  const bool two_phase = rows <= (size_t)kTwoPhaseMaxRows && g.splits * g.groups >= kTwoPhaseMinLists;
+  w.pre_cap = two_phase ? kPreCap : 0;
+  w.precount_bytes = two_phase ? align_up(rows * sizeof(int32_t), 256) : 0;
+  w.pre_bytes = two_phase ? rows * (size_t)kPreCap * sizeof(uint64_t) : 0;
+  // list maxima: threshold seeding (pre-pass lists) and tightening before the pre-filter (main lists) -- each needs
+  // at least 2k lists per row so that the k-th largest maximum is a useful bound
+  const int seed_lists = g.seed_splits * g.groups, main_lists = g.splits * g.groups;
+  w.seed_maxima = rows <= (size_t)kTwoPhaseMaxRows && seed_lists >= 2 * k && seed_lists <= 4096;
+  const bool main_maxima = two_phase && main_lists >= 2 * k && main_lists <= 4096;
+  const int mx = (w.seed_maxima ? seed_lists : 0) > (main_maxima ? main_lists : 0) ? seed_lists
+                                                                                    : (main_maxima ? main_lists : 0);
+  w.maxima_bytes = mx > 0 ? align_up(rows * (size_t)mx * sizeof(uint32_t), 256) : 0;
   return w;
 }
 
@@ -233,8 +253,7 @@ extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype,
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
   if (dtype == KNN_BF16X3) dtype = KNN_BF16;  // same geometry: the split rows are bf16 rows of 3 * dpad columns
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
-  const WsLayout w = ws_layout(g);
-  return w.tau_bytes + w.counts_bytes + w.lists_bytes;
+  return ws_layout(g, k).total();
 }
 
 static int check_common(const void* q, const void* g, const float* qs, const float* gs, int64_t nq, int64_t ng,
@@ -288,11 +307,19 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
   p.split3 = split3 ? 1 : 0;
-  const WsLayout wl = ws_layout(geo);
-  const size_t tau_bytes = wl.tau_bytes;
-  p.tau_global = reinterpret_cast<uint32_t*>(workspace);
-  p.counts = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes);
-  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes + wl.counts_bytes);
+  const WsLayout wl = ws_layout(geo, k);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+  p.tau_global = reinterpret_cast<uint32_t*>(wsb);
+  p.precount = wl.pre_cap ? reinterpret_cast<int32_t*>(wsb + wl.tau_bytes) : nullptr;
+  p.counts = reinterpret_cast<int32_t*>(wsb + wl.tau_bytes + wl.precount_bytes);
+  p.lists = reinterpret_cast<uint64_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes);
+  p.pre = wl.pre_cap ? reinterpret_cast<uint64_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes + wl.lists_bytes)
+                     : nullptr;
+  p.pre_cap = wl.pre_cap;
+  p.maxima = wl.maxima_bytes ? reinterpret_cast<uint32_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes +
+                                                           wl.lists_bytes + wl.pre_bytes)
+                             : nullptr;
+  const size_t tau_bytes = wl.tau_bytes + wl.precount_bytes;   // thresholds and pre-filter counts: zeroed together
   p.dense_out = nullptr;
 
   const bool prof = g_prof.on;
@@ -317,7 +344,9 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
       rc = ts ? launch_search_bf16_ts(ps, s)
               : (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
       if (rc != KNN_OK) return rc;
-      rc = launch_merge_units(ps, 0, nullptr, nullptr, p.tau_global, s);
+      // single query block: hundreds of short lists per row -> seed from the list maxima (list-parallel)
+      rc = wl.seed_maxima ? launch_seed_from_maxima(ps, p.tau_global, s)
+                          : launch_merge_units(ps, 0, nullptr, nullptr, p.tau_global, s);
       if (rc != KNN_OK) return rc;
     }
     if (prof) KNN_CHECK_CUDA(cudaEventRecord(pev[1], s));
@@ -408,8 +437,7 @@ static SearchGeom hamming_geom(int64_t nq, int64_t ng, int k) {
 
 extern "C" size_t knn_search_hamming_workspace(int64_t nq, int64_t ng, int k) {
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
-  const WsLayout w = ws_layout(hamming_geom(nq, ng < 0 ? 0 : ng, k));
-  return w.tau_bytes + w.counts_bytes + w.lists_bytes;
+  return ws_layout(hamming_geom(nq, ng < 0 ? 0 : ng, k), k).total();
 }
 
 extern "C" int knn_pack_bits(const void* x, int64_t n, int bits, int in_dtype, void* out_words, void* stream) {
@@ -449,11 +477,16 @@ extern "C" int knn_search_hamming(const void* q_words, const void* g_words, int6
   p.self_mode = self_mode;
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = 1;
-  const WsLayout wl = ws_layout(geo);
-  p.tau_global = reinterpret_cast<uint32_t*>(workspace);
-  p.counts = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes);
-  p.lists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + wl.tau_bytes + wl.counts_bytes);
-  KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, wl.tau_bytes, s));
+  const WsLayout wl = ws_layout(geo, k);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+  p.tau_global = reinterpret_cast<uint32_t*>(wsb);
+  p.precount = wl.pre_cap ? reinterpret_cast<int32_t*>(wsb + wl.tau_bytes) : nullptr;
+  p.counts = reinterpret_cast<int32_t*>(wsb + wl.tau_bytes + wl.precount_bytes);
+  p.lists = reinterpret_cast<uint64_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes);
+  p.pre = wl.pre_cap ? reinterpret_cast<uint64_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes + wl.lists_bytes)
+                     : nullptr;
+  p.pre_cap = wl.pre_cap;
+  KNN_CHECK_CUDA(cudaMemsetAsync(p.tau_global, 0, wl.tau_bytes + wl.precount_bytes, s));
   if (geo.splits > 0) {
     int rc = launch_search_hamming(p, words, s);
     if (rc != KNN_OK) return rc;

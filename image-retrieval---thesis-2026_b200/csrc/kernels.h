@@ -25,6 +25,11 @@ struct SearchParams {
   uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys (unordered)
   int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
+  // small query batches (one CTA per row would leave the GPU idle): scratch of the two-phase unit merge, nullptr = off
+  uint64_t* pre;         // [qblocks*128][pre_cap] keys >= tau_global gathered by a list-parallel pre-filter
+  int32_t* precount;     // [qblocks*128] keys the pre-filter found (may exceed pre_cap: the merge then re-reads the lists)
+  int pre_cap;
+  uint32_t* maxima;      // [qblocks*128][splits*groups] best score of every list (threshold seeding from list maxima)
   float* dense_out;      // dense mode only
   double* stats_out;     // statistics mode only: [splits][qblocks][128][4] = sum, sum of squares, min, max
 };
@@ -42,6 +47,8 @@ int launch_stats_reduce(const double* partials, int splits, int qblocks, int64_t
 int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table, int64_t table_rows,
                         int table_cols, const int64_t* qcol, float alpha, float beta, int first_m, int64_t self_offset,
                         int mask_self, float* out_vals, cudaStream_t stream);
+// threshold seeding from list maxima: tau_out[row] = k-th largest of the row's list maxima (needs >= k lists per row)
+int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream);
 // order k (value, index) candidates per row best-first, ties by ascending index
 int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
                      int64_t* out_idx, cudaStream_t stream);

@@ -65,7 +65,18 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
 
   // visit every key of this row: warp w walks lists w, w + nwarps, ...; lanes stride through a list (coalesced).
   // fn(key, valid) is called by ALL lanes of the warp in every iteration (warp-aggregated atomics inside).
+  // two-phase form (small query batches): a list-parallel pre-filter already gathered this row's keys >= tau_global
+  const int pre_n = (p.pre != nullptr && tau_out == nullptr) ? __ldcg(p.precount + r) : -1;
+  const bool use_pre = pre_n >= 0 && pre_n <= p.pre_cap;   // overflow (mass ties): read the lists after all
   auto for_each_key = [&](auto&& fn) {
+    if (use_pre) {
+      const uint64_t* base = p.pre + r * (int64_t)p.pre_cap;
+      for (int j0 = warp * 32; j0 < pre_n; j0 += nwarps * 32) {
+        const bool valid = j0 + lane < pre_n;
+        fn(valid ? __ldcg(base + j0 + lane) : 0ull, valid);
+      }
+      return;
+    }
     for (int v = warp; v < V; v += nwarps) {
       const int64_t unit_row = ((int64_t)v * p.qblocks + qb) * kRowsPerUnit + lr;
       int cnt = __ldcg(p.counts + unit_row);
@@ -220,6 +231,76 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
     out_val[r * p.k + j] = v;
     out_idx[r * p.k + j] = id;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-phase unit merge for SMALL query batches.  One CTA per row leaves a 148-SM GPU idle when there are 64 rows, and
+// each CTA then walks hundreds of lists through dependent loads (count -> keys): 134-180 us per merge at 64 queries x
+// 592 lists.  Phase 1 is parallel over (list, row): one warp per list.
+//   * final merge: keys >= tau_global[row] are appended to the row's compact buffer (warp-aggregated atomics); the
+//     CTA-per-row kernel then sorts that buffer alone.
+//   * threshold seeding: only each list's MAXIMUM is kept.  With V >= 2k lists per row the k-th largest of the V
+//     maxima (scores of k distinct gallery rows) is a valid threshold, and nearly as tight as the exact k-th best of
+//     the sample (592 lists, k = 100: ~110 sample rows lie above it instead of 100).
+// ------------------------------------------------------------------------------------------------
+template <bool kSeed>
+__global__ void __launch_bounds__(256) filter_lists_kernel(SearchParams p) {
+  const int lane = threadIdx.x & 31;
+  const int V = p.splits * p.groups;
+  const int64_t rows = (int64_t)p.qblocks * kRowsPerUnit;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // = v * rows + row
+  if (w >= (int64_t)V * rows) return;
+  const int v = (int)(w / rows);
+  const int64_t r = w % rows;
+  if (r >= p.nq) return;
+  const int L = 2 * p.kp;
+  const int64_t unit_row = (int64_t)v * rows + r;
+  int cnt = __ldcg(p.counts + unit_row);
+  cnt = cnt < 0 ? 0 : (cnt > L ? L : cnt);
+  const uint64_t* base = p.lists + unit_row * (int64_t)L;
+  if (kSeed) {
+    uint32_t m = 0u;
+    for (int j = lane; j < cnt; j += 32) m = max(m, (uint32_t)(__ldcg(base + j) >> 32));
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if (lane == 0) p.maxima[r * V + v] = m;
+  } else {
+    const unsigned long long lo = (unsigned long long)__ldcg(p.tau_global + r) << 32;
+    uint64_t* dst = p.pre + r * (int64_t)p.pre_cap;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+      const uint64_t key = j0 + lane < cnt ? __ldcg(base + j0 + lane) : 0ull;
+      const bool keep = key != 0ull && key >= lo;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+      if (b == 0u) continue;
+      int at = 0;
+      if (lane == 0) at = atomicAdd(p.precount + r, __popc(b));
+      at = __shfl_sync(0xFFFFFFFFu, at, 0) + __popc(b & ((1u << lane) - 1u));
+      if (keep && at < p.pre_cap) __stcg(dst + at, key);
+    }
+  }
+}
+
+// One CTA per row: k-th largest of the row's V list maxima (V <= 4096) -> starting threshold.
+__global__ void __launch_bounds__(256) seed_select_kernel(const uint32_t* __restrict__ maxima, int V, int64_t nq, int k,
+                                                          uint32_t* __restrict__ tau_out) {
+  extern __shared__ __align__(16) uint8_t seed_smem[];
+  uint32_t* s = reinterpret_cast<uint32_t*>(seed_smem);
+  const int64_t r = blockIdx.x;
+  const int n = pow2_ge(V);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s[i] = i < V ? __ldcg(maxima + r * V + i) : 0u;
+  __syncthreads();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int lowmask = stride - 1;
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+        const int pos = ((i & ~lowmask) << 1) | (i & lowmask);
+        const bool desc = (pos & size) == 0;
+        const uint32_t a = s[pos], b = s[pos + stride];
+        if (desc ? (a < b) : (a > b)) { s[pos] = b; s[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0 && s[k - 1] != 0u) atomicMax(tau_out + r, s[k - 1]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,9 +546,37 @@ int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k
   return KNN_OK;
 }
 
+int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream) {
+  if (p.nq == 0) return KNN_OK;
+  const int V = p.splits * p.groups;
+  if (p.maxima == nullptr || V < p.k || V > 4096) {
+    set_error("internal: threshold seeding from list maxima needs k <= lists <= 4096 and scratch (lists=%d k=%d)", V, p.k);
+    return KNN_E_INVALID;
+  }
+  const int64_t warps = (int64_t)V * p.qblocks * kRowsPerUnit;
+  filter_lists_kernel<true><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  seed_select_kernel<<<(unsigned)p.nq, 256, (size_t)pow2_ge(V) * sizeof(uint32_t), stream>>>(p.maxima, V, p.nq, p.k, tau_out);
+  KNN_CHECK_CUDA(cudaGetLastError());
+  return KNN_OK;
+}
+
 int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val, int64_t* out_idx,
                        uint32_t* tau_out, cudaStream_t stream) {
   if (p.nq == 0) return KNN_OK;
+  if (p.pre != nullptr && tau_out == nullptr && p.splits > 0) {  // two-phase form: list-parallel pre-filter (precount zeroed by the caller)
+    const int64_t warps = (int64_t)p.splits * p.groups * p.qblocks * kRowsPerUnit;
+    // With >= 2k lists per row, first tighten the shared threshold to the k-th largest LIST MAXIMUM: the running
+    // threshold only ever reflects one list's (or the seeding sample's) k-th best, which leaves ~k * rows / sample keys
+    // per list above it (15 k keys per row at 64 x 10 M); above the k-th largest maximum there are ~1.1 k in total.
+    const int V = p.splits * p.groups;
+    if (p.maxima != nullptr && V >= 2 * p.k && V <= 4096) {
+      int rc = launch_seed_from_maxima(p, p.tau_global, stream);
+      if (rc != KNN_OK) return rc;
+    }
+    filter_lists_kernel<false><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
+    KNN_CHECK_CUDA(cudaGetLastError());
+  }
   // size the CTA and its sort buffer to the input: few short lists per row (small galleries, many queries) get
   // small CTAs so that many rows are merged per SM at once
   const int64_t max_keys = (int64_t)p.splits * p.groups * 2 * p.kp;
