@@ -278,8 +278,10 @@ def main():
     # ---- timed region: device-resident, clocks sampled; the library records CUDA events around its kernels on the
     # launching stream during these very steps (no synchronisation), read back after the region has ended ----------
     lib.knn_profile_enable(1)
+    launches0 = lib.knn_launch_count()
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step_resident, args.steps)
+    launches = lib.knn_launch_count() - launches0            # counted by the library at every launch site
     kern_ms = []
     for i in range(max(0, lib.knn_profile_count() - args.steps), lib.knn_profile_count()):
         sd, a, b = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
@@ -339,7 +341,7 @@ def main():
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps},
         # per step: seeding pre-pass + seeding merge + distance/selection kernel + unit merge
         # (+ k-way shard merge after the all-gather)
-        "gpu_launches": args.steps * (4 + (1 if world > 1 else 0)),
+        "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
     if exact:
@@ -353,7 +355,6 @@ def main():
         line["roofline"]["mma_TFLOPs"] = 3.0 * achieved
         line["roofline"]["mma_frac_of_peak"] = 3.0 * achieved / peaks["tflops"]
         line["config"]["unverified_queries_rerun_on_ffma"] = S._search_exact_tensor.last_unverified
-        line["gpu_launches"] = args.steps * (4 + 3)            # + split of the queries, re-scoring, (norms)
     if world > 1:  # per-rank view of the same timed region: which rank the max-over-ranks step time waits for
         mine = torch.tensor([dist_ms, seed_ms, merge_ms, float(clocks.summary()["sm_mhz"] or 0)], device=dev)
         allr = torch.empty((world, 4), device=dev)

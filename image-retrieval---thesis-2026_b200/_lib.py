@@ -34,6 +34,7 @@ SIGNATURES = {
     "knn_max_sqnorm": (_i, [_p, _i64, _p, _p]),
     "knn_filter_error_bound": (_i, [_p, _i64, _p, _i, _i, _p, _p]),
     "knn_rescore_exact": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i64, _i64, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "knn_launch_count": (C.c_longlong, []),
     "knn_profile_enable": (_i, [_i]),
     "knn_profile_count": (_i, []),
     "knn_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),

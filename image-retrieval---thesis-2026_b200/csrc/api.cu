@@ -1,5 +1,6 @@
 // C-ABI entry points: argument validation, work decomposition, workspace carving, launches.
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -155,6 +156,10 @@ int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d,
   }
   return KNN_OK;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 unsigned long long* debug_stats_buffer() {
   static unsigned long long* buf = [] {
@@ -366,6 +371,8 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   }
   return KNN_OK;
 }
+
+extern "C" long long knn_launch_count(void) { return launches_so_far(); }
 
 extern "C" int knn_profile_enable(int on) {
   g_prof.on = on != 0;

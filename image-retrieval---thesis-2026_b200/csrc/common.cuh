@@ -22,6 +22,14 @@ void set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// After every kernel launch of the library: surface the launch error and count the launch (knn_launch_count).
+void count_launch();
+#define KNN_LAUNCHED()                   \
+  do {                                   \
+    KNN_CHECK_CUDA(cudaGetLastError());  \
+    knn::count_launch();                 \
+  } while (0)
+
 #define KNN_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

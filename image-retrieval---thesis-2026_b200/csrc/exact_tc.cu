@@ -310,7 +310,7 @@ extern "C" int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void
   const int dpad = (d + 7) & ~7;
   split_bf16x3_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       x, n, d, dpad, role, reinterpret_cast<__nv_bfloat16*>(out));
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -359,7 +359,7 @@ extern "C" int knn_rescore_exact(const float* q, const float* g, const float* q_
     kern<<<(unsigned)nq, kRescoreThreads, smem, s>>>(q, g, q_sqnorm, g_sqnorm, ng, d, self_mode, self_local, index_base,
                                                     cand_val, cand_idx, kc, k, npad, eps, out_val, out_idx, unverified);
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -372,7 +372,7 @@ extern "C" int knn_max_sqnorm(const float* sqnorm, int64_t n, float* out, void* 
   int blocks = (int)((n + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   max_nonneg_kernel<<<blocks, 256, 0, s>>>(sqnorm, n, reinterpret_cast<uint32_t*>(out));
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -384,6 +384,6 @@ extern "C" int knn_filter_error_bound(const float* q_sqnorm, int64_t nq, const f
   KNN_REQUIRE(q_sqnorm && g_sqnorm_max && eps, "null pointer");
   error_bound_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q_sqnorm, g_sqnorm_max, nq, d,
                                                                                      metric == KNN_L2 ? 1 : 0, eps);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }

@@ -92,15 +92,39 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
   unsigned long long lo = (unsigned long long)__ldcg(p.tau_global + r) << 32;
   if (threadIdx.x == 0) n_surv = 0;
   __syncthreads();
-  {
+  // gather the keys >= lo into shared memory, counting them all (slots beyond `cap` are not written)
+  auto gather = [&]() {
+    for_each_key([&](uint64_t key, bool valid) {
+      const bool keep = valid && key >= lo;
+      const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+      int base = 0;
+      if (lane == 0 && b) base = atomicAdd(&n_surv, __popc(b));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      const int slot = base + __popc(b & ((1u << lane) - 1u));
+      if (keep && slot < cap) s[slot] = key;
+    });
+  };
+  // Few keys in total (they all fit the sort buffer, or the pre-filter already gathered them): ONE pass.  Otherwise
+  // count first -- with many long lists (8192 x 50 M: 74 lists of ~150 keys) the count usually exceeds `cap`, and a
+  // wasted gather costs more than a counting pass.
+  const bool count_first = !use_pre && (int64_t)V * L > cap;
+  if (count_first) {
     int c = 0;
     for_each_key([&](uint64_t key, bool valid) { c += (valid && key >= lo) ? 1 : 0; });
     c = __reduce_add_sync(0xFFFFFFFFu, c);
     if (lane == 0 && c) atomicAdd(&n_surv, c);
+  } else {
+    gather();
   }
   __syncthreads();
   const int total = n_surv;
   __syncthreads();
+  if (count_first && total <= cap) {
+    if (threadIdx.x == 0) n_surv = 0;
+    __syncthreads();
+    gather();
+    __syncthreads();
+  }
   if (total > cap) {
     // MSB radix select of the k-th largest key among the keys >= lo.  sh_kk = rank still to find inside the
     // current bin; k - sh_kk = keys known to lie strictly above it (all of them are in the answer).
@@ -135,20 +159,11 @@ __global__ void __launch_bounds__(kSortThreads) merge_units_kernel(SearchParams 
       if (sh_done) break;
     }
     if (sh_lo > lo) lo = sh_lo;
+    if (threadIdx.x == 0) n_surv = 0;
+    __syncthreads();
+    gather();   // again, with the raised bound
     __syncthreads();
   }
-  if (threadIdx.x == 0) n_surv = 0;
-  __syncthreads();
-  for_each_key([&](uint64_t key, bool valid) {
-    const bool keep = valid && key >= lo;
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
-    int base = 0;
-    if (lane == 0 && b) base = atomicAdd(&n_surv, __popc(b));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    const int slot = base + __popc(b & ((1u << lane) - 1u));
-    if (keep && slot < cap) s[slot] = key;
-  });
-  __syncthreads();
   int ns = n_surv < cap ? n_surv : cap;
   __syncthreads();
   if (ns > 4 * p.kp) {
@@ -371,7 +386,7 @@ static int launch_merge_parts(const MergeParts& mp, int parts, int64_t nq, int k
   if (nq == 0) return KNN_OK;
   KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<(unsigned)nq, 256, smem, stream>>>(mp, parts, nq, k, metric == KNN_L2 ? 1 : 0, out_val, out_idx);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -523,14 +538,14 @@ int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, i
   const int threads = n >= 512 ? 256 : (n >= 128 ? 64 : 32);
   sort_topk_kernel<<<(unsigned)nq, threads, (size_t)n * sizeof(uint64_t), stream>>>(vals, idx, nq, k, largest, out_vals,
                                                                                   out_idx);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
 int launch_stats_reduce(const double* partials, int splits, int qblocks, int64_t nq, double* out, cudaStream_t stream) {
   if (nq == 0) return KNN_OK;
   stats_reduce_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(partials, splits, qblocks, nq, out);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -542,7 +557,7 @@ int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k
   rescore_topk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(vals, idx, nq, k, table, table_rows, table_cols,
                                                                       qcol, alpha, beta, first_m, self_offset, mask_self,
                                                                       out_vals);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -555,9 +570,9 @@ int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream
   }
   const int64_t warps = (int64_t)V * p.qblocks * kRowsPerUnit;
   filter_lists_kernel<true><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   seed_select_kernel<<<(unsigned)p.nq, 256, (size_t)pow2_ge(V) * sizeof(uint32_t), stream>>>(p.maxima, V, p.nq, p.k, tau_out);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -575,7 +590,7 @@ int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val
       if (rc != KNN_OK) return rc;
     }
     filter_lists_kernel<false><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
-    KNN_CHECK_CUDA(cudaGetLastError());
+    KNN_LAUNCHED();
   }
   // size the CTA and its sort buffer to the input: few short lists per row (small galleries, many queries) get
   // small CTAs so that many rows are merged per SM at once
@@ -585,7 +600,7 @@ int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val
   const int threads = cap <= 1024 ? 128 : (cap <= 2048 ? 256 : kSortThreads);
   merge_units_kernel<<<(unsigned)p.nq, threads, (size_t)cap * sizeof(uint64_t), stream>>>(p, index_base, out_val,
                                                                                         out_idx, tau_out, cap);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -645,6 +660,6 @@ extern "C" int knn_rank_rows(const float* scores, int64_t nq, int64_t ng, int la
   }
   rank_rows_kernel<<<(unsigned)nq, kSortThreads, 0, (cudaStream_t)stream>>>(
       scores, nq, ng, largest_first, rank_npad(ng), reinterpret_cast<uint64_t*>(workspace), ranks);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }

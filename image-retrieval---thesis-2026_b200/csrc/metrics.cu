@@ -240,7 +240,7 @@ extern "C" int knn_relevance_single(const int64_t* idx, int64_t nq, int k, const
   const int64_t total = nq * k;
   relevance_single_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(idx, total, k, qlab, glab, ng,
                                                                                    rel, retrieved_lab);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -254,7 +254,7 @@ extern "C" int knn_relevance_multilabel(const int64_t* idx, int64_t nq, int k, c
   const int64_t total = nq * k;
   relevance_multilabel_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       idx, total, k, qmask, gmask, ng, jaccard_thr, arith, rel_jaccard, rel_any);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -265,7 +265,7 @@ extern "C" int knn_ranked_stats(const uint8_t* rel, int64_t nq, int k, int kk, i
   KNN_REQUIRE(rel, "knn_ranked_stats: null pointer");
   ranked_stats_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(rel, nq, k, kk, hits, first, ap_topk,
                                                                             prec_sum);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -276,7 +276,7 @@ extern "C" int knn_majority_vote(const int64_t* lab, int64_t nq, int k, int kk, 
   if (nq == 0) return KNN_OK;
   KNN_REQUIRE(lab && vote, "knn_majority_vote: null pointer");
   majority_vote_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(lab, nq, k, kk, tie_mode, vote);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -288,7 +288,7 @@ extern "C" int knn_map_full(const int64_t* ranks, int64_t nq, int64_t ng, const 
   KNN_REQUIRE(ranks && qlab && glab && ap && (prs || nkappa == 0), "knn_map_full: null pointer");
   map_full_kernel<<<blocks_for(nq, 4), 128, 0, (cudaStream_t)stream>>>(ranks, nq, ng, qlab, glab, kappas, nkappa, ap,
                                                                       prs, npos);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -307,6 +307,6 @@ extern "C" int knn_ap_sklearn(const float* val, const uint8_t* rel, int64_t nq, 
   }
   ap_sklearn_kernel<<<blocks_for(nq, 64), 64, 0, (cudaStream_t)stream>>>(val, rel, nq, k,
                                                                         reinterpret_cast<double*>(workspace), ap);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }

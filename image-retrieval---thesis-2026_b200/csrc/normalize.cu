@@ -110,7 +110,7 @@ int launch(const void* x, void* y, float* sqnorm, int64_t n, int d, float eps, i
   else
     normalize_kernel<TI, TO, false><<<grid, kWarpsPerBlock * 32, 0, s>>>(
         reinterpret_cast<const TI*>(x), reinterpret_cast<TO*>(y), sqnorm, n, d, eps, eps_mode);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

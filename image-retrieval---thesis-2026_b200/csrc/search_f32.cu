@@ -262,7 +262,7 @@ int launch_one(const SearchParams& p, cudaStream_t stream) {
   KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);
   kern<<<grid, kThreads, smem, stream>>>(p);
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

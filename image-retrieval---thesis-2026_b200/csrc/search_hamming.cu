@@ -83,7 +83,7 @@ int launch_w(const SearchParams& p, int words, cudaStream_t stream) {
     case 8: search_hamming_kernel<E, 8><<<grid, kRows, 0, stream>>>(p); break;
     default: set_error("hamming search: %d words per code not instantiated (1, 2, 3, 4, 8)", words); return KNN_E_UNSUPPORTED;
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 
@@ -122,7 +122,7 @@ int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, u
     set_error("knn_pack_bits: fp32 codes only");
     return KNN_E_UNSUPPORTED;
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

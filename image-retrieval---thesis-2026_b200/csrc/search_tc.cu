@@ -249,7 +249,7 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     kern<<<grid, kThreads, kSmemBytes, stream>>>(tq, tg, p, stats);
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

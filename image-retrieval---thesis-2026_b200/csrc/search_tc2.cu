@@ -377,7 +377,7 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tq, tg, tq2, tg2, p, cfg);
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

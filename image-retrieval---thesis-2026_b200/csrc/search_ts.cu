@@ -383,7 +383,7 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
     KNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KNN_CHECK_CUDA(cudaLaunchKernelEx(&lc, kern, tg, p, cfg));
   }
-  KNN_CHECK_CUDA(cudaGetLastError());
+  KNN_LAUNCHED();
   return KNN_OK;
 }
 

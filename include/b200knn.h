@@ -129,6 +129,9 @@ KNN_API int knn_rescore_exact(const float* q, const float* g, const float* q_sqn
  * knn_profile_enable(1) resets the call counter, knn_profile_count() = calls recorded since, knn_profile_read(i)
  * synchronises on call i's last event and returns its durations (the last 64 calls are kept; host pointers,
  * each nullable); knn_profile_last = (a), (b) of the most recent call. */
+/* Kernels this library has launched in this process so far (every launch site counts itself): the measurement
+ * harness reports the difference over its timed region as "gpu_launches". */
+KNN_API long long knn_launch_count(void);
 KNN_API int knn_profile_enable(int on);
 KNN_API int knn_profile_count(void);
 KNN_API int knn_profile_read(int call, float* seed_ms_host, float* distance_ms_host, float* merge_ms_host);
