@@ -197,7 +197,11 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
     while (rows * 2 <= 65536 && (double)(rows * 2) <= budget) rows *= 2;
   }
   if (rows <= 0) return;
-  int64_t units = (2 * slots + g.qblocks - 1) / g.qblocks;
+  static const int64_t forced_units = [] {
+    const char* e = getenv("KNN_SEED_UNITS");   // experiment knob
+    return e ? (int64_t)atoll(e) : (int64_t)0;
+  }();
+  int64_t units = forced_units > 0 ? forced_units : (2 * slots + g.qblocks - 1) / g.qblocks;
   if (units < 1) units = 1;
   int64_t len = (rows + units - 1) / units;
   if (len < kSeedUnitMin) len = kSeedUnitMin;
