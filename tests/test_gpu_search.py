@@ -426,3 +426,18 @@ def test_full_size_properties(knn, nq, ng, d, k):
         parts_i.append(pi)
     mv, mi = knn.merge_topk(torch.stack(parts_v), torch.stack(parts_i), "cosine")
     assert torch.equal(mi, i) and torch.equal(mv, v)
+
+
+def test_randomised_stress_against_brute_force():
+    """20 s of tools/stress.py: random (precision, metric, shape, k) against torch brute force over the same rows --
+    sortedness, unique in-range indices, tie-aware set equality and score profiles (the kind of check that surfaced
+    the two list-compaction bugs)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "stress.py"), "--seconds", "20", "--seed", "7"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert '"failures": 0' in res.stdout

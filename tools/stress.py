@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Randomised stress of the fused search against brute force (torch fp32 matmul over the SAME rows + topk), meant to
+surface rare selection bugs (lost / duplicated candidates) that fixed-seed parity tests can miss.
+
+    python tools/stress.py [--seconds 90] [--seed 0]
+
+Per trial: random (precision, metric, nq, ng, d, k); checks rows sorted, indices unique and in range, and tie-aware set
+equality with brute force (a returned row may differ from the brute-force set only where its score is within `tol` of
+the k-th score)."""
+import argparse, os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import b200knn
+
+
+def brute(q, g, k, metric, chunk=2048):
+    vals, idx = [], []
+    gf = g.float()
+    gsq = (gf * gf).sum(1) if metric == "l2" else None
+    for s in range(0, q.shape[0], chunk):
+        qf = q[s:s + chunk].float()
+        sc = qf @ gf.T
+        if metric == "l2":
+            sc = -((qf * qf).sum(1, keepdim=True) + gsq[None, :] - 2 * sc).clamp_min(0).sqrt()
+        v, i = torch.topk(sc, min(k, g.shape[0]), dim=1)
+        vals.append(v); idx.append(i)
+    return torch.cat(vals), torch.cat(idx)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=90)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev); gen.manual_seed(args.seed)
+    rs = __import__("random").Random(args.seed)
+    t0, trials, bad = time.time(), 0, []
+    while time.time() - t0 < args.seconds:
+        precision = rs.choice(["bf16", "bf16", "fp32", "fp32-tensor"])
+        metric = rs.choice(["cosine", "l2", "ip"])
+        nq = rs.choice([1, 7, 64, 128, 129, 300, 1000, 2500])
+        ng = rs.choice([500, 5000, 40_000, 200_000, 700_001])
+        d = rs.choice([8, 36, 64, 100, 256, 512, 768, 1024])
+        k = rs.choice([1, 10, 31, 32, 33, 50, 64, 100, 128, 200, 256])
+        if nq * ng * d > 6e11 or (nq * ng < 2e6 and rs.random() < 0.9):
+            continue
+        g = torch.randn((ng, d), generator=gen, device=dev)
+        q = torch.randn((nq, d), generator=gen, device=dev)
+        if rs.random() < 0.3:  # clustered queries: close to gallery rows, many near neighbours
+            q = g[torch.randint(0, ng, (nq,), generator=gen, device=dev)] + 0.05 * q
+        if metric != "ip":
+            g, q = b200knn.normalize(g), b200knn.normalize(q)
+        if precision == "bf16":
+            g, q = g.bfloat16().float(), q.bfloat16().float()    # identical inputs for both sides
+        os.environ.pop("KNN_EXACT_ENGINE", None)
+        if precision == "fp32-tensor":
+            os.environ["KNN_EXACT_ENGINE"] = "tensor"
+        v, i = b200knn.search(q, g, k, metric, precision="bf16" if precision == "bf16" else "fp32")
+        kk = min(k, ng)
+        v, i = v[:, :kk], i[:, :kk]
+        bv, bi = brute(q, g, kk, metric)
+        if metric == "l2":
+            bv = -bv
+            ok_sorted = bool((v[:, 1:] >= v[:, :-1]).all())
+        else:
+            ok_sorted = bool((v[:, 1:] <= v[:, :-1]).all())
+        srt = i.sort(1).values
+        ok_unique = bool((srt[:, 1:] != srt[:, :-1]).all()) and bool((i >= 0).all()) and bool((i < ng).all())
+        scale = float(bv.abs().max()) + 1e-6
+        if metric == "l2":   # rows are normalised: d^2 = 2 - 2 q.g (GEMM form of cdist) carries an ABSOLUTE error of a
+            # few 1e-6 (cancellation; tensor-core truncation at d = 1024), so the error of d = sqrt(d^2) grows as 1 / d
+            tol = 6e-6 / bv.clamp_min(2e-3) + 4e-6
+        else:
+            tol = 2e-5 * scale * (d ** 0.5) / 8 + 1e-6
+        # tie-aware set equality: every returned row not in the brute-force set must score within tol of the k-th
+        kth = bv[:, -1:]
+        tol_k = tol[:, -1:] if torch.is_tensor(tol) else tol
+        member = (i[:, :, None] == bi[:, None, :]).any(2)
+        viol = (~member) & ((v - kth).abs() > tol_k)
+        ok_set = not bool(viol.any())
+        ok_vals = bool(((v - bv).abs() <= tol).all())             # sorted score profiles agree
+        trials += 1
+        if not (ok_sorted and ok_unique and ok_set and ok_vals):
+            bad.append({"precision": precision, "metric": metric, "nq": nq, "ng": ng, "d": d, "k": k, "sorted": ok_sorted,
+                        "unique": ok_unique, "set": ok_set, "vals": ok_vals, "rows_bad": int(viol.any(1).sum())})
+            print("FAIL", bad[-1], flush=True)
+    print(json.dumps({"trials": trials, "failures": len(bad), "seconds": round(time.time() - t0, 1)}))
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
