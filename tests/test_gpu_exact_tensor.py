@@ -121,10 +121,16 @@ def test_observed_filter_error_is_far_inside_the_bound(knn):
     S = importlib.import_module("b200knn.search")
 
     rs = np.random.RandomState(21)
-    for d, positive in ((1024, True), (1024, False), (2048, True), (96, True)):
+    for d, positive in ((1024, True), (1024, False), (2048, True), (96, True), (1024, "tiny-tail")):
         g = rs.standard_normal((20000, d)).astype(np.float32)
         q = rs.standard_normal((256, d)).astype(np.float32)
-        if positive:
+        if positive == "tiny-tail":
+            # one unit term followed by d - 1 products just below half an ulp of the running sum: the fp32 chain
+            # drops every one of them, a wider accumulator keeps them -- the largest chain-vs-filter gap by design
+            g = np.full((20000, d), 2.0 ** -12, dtype=np.float32) * rs.uniform(0.9, 1.0, (20000, d)).astype(np.float32)
+            q = np.full((256, d), 2.0 ** -12, dtype=np.float32) * rs.uniform(0.9, 1.0, (256, d)).astype(np.float32)
+            g[:, 0], q[:, 0] = 1.0, 1.0
+        elif positive:
             g, q = np.abs(g), np.abs(q)
         gd, qd = dev(g), dev(q)
         kc = 64

@@ -441,3 +441,27 @@ def test_randomised_stress_against_brute_force():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
     assert '"failures": 0' in res.stdout
+
+
+def test_search_is_cuda_graph_capturable(knn):
+    """The library only enqueues work on the caller's stream (no hidden synchronisation, no allocation): a whole
+    FlatIndex.search -- normalise + cast, threshold seeding, distance + selection, two-phase merge -- can be captured
+    into a CUDA graph and replayed on new query contents (small-batch serving without launch overhead)."""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(12)
+    g = torch.randn((300_000, 256), generator=gen, device="cuda")
+    index = knn.FlatIndex(256, "cosine", "bf16", normalize=True).add(g)
+    q_static = torch.randn((16, 256), generator=gen, device="cuda")
+    index.search(q_static, 50)                                   # warm-up outside the capture (lazy initialisation)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        v_static, i_static = index.search(q_static, 50)
+    for seed in (1, 2, 3):
+        gen.manual_seed(seed)
+        q_new = torch.randn((16, 256), generator=gen, device="cuda")
+        q_static.copy_(q_new)
+        graph.replay()
+        torch.cuda.synchronize()
+        v, i = index.search(q_new, 50)
+        assert torch.equal(i, i_static) and torch.equal(v, v_static)
