@@ -442,3 +442,155 @@ def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jacc
     if len(aps) == 0:
         return 0.0
     return float(np.mean(aps) * 100.0)
+
+
+# --------------------------------------------------------------------------------------------------
+# D12 evaluate_retrieval  (evaluate_medsiglip.py:142-163)
+# --------------------------------------------------------------------------------------------------
+def evaluate_retrieval(image_features: torch.Tensor, labels, topk_values) -> Dict[str, float]:
+    """Self-retrieval over (already normalised) features: ``sim = f @ f.T``, ``fill_diagonal_(-1.0)``, row-wise
+    ranking; R@k any-hit, and majority vote with ``np.unique`` + ``argmax`` (ties -> the SMALLEST label) scored by
+    accuracy and macro F1, all in percent.  Same keys as the reference: ``r_at_{k}``, ``majority_accuracy_at_{k}``,
+    ``majority_macro_f1_at_{k}``."""
+    _require_cuda(image_features)
+    kmax = max(int(k) for k in topk_values)
+    _, idx = search(image_features, image_features, kmax, "ip", self_mode="minus1")
+    lab_dev = _dev_i64(labels, idx.device).view(-1)
+    rel, lab = relevance_single(idx, lab_dev, lab_dev)
+    true = lab_dev.cpu().numpy()
+    results: Dict[str, float] = {}
+    for k in topk_values:
+        hits = ranked_stats(rel, int(k))[0].cpu().numpy()
+        pred = majority_vote_labels(lab, int(k), "smallest").cpu().numpy()
+        prf = _prf_from_predictions(true, pred)
+        results[f"r_at_{k}"] = float(np.mean(hits > 0) * 100.0)
+        results[f"majority_accuracy_at_{k}"] = prf["accuracy"]
+        results[f"majority_macro_f1_at_{k}"] = prf["f1_macro"]
+    return results
+
+
+# --------------------------------------------------------------------------------------------------
+# D10' compute_retrieval_metrics  (train_ath.py:171-218): the training-time variant of compute_metrics
+# --------------------------------------------------------------------------------------------------
+def compute_retrieval_metrics(query_codes, query_labels, gallery_codes, gallery_labels, topk_values,
+                              binary_codes: bool, precision: str = "fp32") -> Dict[int, Dict[str, float]]:
+    """mHR, mAP@k (precision sum / positives in the top-k), mRR and majority accuracy with ``torch.mode``
+    (ties -> the smallest label), ranking by ascending L2 or Hamming distance."""
+    _require_cuda(query_codes, gallery_codes)
+    kmax = max(int(k) for k in topk_values)
+    if binary_codes:
+        _, idx = search_hamming(query_codes, gallery_codes, kmax)
+    else:
+        _, idx = search(query_codes.float(), gallery_codes.float(), kmax, "l2", precision=precision)
+    ql, gl = _dev_i64(query_labels, idx.device).view(-1), _dev_i64(gallery_labels, idx.device).view(-1)
+    rel, lab = relevance_single(idx, ql, gl)
+    results = {}
+    for topk in topk_values:
+        hits, first, ap, _ = ranked_stats(rel, int(topk))
+        hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
+        vote = majority_vote_labels(lab, int(topk), "smallest")
+        rr = np.where(first_np > 0, 1.0 / np.maximum(first_np, 1), 0.0)
+        results[topk] = {
+            "mhr": float(np.mean((hits_np > 0).astype(np.float64))),
+            "map": float(np.mean(ap.cpu().numpy())),
+            "mrr": float(np.mean(rr)),
+            "majority_acc": float(np.mean((vote == ql).cpu().numpy().astype(np.float64))),
+        }
+    return results
+
+
+# --------------------------------------------------------------------------------------------------
+# D14 retrieval_accuracy_from_ranks / compute_classification_metrics_from_ranks  (ChestMIR/chestmir_eval.py:191-272)
+# --------------------------------------------------------------------------------------------------
+def _labels_to_codes(labels) -> Tuple[np.ndarray, np.ndarray]:
+    """Arbitrary (string / object) labels -> (int64 codes, the distinct labels); equality is all the metrics need."""
+    arr = np.asarray(labels)
+    uniq, inv = np.unique(arr.astype(str) if arr.dtype == object else arr, return_inverse=True)
+    return inv.astype(np.int64).reshape(-1), uniq
+
+
+def _ranks_topk_device(ranks: np.ndarray, kmax: int, device) -> torch.Tensor:
+    """The reference's column layout ``ranks[:k, i]`` = top-k of query i  ->  int64 [N, kmax] on the device."""
+    r = np.ascontiguousarray(np.asarray(ranks)[:kmax, :].T).astype(np.int64)
+    return torch.from_numpy(r).to(device)
+
+
+def retrieval_accuracy_from_ranks(ranks: np.ndarray, labels, topk, device=None) -> np.ndarray:
+    """R@K in percent (float64 array) from a full column-wise ranking matrix; any label match in ``ranks[:k, i]``."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    codes, _ = _labels_to_codes(labels)
+    n = len(codes)
+    kmax = min(max(int(k) for k in topk), np.asarray(ranks).shape[0])
+    idx = _ranks_topk_device(ranks, kmax, device)
+    lab = torch.from_numpy(codes).to(device)
+    rel, _ = relevance_single(idx, lab, lab)
+    out = []
+    for k in topk:
+        correct = int((ranked_stats(rel, min(int(k), kmax))[0] > 0).sum().item())
+        out.append((correct * 100.0) / max(1, n))
+    return np.array(out, dtype=np.float64)
+
+
+def compute_classification_metrics_from_ranks(labels, ranks: np.ndarray, k_values, device=None):
+    """Majority vote (``Counter.most_common``: first label met in rank order wins a tie) + the reference's hand-rolled
+    per-class precision / recall / F1 (``f1 = 2pr / (p + r)``), macro and support-weighted, in percent."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    codes, _ = _labels_to_codes(labels)
+    kmax = min(max(int(k) for k in k_values), np.asarray(ranks).shape[0])
+    idx = _ranks_topk_device(ranks, kmax, device)
+    lab = torch.from_numpy(codes).to(device)
+    _, retrieved = relevance_single(idx, lab, lab)
+    results = {}
+    for k in k_values:
+        y_pred = majority_vote_labels(retrieved, min(int(k), kmax), "first").cpu().numpy()
+        y_true = codes
+        classes = np.unique(np.concatenate([y_true, y_pred], axis=0))
+        per_p, per_r, per_f, supports = [], [], [], []
+        for c in classes:
+            tp = int(np.sum((y_true == c) & (y_pred == c)))
+            fp = int(np.sum((y_true != c) & (y_pred == c)))
+            fn = int(np.sum((y_true == c) & (y_pred != c)))
+            p = tp / (tp + fp) if (tp + fp) > 0 else 0.0
+            r = tp / (tp + fn) if (tp + fn) > 0 else 0.0
+            per_p.append(p)
+            per_r.append(r)
+            per_f.append((2.0 * p * r / (p + r)) if (p + r) > 0 else 0.0)
+            supports.append(int(np.sum(y_true == c)))
+        sup = np.asarray(supports, dtype=np.float64)
+        wsum = float(np.sum(sup))
+        weights = sup / (wsum if wsum > 0 else 1.0)
+        results[k] = {
+            "accuracy": float(np.mean(y_true == y_pred)) * 100.0,
+            "precision_macro": (float(np.mean(per_p)) if per_p else 0.0) * 100.0,
+            "recall_macro": (float(np.mean(per_r)) if per_r else 0.0) * 100.0,
+            "f1_macro": (float(np.mean(per_f)) if per_f else 0.0) * 100.0,
+            "precision_weighted": (float(np.sum(np.asarray(per_p) * weights)) if per_p else 0.0) * 100.0,
+            "recall_weighted": (float(np.sum(np.asarray(per_r) * weights)) if per_r else 0.0) * 100.0,
+            "f1_weighted": (float(np.sum(np.asarray(per_f) * weights)) if per_f else 0.0) * 100.0,
+        }
+    return results
+
+
+# --------------------------------------------------------------------------------------------------
+# D9 helpers  (evaluate_nih_zilliz.py:12-31): the per-item functions behind evaluate_results
+# --------------------------------------------------------------------------------------------------
+def jaccard_score(query_label, gallery_label) -> float:
+    """``intersection / (union + 1e-8)`` of two multi-hot vectors: float32 products / clipped sums, Python-float ratio
+    (host scalar math on two label vectors; the batched form is relevance_multilabel(arith="fp64"))."""
+    q = np.asarray(query_label, dtype=np.float32)
+    g = np.asarray(gallery_label, dtype=np.float32)
+    return float((q * g).sum()) / (float(np.clip(q + g, 0.0, 1.0).sum()) + 1e-8)
+
+
+def precision_at_k(binary_relevance, k: int) -> float:
+    if not len(binary_relevance):
+        return 0.0
+    k = min(k, len(binary_relevance))
+    return float(np.mean(binary_relevance[:k]))
+
+
+def recall_at_k(binary_relevance, total_positives: int, k: int) -> float:
+    if total_positives <= 0:
+        return 0.0
+    k = min(k, len(binary_relevance))
+    return float(np.sum(binary_relevance[:k]) / total_positives)
