@@ -18,7 +18,7 @@ values afterwards.  torch is used for embedding plumbing only (concatenation, pe
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Dict, Iterable, List, Optional, Protocol, Sequence, Tuple
 
 import numpy as np
@@ -167,16 +167,35 @@ class ExperimentResult:
     skipped_reason: Optional[str] = None
 
 
-def run_late_fusion_experiments(conv_embeddings, dino_embeddings, labels: Sequence, image_paths: Sequence,
+@dataclass(frozen=True)
+class AlignedEmbeddings:
+    """Intersection-aligned embedding payload of the fusion experiments (fusion_eval/align.py:27-35)."""
+
+    image_paths: List[str]
+    labels: List[str]
+    conv_embeddings: np.ndarray
+    dino_embeddings: np.ndarray
+    coverage: Dict[str, List[str]] = field(default_factory=dict)
+
+
+def run_late_fusion_experiments(conv_embeddings, dino_embeddings=None, labels: Optional[Sequence] = None,
+                                image_paths: Optional[Sequence] = None,
                                 alpha_values: Sequence[float] = (0.2, 0.4, 0.5, 0.6, 0.8),
                                 k_values: Iterable[int] = (1, 5, 10), include_score_fusion: bool = True,
                                 score_normalization: str = "none",
                                 include_confidence_fusion: bool = True) -> List[ExperimentResult]:
-    """Same experiments, names and metric keys as the reference's loop; the aligned payload is passed as its four
+    """Same experiments, names and metric keys as the reference's loop.  Call it like the reference --
+    ``run_late_fusion_experiments(aligned, alpha_values=...)`` with an :class:`AlignedEmbeddings` -- or with the four
     arrays.  Full-ranking metrics (mAP) use k = N-1 searches, so this is meant for the evaluation-set sizes the
     reference runs it on."""
     from . import metrics as M
 
+    if isinstance(conv_embeddings, AlignedEmbeddings):
+        aligned = conv_embeddings
+        conv_embeddings, dino_embeddings = aligned.conv_embeddings, aligned.dino_embeddings
+        labels, image_paths = aligned.labels, aligned.image_paths
+    if dino_embeddings is None or labels is None or image_paths is None:
+        raise ValueError("pass an AlignedEmbeddings, or conv / dino embeddings with labels and image paths")
     conv, dino = _cuda_f32(conv_embeddings), _cuda_f32(dino_embeddings)
     n = conv.shape[0]
     k_values = list(k_values)

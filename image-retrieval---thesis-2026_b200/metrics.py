@@ -410,6 +410,22 @@ def compute_map_multilabel_from_embeddings(embeds: torch.Tensor, labels_multihot
     return float(np.mean(aps)) if len(aps) else 0
 
 
+def compute_map_multilabel(dists: torch.Tensor, labels: torch.Tensor, threshold: float = 0.5) -> float:
+    """Reference signature (test.py:941): dense ``dists`` (larger = closer, diagonal already -inf), multi-hot
+    ``labels``; ranks COLUMNS (``np.argsort(-dists, axis=0)``, ties by ascending row), relevance = Jaccard > threshold
+    with the query itself removed, rank-by-rank AP normalised by the number of relevant items, queries without any
+    skipped.  For small N (the dense matrix exists); the embeddings-in form above never builds it."""
+    _require_cuda(dists)
+    n = dists.shape[0]
+    m = pack_multihot(labels.to(dists.device))
+    ranks = rank_rows(dists.t().contiguous(), largest_first=True)
+    rel, _ = relevance_multilabel(ranks, m, m, threshold, arith="fp32")
+    rel[ranks == torch.arange(n, device=ranks.device)[:, None]] = 0       # binary_relevance[i] = 0
+    hits, _, ap, _ = ranked_stats(rel)
+    aps = ap.cpu().numpy()[hits.cpu().numpy() > 0]
+    return float(np.mean(aps)) if len(aps) else 0
+
+
 def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10),
                                           relevance_threshold: float = 0.4):
     """train.py:444-487: sklearn AP (tied scores grouped) with self masked out, R@K = any relevant in top-k."""

@@ -110,6 +110,12 @@ def test_experiment_loop_reproduces_the_reference_metric_dicts(knn, gf, case, mo
     res = knn.fusion.run_late_fusion_experiments(dev(conv), dev(dino), labels, paths, alpha_values=(0.2, 0.5, 0.8),
                                                  k_values=(1, 5, 10), include_score_fusion=True,
                                                  score_normalization=mode, include_confidence_fusion=True)
+    if mode == "none":  # the reference's own call shape: one AlignedEmbeddings payload (fusion_eval/evaluate.py:30)
+        aligned = knn.fusion.AlignedEmbeddings(image_paths=paths, labels=labels, conv_embeddings=conv,
+                                               dino_embeddings=dino, coverage={})
+        res2 = knn.fusion.run_late_fusion_experiments(aligned, alpha_values=(0.2, 0.5, 0.8), k_values=(1, 5, 10),
+                                                      score_normalization=mode)
+        assert [(r.experiment_name, r.metrics) for r in res2] == [(r.experiment_name, r.metrics) for r in res]
     want = gf[f"{case}_{mode}"]
     assert [r.experiment_name for r in res] == [w["experiment_name"] for w in want]
     for r, w in zip(res, want):

@@ -126,6 +126,9 @@ def test_multilabel_self_retrieval_metrics(knn, golden):
         assert got[k] == pytest.approx(v, rel=1e-9), k
     for t, v in golden["ml_self_map_multilabel"].items():
         assert M.compute_map_multilabel_from_embeddings(emb, tl, float(t)) == pytest.approx(v, rel=1e-12)
+        # the reference's own signature: dense dists with the diagonal at -inf (test.py:1007 -> :941)
+        dense = knn.scores_dense(emb, emb, "cosine", normalize=True, self_mode="exclude")
+        assert M.compute_map_multilabel(dense, tl, float(t)) == pytest.approx(v, rel=1e-12)
     assert M.evaluate_map_embeddings(emb, tl, 0.4) == pytest.approx(golden["ml_self_evaluate_map"], rel=1e-9)
     _, idx = knn.search(emb, emb, 20, "cosine", normalize=True, exclude_self=True)
     hr = M.multilabel_hit_rate_from_topk(idx, tl, tl, (1, 5, 10, 15, 20))
