@@ -46,6 +46,7 @@ SIGNATURES = {
     "knn_score_stats": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p, _sz, _p]),
     "knn_score_stats_workspace": (_sz, [_i64, _i64]),
     "knn_rescore_topk": (_i, [_p, _p, _i64, _i, _p, _i64, _i, _p, _f, _f, _i, _i64, _i, _p, _p]),
+    "knn_lesion_rerank": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p, _p, _i64, _i, _i, _d, _p, _p, _p, _p]),
     "knn_sort_topk": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
     "knn_scores_dense": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p]),
     "knn_rank_rows": (_i, [_p, _i64, _i64, _i, _p, _p, _sz, _p]),

@@ -297,3 +297,122 @@ class IdentityReranker:
 
     def rerank(self, query, results: Iterable) -> Iterable:
         return list(results)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# lesion (region) re-ranking  (ChestMIR/chestmir_eval.py:275-318, 461-650)
+# --------------------------------------------------------------------------------------------------------------
+def normalize_lesion_text(name) -> str:
+    """chestmir_eval.py:281-285: lower-case, `_ - /` -> space, collapse blanks."""
+    text = str(name).strip().lower().replace("_", " ").replace("-", " ").replace("/", " ")
+    return " ".join(text.split())
+
+
+def canonical_lesion_name(name, alias_to_canon: Optional[Dict[str, str]] = None) -> str:
+    """chestmir_eval.py:288-290; the alias table (LESION_ALIAS_GROUPS) is the caller's data."""
+    normalized = normalize_lesion_text(name)
+    return (alias_to_canon or {}).get(normalized, normalized)
+
+
+class LesionIndex:
+    """Device-resident region vectors of a gallery: ``lesion_maps[i]`` = {canonical lesion -> [unit vectors]} (the
+    output of ``build_lesion_vector_map``), stored CSR over (image, lesion slot) for ``knn_lesion_rerank``."""
+
+    def __init__(self, lesion_maps: Sequence[Dict[str, Sequence[np.ndarray]]], device=None):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.maps = lesion_maps
+        names = sorted({k for m in lesion_maps for k, v in m.items() if len(v)})
+        self.slot = {name: s for s, name in enumerate(names)}
+        self.n_slots = max(1, len(names))
+        self.n_img = len(lesion_maps)
+        dl = next((len(v[0]) for m in lesion_maps for v in m.values() if len(v)), 1)
+        offsets = np.zeros(self.n_img * self.n_slots + 1, dtype=np.int64)
+        rows: List[np.ndarray] = []
+        for i, m in enumerate(lesion_maps):
+            for name, vecs in m.items():
+                if len(vecs):
+                    offsets[i * self.n_slots + self.slot[name] + 1] = len(vecs)
+        np.cumsum(offsets, out=offsets)
+        flat = np.zeros((max(1, int(offsets[-1])), dl), dtype=np.float32)
+        for i, m in enumerate(lesion_maps):
+            for name, vecs in m.items():
+                if len(vecs):
+                    b = offsets[i * self.n_slots + self.slot[name]]
+                    flat[b:b + len(vecs)] = np.asarray(vecs, dtype=np.float32)
+        self.dl = dl
+        self.offsets = torch.from_numpy(offsets).to(self.device)
+        self.vectors = torch.from_numpy(flat).to(self.device)
+
+    def query_vector(self, i: int, lesion: str):
+        """choose_query_lesion_vector (chestmir_eval.py:461-469): the image's FIRST vector of that lesion."""
+        cands = self.maps[i].get(lesion, [])
+        return cands[0] if len(cands) else None
+
+    def adaptive_query_vector(self, i: int, target_keys: Sequence[str]):
+        """choose_query_adaptive_lesion_vector (chestmir_eval.py:484-505): the target lesion with the most regions in
+        the image (first such target on ties)."""
+        best_name, best_vec, best_count = None, None, -1
+        for name in target_keys:
+            cands = self.maps[i].get(name, [])
+            if len(cands) > best_count and len(cands):
+                best_count, best_name, best_vec = len(cands), name, cands[0]
+        return best_name, best_vec
+
+
+def lesion_rerank_search(global_vectors, lesion_maps, k: int, rerank_topk: int, global_weight: float,
+                         lesion_name: Optional[str] = None, target_lesions: Optional[Sequence[str]] = None,
+                         alias_to_canon: Optional[Dict[str, str]] = None, index: Optional[LesionIndex] = None):
+    """Two-stage self-retrieval of chestmir_eval.py: global cosine ranking, then the top ``rerank_topk`` candidates of
+    every query re-ordered by ``gw * global + (1 - gw) * best region cosine`` for ONE lesion (``lesion_name``:
+    rerank_with_specific_lesion) or for the query's dominant target lesion (``target_lesions``:
+    rerank_with_adaptive_lesion).  -> (indices [N, K] with K = max(k, rerank_topk), stats dict with the reference's
+    keys).  No N x N matrix: stage 1 is the fused search, stage 2 ``knn_lesion_rerank`` on its candidate lists."""
+    if (lesion_name is None) == (target_lesions is None):
+        raise ValueError("pass exactly one of lesion_name / target_lesions")
+    g = _cuda_f32(global_vectors)
+    n = g.shape[0]
+    topk = min(int(rerank_topk), n - 1)
+    K = min(max(int(k), topk), n - 1)
+    vals, idx = search(g, g, K, "ip", exclude_self=True)
+    index = index or LesionIndex(lesion_maps, g.device)
+    qslot = np.full(n, -1, dtype=np.int32)
+    qvec = np.zeros((n, index.dl), dtype=np.float32)
+    usage: Dict[str, int] = {}
+    chosen: List[Optional[str]] = [None] * n
+    if lesion_name is not None:
+        key = canonical_lesion_name(lesion_name, alias_to_canon)
+        for i in range(n):
+            v = index.query_vector(i, key)
+            if v is not None:
+                qslot[i], qvec[i], chosen[i] = index.slot[key], v, key
+    else:
+        keys = [canonical_lesion_name(x, alias_to_canon) for x in target_lesions]
+        for i in range(n):
+            name, v = index.adaptive_query_vector(i, keys)
+            if v is not None:
+                qslot[i], qvec[i], chosen[i] = index.slot[name], v, name
+    out_idx = torch.empty_like(idx)
+    matched = torch.empty((n,), dtype=torch.int32, device=g.device)
+    qv, qs = torch.from_numpy(qvec).to(g.device), torch.from_numpy(qslot).to(g.device)
+    with torch.cuda.device(g.device):
+        rc = L.load().knn_lesion_rerank(_ptr(vals), _ptr(idx), n, K, topk, _ptr(qv), _ptr(qs), _ptr(index.offsets),
+                                        _ptr(index.vectors), index.n_img, index.n_slots, index.dl, float(global_weight),
+                                        _ptr(out_idx), None, _ptr(matched), _stream(g))
+    L.check(rc, "knn_lesion_rerank")
+    mt = matched.cpu().numpy()
+    reranked = int((mt > 0).sum())
+    for i in np.nonzero(mt > 0)[0]:
+        usage[chosen[i]] = usage.get(chosen[i], 0) + 1
+    total_topk = n * topk
+    total_matched = int(mt[mt > 0].sum())
+    stats = {
+        "queries_total": n, "queries_reranked": reranked, "queries_fallback_global": n - reranked,
+        "queries_with_candidate_match": reranked, "matched_candidates_in_topk": total_matched,
+        "candidate_match_rate_pct": (100.0 * total_matched / total_topk) if total_topk > 0 else 0.0,
+        "rerank_topk": rerank_topk, "global_weight": global_weight, "region_weight": 1.0 - global_weight,
+    }
+    if lesion_name is not None:
+        stats = {"lesion": lesion_name, **stats}
+    else:
+        stats = {"mode": "adaptive", **stats, "lesion_usage": usage}
+    return out_idx, stats

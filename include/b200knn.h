@@ -169,6 +169,18 @@ KNN_API size_t knn_score_stats_workspace(int64_t nq, int64_t ng);
 KNN_API int knn_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k, const float* table,
                      int64_t table_rows, int table_cols, const int64_t* qcol, float alpha, float beta,
                      int first_m, int64_t self_offset, int mask_self, float* out_vals, void* stream);
+/* Region (lesion) re-ranking of the first `first_m` candidates of every query: rerank_with_specific_lesion /
+ * rerank_with_adaptive_lesion, ChestMIR/chestmir_eval.py:507-650, on top-k lists.  Images carry ragged sets of
+ * normalised region vectors per lesion slot, CSR over (image, slot): vectors[offsets[img*n_slots+slot] ..
+ * offsets[img*n_slots+slot+1]) of dl floats.  Query q uses qvec[q] of slot qslot[q] (-1: none).  Candidate j gets
+ * region = max <qvec, v> over its vectors of that slot (-1.0 if none), score = gw*base + (1-gw)*region in IEEE double;
+ * the first_m candidates are stably re-ordered by (score, base) descending.  matched[q] = candidates with region >= 0
+ * (0: list left in global order, as the reference's fallback; -1: the query has no vector).  out_score [nq,first_m]
+ * (nullable) = the combined scores in the new order. */
+KNN_API int knn_lesion_rerank(const float* cand_val, const int64_t* cand_idx, int64_t nq, int k, int first_m,
+                      const float* qvec, const int32_t* qslot, const int64_t* offsets, const float* vectors,
+                      int64_t n_img, int n_slots, int dl, double global_weight, int64_t* out_idx,
+                      double* out_score, int32_t* matched, void* stream);
 /* Order k <= 4096 (value, index) candidates per row best-first (largest != 0: descending values), ties by ascending
  * index, entries with index < 0 last; indices must be < 2^32 - 1.  The deterministic form of the `argsort` that
  * follows a re-scoring (test.py:633). */
