@@ -41,6 +41,8 @@ SIGNATURES = {
     "knn_profile_last": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "knn_debug_stats": (_i, [C.POINTER(C.c_ulonglong), _i]),
     "knn_pack_bits": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "knn_unpack_bits_pm1": (_i, [_p, _i64, _i, _p, _p]),
+    "knn_hamming_from_scores": (_i, [_p, _i64, _i, _p, _p]),
     "knn_search_hamming": (_i, [_p, _p, _i64, _i64, _i, _i, _i, _i64, _i64, _p, _p, _p, _sz, _p]),
     "knn_search_hamming_workspace": (_sz, [_i64, _i64, _i]),
     "knn_score_stats": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p, _sz, _p]),

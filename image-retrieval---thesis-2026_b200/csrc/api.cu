@@ -459,6 +459,22 @@ extern "C" int knn_pack_bits(const void* x, int64_t n, int bits, int in_dtype, v
                           (cudaStream_t)stream);
 }
 
+extern "C" int knn_unpack_bits_pm1(const void* words, int64_t n, int bits, void* out_bf16, void* stream) {
+  KNN_REQUIRE(n >= 0 && bits >= 1, "knn_unpack_bits_pm1: bad shape n=%lld bits=%d", (long long)n, bits);
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(words && out_bf16, "knn_unpack_bits_pm1: null pointer");
+  KNN_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "out must be 16-byte aligned");
+  return launch_unpack_pm1(reinterpret_cast<const uint64_t*>(words), n, bits, (bits + 63) / 64, out_bf16,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int knn_hamming_from_scores(const float* score, int64_t n, int bits, float* out, void* stream) {
+  KNN_REQUIRE(n >= 0 && bits >= 1, "knn_hamming_from_scores: bad sizes");
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(score && out, "knn_hamming_from_scores: null pointer");
+  return launch_hamming_from_scores(score, n, bits, out, (cudaStream_t)stream);
+}
+
 extern "C" int knn_search_hamming(const void* q_words, const void* g_words, int64_t nq, int64_t ng, int words, int k,
                                   int self_mode, int64_t self_offset, int64_t index_base, float* out_val,
                                   int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {

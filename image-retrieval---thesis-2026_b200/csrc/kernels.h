@@ -55,6 +55,8 @@ int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, i
 
 // Hamming distance over packed 64-bit code words (csrc/search_hamming.cu); p.q / p.g point at uint64 [rows, words]
 int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream);
+int launch_hamming_from_scores(const float* score, int64_t n, int bits, float* out, cudaStream_t stream);
+int launch_unpack_pm1(const uint64_t* words, int64_t n, int bits, int nwords, void* out_bf16, cudaStream_t stream);
 int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, uint64_t* out, cudaStream_t stream);
 
 // [rows, d] bf16 row-major -> tensor map with a {64, box_rows} box, 128-byte swizzle (api.cu)

@@ -101,7 +101,52 @@ __global__ void pack_bits_kernel(const T* __restrict__ x, int64_t n, int bits, i
   out[t] = v;
 }
 
+// packed words -> +-1 rows in bf16 (bit set -> +1, clear -> -1, columns bits .. dpad-1 -> 0): the operand form of the
+// tensor-core Hamming search, <q, g> = bits - 2 * hamming(q, g) exactly.  One thread per 8 output columns.
+__global__ void __launch_bounds__(256) unpack_pm1_kernel(const uint64_t* __restrict__ words, int64_t n, int bits,
+                                                         int nwords, int dpad, __nv_bfloat16* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = dpad / 8;
+  if (t >= n * groups) return;
+  const int64_t r = t / groups;
+  const int c0 = (int)(t % groups) * 8;
+  const uint64_t w = __ldg(words + r * nwords + (c0 >> 6));
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const float x = c < bits ? (((w >> (c & 63)) & 1ull) ? 1.0f : -1.0f) : 0.0f;
+    v[j] = __float2bfloat16_rn(x);
+  }
+  *reinterpret_cast<uint4*>(out + r * (int64_t)dpad + c0) = *reinterpret_cast<const uint4*>(v);
+}
+
+__global__ void __launch_bounds__(256) hamming_from_scores_kernel(const float* __restrict__ score, int64_t n, float bits,
+                                                                 float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const float s = score[t];
+  out[t] = s == -INFINITY ? INFINITY : (bits - s) * 0.5f;   // integers: exact
+}
+
 }  // namespace
+
+int launch_hamming_from_scores(const float* score, int64_t n, int bits, float* out, cudaStream_t stream) {
+  if (n == 0) return KNN_OK;
+  hamming_from_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(score, n, (float)bits, out);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+int launch_unpack_pm1(const uint64_t* words, int64_t n, int bits, int nwords, void* out, cudaStream_t stream) {
+  const int dpad = (bits + 7) & ~7;
+  const int64_t total = n * (dpad / 8);
+  if (total == 0) return KNN_OK;
+  unpack_pm1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(words, n, bits, nwords, dpad,
+                                                                        reinterpret_cast<__nv_bfloat16*>(out));
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
 
 int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream) {
   switch (p.kp) {

@@ -179,7 +179,8 @@ class FlatIndex:
         q, qsq = _prepare(queries.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
                           self.metric == "l2")
         mode = self_mode or ("exclude" if exclude_self else "keep")
-        if self.precision == "fp32" and exact_engine(q.shape[0], self.ntotal, self.dim, int(k)) == "tensor":
+        if self.precision == "fp32" and exact_engine(q.shape[0], self.ntotal, self.dim, int(k), self.device,
+                                                     self._filter is not None) == "tensor":
             if self._filter is None:
                 self._filter = ExactFilterRows.build(self.rows, self.sqnorm)
             return _search_exact_tensor(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
@@ -205,11 +206,16 @@ def _filter_k(k: int) -> int:
     return kc
 
 
-def exact_engine(nq: int, ng: int, d: int, k: int) -> str:
+def exact_engine(nq: int, ng: int, d: int, k: int, device=None, have_split: bool = False) -> str:
     """Which kernel family serves precision="fp32": "ffma" (search_f32.cu) or "tensor" (filter + re-score).
-    KNN_EXACT_ENGINE=ffma|tensor forces one (tests, measurements)."""
+    KNN_EXACT_ENGINE=ffma|tensor forces one (tests, measurements).  The tensor engine keeps a bf16 split of the gallery
+    (6 bytes per element next to the 4 of the fp32 rows): it is only chosen when that fits the device's free memory
+    (``device`` given and the split not built yet)."""
     forced = os.environ.get("KNN_EXACT_ENGINE", "")
     feasible = k <= L.MAX_FUSED_K and _filter_k(k) <= L.MAX_FUSED_K and nq > 0 and ng > 0
+    if feasible and device is not None and not have_split and torch.cuda.is_available():
+        free, _ = torch.cuda.mem_get_info(device)
+        feasible = 6 * ng * ((d + 7) // 8 * 8) + 6 * nq * d + (1 << 28) < 0.9 * free
     if forced == "ffma" or not feasible:
         return "ffma"
     if forced == "tensor":
@@ -423,7 +429,7 @@ def search(
         else:
             g, gsq = _prepare(gallery, normalize, precision, eps, eps_mode, want_sq)
         mode = self_mode or ("exclude" if exclude_self else "keep")
-        if precision == "fp32" and exact_engine(q.shape[0], g.shape[0], q.shape[1], int(k)) == "tensor":
+        if precision == "fp32" and exact_engine(q.shape[0], g.shape[0], q.shape[1], int(k), q.device) == "tensor":
             vals, idx = _search_exact_tensor(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
         else:
             vals, idx = _search_prepared(q, qsq, g, gsq, int(k), metric, mode, int(query_offset), 0)
@@ -460,24 +466,60 @@ def pack_bits(codes: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def unpack_bits_pm1(words: torch.Tensor, bits: int) -> torch.Tensor:
+    """Packed codes ``[N, ceil(bits/64)]`` int64 -> ``[N, dpad]`` bf16 rows of +1 / -1 (``knn_unpack_bits_pm1``)."""
+    _require_cuda(words)
+    words = words.contiguous()
+    n = words.shape[0]
+    out = torch.empty((n, (bits + 7) // 8 * 8), dtype=torch.bfloat16, device=words.device)
+    if n:
+        with torch.cuda.device(words.device):
+            rc = L.load().knn_unpack_bits_pm1(_ptr(words), n, int(bits), _ptr(out), _stream(words))
+        L.check(rc, "knn_unpack_bits_pm1")
+    return out
+
+
 def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: int, *, exclude_self: bool = False,
-                   query_offset: int = 0, packed: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+                   query_offset: int = 0, packed: bool = False, bits: Optional[int] = None,
+                   method: str = "auto") -> Tuple[torch.Tensor, torch.Tensor]:
     """Hamming ranking of binary codes: the fused form of ``(q[:, None, :] != g[None, :, :]).sum(2).float()`` +
     ``argsort(dim=1)[:, :k]`` (test_ath.py:80-100) -> (distances [Q,k] fp32 ascending, indices [Q,k] int64), ties by
     ascending gallery row.  Codes are 0/1 tensors ``[N, bits]`` (as ``(codes >= 0).float()``, test_ath.py:68), or
-    already packed words with ``packed=True``."""
+    already packed words with ``packed=True`` (then pass ``bits``; default 64 * words).
+
+    method: "popc" = xor + popcount over the packed words (``knn_search_hamming``; 8 bytes per 64 bits of gallery);
+    "mma" = the codes as +-1 bf16 rows through the tcgen05 kernels (``<q, g> = bits - 2 d``, exact); "auto" = mma for
+    batches of >= 32 queries (the popcount kernel is issue-bound there), popc below."""
     _require_cuda(query_codes, gallery_codes)
+    if method not in ("auto", "popc", "mma"):
+        raise ValueError("method must be 'auto', 'popc' or 'mma'")
     qw = query_codes.contiguous() if packed else pack_bits(query_codes)
     gw = gallery_codes.contiguous() if packed else (qw if gallery_codes is query_codes else pack_bits(gallery_codes))
     if qw.dtype != torch.int64 or gw.dtype != torch.int64 or qw.shape[1] != gw.shape[1]:
         raise ValueError("packed codes must be int64 words with the same number of words per row")
     nq, words = qw.shape
     ng = gw.shape[0]
+    nbits = int(bits) if bits is not None else (words * 64 if packed else int(query_codes.shape[1]))
+    if not (words - 1) * 64 < nbits <= words * 64:
+        raise ValueError(f"bits={nbits} does not match {words} words per code")
     if k < 1:
         raise ValueError("k must be >= 1")
     if k > L.MAX_FUSED_K:
         raise L.KnnError(f"Hamming search supports k <= {L.MAX_FUSED_K}")
     dev = qw.device
+    if method == "mma" or (method == "auto" and nq >= 32 and ng > 0):
+        q1 = unpack_bits_pm1(qw, nbits)
+        g1 = q1 if gw is qw else unpack_bits_pm1(gw, nbits)
+        score, idx = _search_prepared(q1, None, g1, None, int(k), "ip", "exclude" if exclude_self else "keep",
+                                      int(query_offset), 0)
+        # d = (bits - score) / 2: exact small integers; empty slots (score -inf) -> +inf like the popcount path
+        dist_out = torch.empty_like(score)
+        with torch.cuda.device(dev):
+            rc = L.load().knn_hamming_from_scores(_ptr(score), score.numel(), nbits, _ptr(dist_out), _stream(score))
+        L.check(rc, "knn_hamming_from_scores")
+        return dist_out, idx
+    if words not in (1, 2, 3, 4, 8):
+        raise L.KnnError(f"the popcount kernel is instantiated for 1, 2, 3, 4 or 8 words per code, got {words}")
     out_val = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
     if nq == 0:

@@ -147,6 +147,14 @@ KNN_API int knn_debug_stats(unsigned long long* out32_host, int reset);
  * knn_search_hamming: q/g packed words [rows, words] (words in 1, 2, 3, 4, 8); out_val = distance as fp32 ascending,
  * out_idx = gallery row (+index_base), ties by ascending gallery row; KNN_SELF_KEEP / KNN_SELF_EXCLUDE. */
 KNN_API int knn_pack_bits(const void* x, int64_t n, int bits, int in_dtype, void* out_words, void* stream);
+/* Packed codes -> rows of +1 / -1 in bf16, [n, dpad] with dpad = bits rounded up to 8 (padding columns 0): the
+ * operand form of the TENSOR-CORE Hamming search -- <q, g> = bits - 2 * hamming(q, g) exactly (integers far below
+ * 2^24), so knn_search(KNN_BF16, KNN_IP) over these rows ranks like knn_search_hamming, ties included, and
+ * distance = (bits - score) / 2.  For batches of >= 32 queries the popcount kernel is issue-bound; the MMA form is
+ * ~8x faster at 16x the gallery bytes. */
+KNN_API int knn_unpack_bits_pm1(const void* words, int64_t n, int bits, void* out_bf16, void* stream);
+/* out[i] = (bits - score[i]) / 2 (the Hamming distance behind a +-1 inner product; -inf = empty slot -> +inf). */
+KNN_API int knn_hamming_from_scores(const float* score, int64_t n, int bits, float* out, void* stream);
 KNN_API int knn_search_hamming(const void* q_words, const void* g_words, int64_t nq, int64_t ng, int words, int k,
                        int self_mode, int64_t self_offset, int64_t index_base,
                        float* out_val, int64_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);

@@ -47,11 +47,14 @@ def test_hamming_search_bit_exact(name, case):
     w = words.cpu().numpy().view(np.uint64)
     bit = ((w[:, :, None] >> np.arange(64, dtype=np.uint64)[None, None, :]) & np.uint64(1)).reshape(g.shape[0], -1)
     assert np.array_equal(bit[:, : case["bits"]].astype(np.float32), g) and not bit[:, case["bits"]:].any()
-    v, i = b200knn.search_hamming(tq, tg, 10)
-    assert np.array_equal(i.cpu().numpy(), ga[f"{name}_top10_idx"])       # integer distances: bit-exact, ties by row
-    assert np.array_equal(v.cpu().numpy(), ga[f"{name}_top10_dist"])
-    v2, i2 = b200knn.search_hamming(b200knn.pack_bits(tq), words, 10, packed=True)
-    assert torch.equal(i, i2) and torch.equal(v, v2)
+    for method in ("popc", "mma", "auto"):   # xor + popcount over packed words / +-1 rows on the tensor cores
+        v, i = b200knn.search_hamming(tq, tg, 10, method=method)
+        assert np.array_equal(i.cpu().numpy(), ga[f"{name}_top10_idx"])   # integer distances: bit-exact, ties by row
+        assert np.array_equal(v.cpu().numpy(), ga[f"{name}_top10_dist"])
+        v2, i2 = b200knn.search_hamming(b200knn.pack_bits(tq), words, 10, packed=True, method=method)
+        assert torch.equal(i, i2) and torch.equal(v, v2)
+        v3, i3 = b200knn.search_hamming(b200knn.pack_bits(tq)[:5], words, 10, packed=True, bits=case["bits"], method=method)
+        assert torch.equal(i[:5], i3) and torch.equal(v[:5], v3)
     # full metric dict through the reference-named entry point
     got = b200knn.metrics.compute_metrics(tq, torch.from_numpy(ql), tg, torch.from_numpy(gl), None, (1, 5, 10), True)
     d = hamming_oracle(q, g)
@@ -69,11 +72,14 @@ def test_hamming_self_exclusion_large_k_and_mass_ties():
     x = rs.randint(0, 2, size=(5000, 64)).astype(np.float32)
     x[100:400] = x[7]                                    # 300 identical codes: a block of exact ties
     t = torch.from_numpy(x).cuda()
-    v, i = b200knn.search_hamming(t[:300], t, 256, exclude_self=True)
     d = hamming_oracle(x[:300], x)
     d[np.arange(300), np.arange(300)] = np.inf
     order = np.argsort(d, axis=1, kind="stable")[:, :256]
-    assert np.array_equal(i.cpu().numpy(), order)
-    assert np.array_equal(v.cpu().numpy(), np.take_along_axis(d, order, 1))
+    for method in ("popc", "mma"):
+        v, i = b200knn.search_hamming(t[:300], t, 256, exclude_self=True, method=method)
+        assert np.array_equal(i.cpu().numpy(), order)
+        assert np.array_equal(v.cpu().numpy(), np.take_along_axis(d, order, 1))
+    v, i = b200knn.search_hamming(t[:3], t[:40], 64, method="mma")      # fewer rows than k: (+inf, -1) tail
+    assert (i.cpu().numpy()[:, 40:] == -1).all() and np.isposinf(v.cpu().numpy()[:, 40:]).all()
     v, i = b200knn.search_hamming(t[1000:1003], t, 5, exclude_self=True, query_offset=1000)
     assert not (i.cpu().numpy() == np.arange(1000, 1003)[:, None]).any()

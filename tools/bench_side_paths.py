@@ -100,12 +100,17 @@ def main():
     gw = torch.randint(-(2 ** 62), 2 ** 62, (ng, 1), generator=gen, device=dev, dtype=torch.int64)
     qw = torch.randint(-(2 ** 62), 2 ** 62, (nq, 1), generator=gen, device=dev, dtype=torch.int64)
     for nqq in (1, 128, 1024):
-        ms = timed(lambda: b200knn.search_hamming(qw[:nqq], gw, k, packed=True), args.steps)
-        print(json.dumps({"path": "hamming", "workload": f"{nqq} x {ng} x {bits}-bit codes, top-{k}", "ms_per_call": ms,
-                          "queries_per_s": nqq / (ms / 1e3), "kernel": "search_hamming_kernel",
-                          "pair_rate_G_per_s": nqq * ng / (ms / 1e3) / 1e9,
-                          "gallery_GBps": ng * 8 / (ms / 1e3) / 1e9,
-                          "note": "integer xor+popc, one thread per query row; issue-bound for >= 128 queries"}), flush=True)
+        for method in ("popc", "mma"):
+            ms = timed(lambda: b200knn.search_hamming(qw[:nqq], gw, k, packed=True, method=method), args.steps)
+            print(json.dumps({
+                "path": f"hamming/{method}", "workload": f"{nqq} x {ng} x {bits}-bit codes, top-{k}", "ms_per_call": ms,
+                "queries_per_s": nqq / (ms / 1e3),
+                "kernel": "search_hamming_kernel" if method == "popc" else "unpack_pm1 + tcgen05 bf16 search",
+                "pair_rate_G_per_s": nqq * ng / (ms / 1e3) / 1e9,
+                "note": ("integer xor+popc over packed words, one thread per query row; issue-bound for >= 128 queries"
+                         if method == "popc" else
+                         "codes as +-1 bf16 rows (16x the gallery bytes, expanded inside the timed call): "
+                         "<q, g> = bits - 2 d exactly")}), flush=True)
 
     # ---- score fusion ----------------------------------------------------------------------------------------
     n = 4096
