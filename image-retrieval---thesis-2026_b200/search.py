@@ -488,8 +488,8 @@ def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: in
     already packed words with ``packed=True`` (then pass ``bits``; default 64 * words).
 
     method: "popc" = xor + popcount over the packed words (``knn_search_hamming``; 8 bytes per 64 bits of gallery);
-    "mma" = the codes as +-1 bf16 rows through the tcgen05 kernels (``<q, g> = bits - 2 d``, exact); "auto" = mma for
-    batches of >= 32 queries (the popcount kernel is issue-bound there), popc below."""
+    "mma" = the codes as +-1 bf16 rows through the tcgen05 kernels (``<q, g> = bits - 2 d``, exact); "auto" = mma
+    whenever the expanded rows fit the device's free memory (measured faster at every batch size), else popc."""
     _require_cuda(query_codes, gallery_codes)
     if method not in ("auto", "popc", "mma"):
         raise ValueError("method must be 'auto', 'popc' or 'mma'")
@@ -507,7 +507,10 @@ def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: in
     if k > L.MAX_FUSED_K:
         raise L.KnnError(f"Hamming search supports k <= {L.MAX_FUSED_K}")
     dev = qw.device
-    if method == "mma" or (method == "auto" and nq >= 32 and ng > 0):
+    if method == "auto":   # the +-1 expansion (2 bytes per code bit) must fit comfortably; it wins at every batch size
+        free, _ = torch.cuda.mem_get_info(dev)
+        method = "mma" if ng > 0 and nq > 0 and 2 * (ng + nq) * ((nbits + 7) // 8 * 8) < 0.5 * free else "popc"
+    if method == "mma":
         q1 = unpack_bits_pm1(qw, nbits)
         g1 = q1 if gw is qw else unpack_bits_pm1(gw, nbits)
         score, idx = _search_prepared(q1, None, g1, None, int(k), "ip", "exclude" if exclude_self else "keep",
