@@ -34,7 +34,12 @@ def _worker(rank, world, port, out_dir):
     gen.manual_seed(5)                                   # same data on every rank
     failures = []
     for precision, nq, ng, d, k, metric in (("bf16", 300, 70_001, 128, 100, "cosine"), ("fp32", 64, 9_000, 96, 10, "l2"),
-                                            ("bf16", 1, 50_000, 768, 100, "cosine")):
+                                            ("bf16", 1, 50_000, 768, 100, "cosine"),
+                                            ("fp32-tensor", 300, 40_000, 128, 50, "cosine")):
+        os.environ.pop("KNN_EXACT_ENGINE", None)
+        if precision == "fp32-tensor":      # the tensor-core exact engine on every shard (split filter + proof)
+            os.environ["KNN_EXACT_ENGINE"] = "tensor"
+            precision = "fp32"
         g = b200knn.normalize(torch.randn((ng, d), generator=gen, device=dev))
         q = b200knn.normalize(torch.randn((nq, d), generator=gen, device=dev))
         g[17] = g[ng - 5]                                # a tie across the shard boundary
