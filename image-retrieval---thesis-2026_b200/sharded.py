@@ -64,6 +64,7 @@ class PeerExchange:
         self.buf = None
         self.hdl = None
         self.turn = 0
+        self._retired = []       # outgrown buffers stay mapped: a peer's merge may still be reading them
 
     def _ensure(self, words: int) -> None:
         if words <= self.capacity:
@@ -72,6 +73,8 @@ class PeerExchange:
 
         # the capacity must be identical on every rank: it only depends on (Q, k), which are
         cap = max(words, 1 << 16)
+        if self.buf is not None:
+            self._retired.append((self.buf, self.hdl))
         self.buf = symm_mem.empty((2 * cap,), dtype=torch.int32, device=self.device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.capacity = cap
