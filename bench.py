@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--gallery-rows", type=int, default=0, help="override the gallery size (debug only)")
     ap.add_argument("--queries", type=int, default=0, help="override the query batch (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true",
+                    help="instead of the headline line: per-stage GPU vs host-CPU timings (normalise / distance / "
+                         "ranking / each metric) for BASELINE configs 1-3, one JSON line each (bench_stages.py)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
                     help="N > 1: candidate exchange -- merge kernel reading the peers' symmetric-memory buffers over "
                          "NVLink (falls back to the all-gather if symmetric memory is unavailable), or NCCL all-gather")
@@ -175,6 +178,11 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.stages:
+        import bench_stages
+
+        bench_stages.run_stages()
         return
 
     import torch

@@ -135,10 +135,11 @@ def recall_at_k_from_topk(indices: torch.Tensor, qlabels, glabels, topk: Sequenc
     rel, _ = relevance_single(indices, qlabels, glabels)
     _, first, _, _ = ranked_stats(rel)
     nq = rel.shape[0]
+    first_np = first.cpu().numpy()                      # one read-back: rank of the first match settles every k
     res = []
     for k in topk:
-        correct_k = ((first > 0) & (first <= int(k))).sum(dtype=torch.float32)
-        res.append((correct_k * (100.0 / nq)).cpu())
+        correct_k = torch.tensor(float(((first_np > 0) & (first_np <= int(k))).sum()), dtype=torch.float32)
+        res.append(correct_k * (100.0 / nq))            # fp32, as `correct_k.sum(dtype=float32) * (100.0 / batch)`
     return res
 
 
