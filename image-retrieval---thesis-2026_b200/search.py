@@ -213,14 +213,15 @@ def exact_engine(nq: int, ng: int, d: int, k: int, device=None, have_split: bool
     (``device`` given and the split not built yet)."""
     forced = os.environ.get("KNN_EXACT_ENGINE", "")
     feasible = k <= L.MAX_FUSED_K and _filter_k(k) <= L.MAX_FUSED_K and nq > 0 and ng > 0
-    if feasible and device is not None and not have_split and torch.cuda.is_available():
-        free, _ = torch.cuda.mem_get_info(device)
-        feasible = 6 * ng * ((d + 7) // 8 * 8) + 6 * nq * d + (1 << 28) < 0.9 * free
     if forced == "ffma" or not feasible:
         return "ffma"
-    if forced == "tensor":
-        return "tensor"
-    return "tensor" if 2.0 * nq * ng * d >= _EXACT_MIN_FLOP else "ffma"
+    if forced != "tensor" and 2.0 * nq * ng * d < _EXACT_MIN_FLOP:
+        return "ffma"
+    if device is not None and not have_split and torch.cuda.is_available():   # (a driver query: only asked when it matters)
+        free, _ = torch.cuda.mem_get_info(device)
+        if 6 * ng * ((d + 7) // 8 * 8) + 6 * nq * d + (1 << 28) >= 0.9 * free:
+            return "ffma"
+    return "tensor"
 
 
 def rerun_ranges(bad_rows, nq: int, block: int = 128):
