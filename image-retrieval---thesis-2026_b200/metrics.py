@@ -611,3 +611,35 @@ def recall_at_k(binary_relevance, total_positives: int, k: int) -> float:
         return 0.0
     k = min(k, len(binary_relevance))
     return float(np.sum(binary_relevance[:k]) / total_positives)
+
+
+# --------------------------------------------------------------------------------------------------
+# The evaluation body of test.py:1077-1126 / test_nonclip.py:150-172 / eval_medsiglip.py:238-260 after the model forward
+# --------------------------------------------------------------------------------------------------
+def evaluate_embeddings(embeds: torch.Tensor, labels, metric: str = "l2", kappas=(1, 5, 10),
+                        k_values=(1, 5, 10, 15, 20), save_path: Optional[str] = None):
+    """What ``evaluate(model, loader, device, args)`` computes once the embeddings exist: ``dists = -cdist(e, e)``
+    (``metric="l2"``, test.py:1080) or ``e @ e.T`` (``"cosine"`` / ``"ip"``, test.py:1006, eval_medsiglip.py:238) with the
+    diagonal at -inf; R@K; the trapezoidal mAP and mP@K over the column-wise full ranking; majority-vote classification
+    metrics; optionally the ``np.savez`` bundle of test.py:1122-1126.
+    -> {"acc": float32 [len(kappas)], "mAP": float, "pr": float64 [len(kappas)], "classification": {k: {...}}}.
+    Dense in N (the reference's own formulation needs the full ranking); for large N use the top-k entry points."""
+    _require_cuda(embeds)
+    from .search import scores_dense
+
+    kappas, k_values = list(kappas), list(k_values)
+    if metric == "l2":
+        dists = -scores_dense(embeds, embeds, "l2", self_mode="exclude")          # -cdist, diagonal -inf
+    else:
+        dists = scores_dense(embeds, embeds, metric, self_mode="exclude")
+    lab = _dev_i64(labels, dists.device).view(-1)
+    ranks = rank_rows(dists.t().contiguous(), largest_first=True)                  # [nq, db]: argsort(dim=0) per query
+    acc = torch.stack(retrieval_accuracy(dists, lab, topk=kappas)).numpy()        # rows (topk dim=1), as test.py:44
+    mAP, _, pr, _ = compute_map(ranks.t(), lab, kappas)
+    classification = classification_metrics_from_topk(ranks[:, : max(k_values)].contiguous(), lab, lab, k_values)
+    out = {"acc": acc, "mAP": mAP, "pr": pr, "classification": classification}
+    if save_path is not None:
+        from .formats import save_evaluation_npz
+
+        save_evaluation_npz(save_path, embeds, lab, kappas, acc, mAP, pr, classification, dists=dists)
+    return out

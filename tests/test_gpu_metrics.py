@@ -87,6 +87,25 @@ def test_c1_cdist_pipeline(knn, c1, golden):
     assert abs(mAP - g["mAP"]) < 1e-6 and list(pr) == g["pr"]
 
 
+def test_evaluate_embeddings_is_the_reference_evaluate_body(knn, c1, golden, tmp_path):
+    """One call = test.py:1077-1126 after the forward pass, for both distance conventions, + the npz bundle."""
+    e, lab = c1
+    for metric, key in (("cosine", "c1_cosine"), ("l2", "c1_cdist")):
+        g = golden[key]
+        path = str(tmp_path / f"eval_{metric}.npz")
+        out = knn.metrics.evaluate_embeddings(e, dev(lab), metric, save_path=path)
+        assert out["acc"].dtype == np.float32 and [float(a) for a in out["acc"]] == g["acc"]
+        assert abs(out["mAP"] - g["mAP"]) < 1e-6 and list(out["pr"]) == g["pr"]
+        for k, d in g["classification"].items():
+            got = out["classification"][int(k)]
+            want = d if isinstance(d, dict) else dict(zip(got.keys(), d))   # cdist golden: values in the npz order
+            for m, v in want.items():
+                assert got[m] == pytest.approx(v, rel=1e-12), (k, m)
+        z = np.load(path, allow_pickle=True)
+        assert set(z.files) >= {"embeds", "labels", "dists", "kappas", "acc", "mAP", "pr", "classification_k_values"}
+        assert np.isposinf(np.diag(z["dists"])).all() and float(z["mAP"]) == out["mAP"]   # stored negated, as test.py:1123
+
+
 def test_c2_test_ath_compute_metrics(knn, golden):
     c = golden["cases"]["c2"]
     x, lab = synth.clustered(c["nq"] + c["ng"], c["d"], c["classes"], c["seed"], c["noise"], c["priors"])
