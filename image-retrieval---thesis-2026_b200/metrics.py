@@ -643,3 +643,21 @@ def evaluate_embeddings(embeds: torch.Tensor, labels, metric: str = "l2", kappas
 
         save_evaluation_npz(save_path, embeds, lab, kappas, acc, mAP, pr, classification, dists=dists)
     return out
+
+
+def evaluate_multilabel_embeddings(embeds: torch.Tensor, labels_multihot: torch.Tensor, thresholds=(0.25, 0.5),
+                                   k_values=(1, 5, 10, 15, 20), save_path: Optional[str] = None):
+    """What ``evaluate_multilabels`` (test.py:987-1062) computes once the embeddings exist: cosine self-retrieval,
+    mAP with Jaccard > t relevance for every t, and the Precision@K / Recall@K (hit-rate) table.  Never builds the
+    N x N matrix: the full-ranking AP runs on a k = N-1 search, the table on a top-max(k) search.
+    -> {"mAP": {t: float}, "precision_recall_at_k": {k: (precision %, recall %)}}; ``save_path`` writes the
+    ``embeds`` / ``labels`` bundle of test.py:1059-1061."""
+    _require_cuda(embeds)
+    lab = labels_multihot.to(embeds.device)
+    out = {"mAP": {float(t): compute_map_multilabel_from_embeddings(embeds, lab, float(t)) for t in thresholds}}
+    kmax = min(max(int(k) for k in k_values), embeds.shape[0] - 1)
+    _, idx = search(embeds, embeds, kmax, "cosine", normalize=True, exclude_self=True)
+    out["precision_recall_at_k"] = multilabel_hit_rate_from_topk(idx, lab, lab, k_values)
+    if save_path is not None:
+        np.savez(save_path, embeds=embeds.detach().cpu().numpy(), labels=lab.detach().cpu().numpy())
+    return out

@@ -149,6 +149,12 @@ def test_multilabel_self_retrieval_metrics(knn, golden):
         dense = knn.scores_dense(emb, emb, "cosine", normalize=True, self_mode="exclude")
         assert M.compute_map_multilabel(dense, tl, float(t)) == pytest.approx(v, rel=1e-12)
     assert M.evaluate_map_embeddings(emb, tl, 0.4) == pytest.approx(golden["ml_self_evaluate_map"], rel=1e-9)
+    whole = M.evaluate_multilabel_embeddings(emb, tl)                       # test.py:987-1062 in one call
+    for t, v in golden["ml_self_map_multilabel"].items():
+        assert whole["mAP"][float(t)] == pytest.approx(v, rel=1e-12)
+    for k, (p, r) in golden["ml_self_prk_printed"].items():
+        assert round(whole["precision_recall_at_k"][int(k)][0], 2) == p
+        assert round(whole["precision_recall_at_k"][int(k)][1], 2) == r
     _, idx = knn.search(emb, emb, 20, "cosine", normalize=True, exclude_self=True)
     hr = M.multilabel_hit_rate_from_topk(idx, tl, tl, (1, 5, 10, 15, 20))
     for k, (p, r) in golden["ml_self_prk_printed"].items():
