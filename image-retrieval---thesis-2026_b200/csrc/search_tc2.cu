@@ -147,8 +147,11 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       for (int t = 0; t < ntiles; ++t, col0 += TN) {
         for (int kb = 0; kb < nkb; ++kb) {
           if (cfg.prefetch > 0) {
-            if (pf_t < ntiles)
+            if (pf_t < ntiles) {
               ptx::tma_prefetch_2d(&tmap_g, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
+              if (kSplit)
+                ptx::tma_prefetch_2d(&tmap_g2, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
+            }
             if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
           }
           const long long c0 = stats_on ? clock64() : 0;
