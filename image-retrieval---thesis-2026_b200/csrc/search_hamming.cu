@@ -55,19 +55,33 @@ __global__ void __launch_bounds__(kRows, 4) search_hamming_kernel(SearchParams p
       gtile[i] = r < c_end ? __ldg(G + r * W + (i % W)) : 0ull;
     }
     __syncthreads();
-#pragma unroll 8
+    // Fast path in integers: 32 distances in registers, their minimum against the row's threshold distance.  Only a
+    // chunk that can contribute (min d <= d_k; always, until k candidates exist) takes the float / shared-memory
+    // route of the common selection code.
+    int dist[kChunk];
+    int dmin = 1 << 30;
+#pragma unroll
     for (int j = 0; j < kChunk; ++j) {
       int d = 0;
 #pragma unroll
       for (int w = 0; w < W; ++w) d += __popcll(qw[w] ^ gtile[j * W + w]);
-      srow[j] = -(float)d;
+      dist[j] = d;
+      dmin = min(dmin, d);
     }
     if ((col0 - c_begin) % (16 * kChunk) == 0) refresh_tau<false>(st, tau_row);
-    const int64_t rem = c_end - col0;
-    const uint32_t nvalid = rem >= kChunk ? (uint32_t)kChunk : (uint32_t)rem;
-    auto fv = [&](int j) -> float { return srow[j]; };
-    select_chunk_mem<false>(st, fv, srow, 4, 0.f, nullptr, (uint32_t)col0, nvalid, self_row, p.self_mode, row_valid);
-    warp_compact_if_needed<E, 32, false>(st, p.k, lane, tau_row);
+    // st.tau = -(k-th best distance) (or -inf): a row qualifies iff -d >= tau
+    const bool hit = row_valid && -(float)dmin >= st.ftau;
+    if (__any_sync(kFullMask, hit)) {
+      if (hit) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) srow[j] = -(float)dist[j];
+        const int64_t rem = c_end - col0;
+        const uint32_t nvalid = rem >= kChunk ? (uint32_t)kChunk : (uint32_t)rem;
+        auto fv = [&](int j) -> float { return srow[j]; };
+        select_chunk_mem<false>(st, fv, srow, 4, 0.f, nullptr, (uint32_t)col0, nvalid, self_row, p.self_mode, row_valid);
+      }
+      warp_compact_if_needed<E, 32, false>(st, p.k, lane, tau_row);
+    }
   }
   p.counts[unit * kRows + tid] = row_valid ? st.cnt : 0;
 }
