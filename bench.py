@@ -291,7 +291,8 @@ def main():
         total_ms = timed(step_resident, args.steps)
     launches = lib.knn_launch_count() - launches0            # counted by the library at every launch site
     kern_ms = []
-    for i in range(max(0, lib.knn_profile_count() - args.steps), lib.knn_profile_count()):
+    n_prof = lib.knn_profile_count()
+    for i in range(max(0, n_prof - min(args.steps, 48)), n_prof):     # the library keeps the last 64 calls
         sd, a, b = ctypes.c_float(), ctypes.c_float(), ctypes.c_float()
         _lib.check(lib.knn_profile_read(i, ctypes.byref(sd), ctypes.byref(a), ctypes.byref(b)), "knn_profile_read")
         kern_ms.append((a.value, b.value, sd.value))
