@@ -46,6 +46,17 @@ def test_argument_validation_without_a_device():
     assert rc == -1
     rc = lib.knn_merge_topk(None, None, 2, 4, 8, 0, None, None, None)
     assert rc == -1
+    # KNN_BF16X3 rows are three parts of a multiple of 8 columns
+    rc = lib.knn_search(None, None, None, None, 4, 4, 40, 2, 1, 0, 0, 0, 0, None, None, None, 0, None)
+    assert rc == -1 and b"KNN_BF16X3" in lib.knn_last_error()
+    assert lib.knn_search_workspace(300, 100000, 192, 2, 64) == lib.knn_search_workspace(300, 100000, 192, 1, 64)
+    rc = lib.knn_rescore_exact(None, None, None, None, 4, 4, 8, 0, 0, 0, 0, None, None, 8, 16, None, None, None, None, None)
+    assert rc == -1 and b"kc" in lib.knn_last_error()            # k must not exceed the candidate count
+    rc = lib.knn_lesion_rerank(None, None, 4, 10, 11, None, None, None, None, 4, 1, 8, 0.5, None, None, None, None)
+    assert rc == -1
+    rc = lib.knn_merge_topk_parts(None, None, 17, 4, 8, 0, None, None, None)
+    assert rc == -1
+    assert lib.knn_launch_count() >= 0
     assert lib.knn_search_workspace(0, 100, 8, 0, 10) == 0
     assert lib.knn_search_workspace(300, 100000, 64, 0, 100) > 0
     assert lib.knn_rank_rows_workspace(4, 100) == 0 and lib.knn_rank_rows_workspace(4, 5000) == 4 * 8192 * 8
