@@ -121,7 +121,7 @@ def test_observed_filter_error_is_far_inside_the_bound(knn):
     S = importlib.import_module("b200knn.search")
 
     rs = np.random.RandomState(21)
-    for d, positive in ((1024, True), (1024, False), (2048, True), (96, True), (1024, "tiny-tail")):
+    for d, positive in ((1024, True), (1024, False), (2048, True), (96, True), (1024, "tiny-tail"), (4096, "ulp-tail")):
         g = rs.standard_normal((20000, d)).astype(np.float32)
         q = rs.standard_normal((256, d)).astype(np.float32)
         if positive == "tiny-tail":
@@ -129,6 +129,13 @@ def test_observed_filter_error_is_far_inside_the_bound(knn):
             # drops every one of them, a wider accumulator keeps them -- the largest chain-vs-filter gap by design
             g = np.full((20000, d), 2.0 ** -12, dtype=np.float32) * rs.uniform(0.9, 1.0, (20000, d)).astype(np.float32)
             q = np.full((256, d), 2.0 ** -12, dtype=np.float32) * rs.uniform(0.9, 1.0, (256, d)).astype(np.float32)
+            g[:, 0], q[:, 0] = 1.0, 1.0
+        elif positive == "ulp-tail":
+            # one unit term, then d - 1 products just BELOW one ulp of the running sum: the chain (round to nearest)
+            # keeps every one, an accumulator that truncated each product to the sum's ulp would keep none -- the
+            # worst case for the tensor cores' side of the bound
+            q = np.full((256, d), 2.0 ** -11, dtype=np.float32)
+            g = (0.99 * 2.0 ** -12 * rs.uniform(0.98, 1.0, (20000, d))).astype(np.float32)
             g[:, 0], q[:, 0] = 1.0, 1.0
         elif positive:
             g, q = np.abs(g), np.abs(q)
