@@ -138,17 +138,23 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_numbers(nq_total, ng_total, d, k, steps=1, warmup=1):
-    """Bounded sample of the workload on the host cores -> (q/s extrapolated to the full gallery, dict)."""
+def cpu_reference_numbers(nq_total, ng_total, d, k, steps=None, warmup=1):
+    """Bounded sample of the workload on the host cores -> (q/s extrapolated to the full gallery, dict).
+    steps=None: about 10 s of CPU work (the sample pass repeated, at most 20 times) -- the default arm's cpu_baseline;
+    the --impl reference arm passes its own --steps / --warmup."""
     from oracle import cpu_baseline
 
     sq, sg = min(nq_total, 1024), min(ng_total, 1_000_000)
+    if steps is None:
+        first, threads = cpu_baseline.time_reference(sq, sg, d, k, steps=1, warmup=warmup)
+        steps = max(1, min(20, int(10.0 / max(first, 1e-3))))
+        warmup = 0
     sec, threads = cpu_baseline.time_reference(sq, sg, d, k, steps=steps, warmup=warmup)
     factor = ng_total / sg
     qps = sq / (sec * factor)
     info = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-            "sample": f"{sq} queries x {sg} rows x {d}-d fp32, F.normalize+mm+topk({k}) (test.py:1005-1006,44) in "
-                      f"{sec:.3f} s; x{factor:g} rows extrapolated linearly"}
+            "sample": f"{sq} queries x {sg} rows x {d}-d fp32, F.normalize+mm+topk({k}) (test.py:1005-1006,44): "
+                      f"{sec:.3f} s per pass, mean of {steps} passes; x{factor:g} rows extrapolated linearly"}
     return qps, sec, info
 
 
