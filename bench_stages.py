@@ -13,8 +13,6 @@ from __future__ import annotations
 import json
 import time
 
-import numpy as np
-
 
 def _gpu_ms(fn, reps=20, warmup=3):
     import torch

@@ -5,8 +5,8 @@ Drop-in for the query x gallery similarity-search hot path of CrispyChillies/Ima
 ``image-retrieval---thesis-2026_b200/``; it is importable as ``b200knn`` through the shim next to it.
 """
 from ._lib import KnnError, LIB_PATH, load as load_library
-from .search import (FlatIndex, merge_topk, normalize, pack_bits, rank_rows, row_sqnorm, scores_dense, search,
-                     search_hamming)
+from .search import (FlatIndex, merge_topk, merge_topk_parts, normalize, pack_bits, rank_rows, row_sqnorm,
+                     scores_dense, search, search_hamming, split_bf16x3, unpack_bits_pm1)
 from . import metrics
 from . import fusion
 from . import collection
@@ -15,5 +15,6 @@ from .sharded import ShardedFlatIndex
 
 __all__ = [
     "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
-    "pack_bits", "rank_rows", "row_sqnorm", "scores_dense", "search", "search_hamming", "metrics", "fusion", "collection", "formats",
+    "merge_topk_parts", "pack_bits", "rank_rows", "row_sqnorm", "scores_dense", "search", "search_hamming",
+    "split_bf16x3", "unpack_bits_pm1", "metrics", "fusion", "collection", "formats",
 ]

@@ -13,9 +13,8 @@ from __future__ import annotations
 
 import csv
 import json
-import os
 from pathlib import Path
-from typing import Any, Dict, Iterable, List, Mapping, Optional, Sequence
+from typing import Any, Dict, List, Mapping, Sequence
 
 import numpy as np
 

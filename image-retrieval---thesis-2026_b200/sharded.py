@@ -14,7 +14,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .search import FlatIndex, merge_topk
+from .search import FlatIndex
 
 
 def shard_rows(n_total: int, world_size: int) -> List[Tuple[int, int]]:
