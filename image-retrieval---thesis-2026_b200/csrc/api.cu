@@ -131,7 +131,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // [rows, d] bf16 row-major -> 2-D tensor map with a {64 elements, box_rows} box and 128-byte swizzle (the layout
 // the UMMA shared-memory descriptors of ptx.cuh expect).  Rows past the end read as zeros.
-int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch) {
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch,
+                        int box_cols) {
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -145,10 +146,11 @@ int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d,
   }
   cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)(pitch > 0 ? pitch : d) * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld d=%d)", (int)r, (long long)rows, d);

@@ -61,7 +61,8 @@ int launch_pack_bits(const void* x, int dtype, int64_t n, int bits, int words, u
 
 // [rows, d] bf16 row-major -> tensor map with a {64, box_rows} box, 128-byte swizzle (api.cu)
 // pitch = elements between consecutive rows (0: d) -- a map over a column range of wider rows reads zeros past d
-int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch = 0);
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int d, int box_rows, int64_t pitch = 0,
+                        int box_cols = 64);   // box_cols 64 -> 128-byte swizzle, 32 -> 64-byte swizzle
 
 // Diagnostics (KNN_PAIR_STATS=1): 32 device counters the tcgen05 kernels add stall cycles to; nullptr when off.
 unsigned long long* debug_stats_buffer();

@@ -338,6 +338,15 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t lo) {
   return d;
 }
 
+// 64-byte swizzle, K-major (tile rows of 32 bf16 = 64 B, 8-row groups 512 B apart): the finer k-block of the split
+// filter's ring.  Same two-word form as sw128_desc.
+__device__ __forceinline__ uint64_t sw64_desc(uint32_t lo) {
+  constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO 512 B, version 1, layout SWIZZLE_64B
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4)                 // D format  F32

@@ -61,7 +61,9 @@ struct PairCfg {
 // qhi.ghi + qlo.ghi + qhi.glo: every ring stage holds the hi AND lo k-blocks of both operands (4 x 16 KB per CTA,
 // tmap_q / tmap_g = hi parts, tmap_q2 / tmap_g2 = lo parts) and feeds 12 MMAs, so each part crosses L2 -> SM once
 // per tile instead of once per product (as plain bf16 rows of 3x the width the kernel is L2 -> SM bound: 64 B/cycle/SM).
-template <int E, bool kL2, bool kDiag, bool kSplit>
+// kSplit = 0 (plain rows), 64 or 32 = elements per k-block in split mode (32: 64-byte swizzle, stages of 32 KB, so the
+// ring is 7 deep instead of 3 -- 192 KB in flight instead of 128 KB).
+template <int E, bool kL2, bool kDiag, int kSplit>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                         const __grid_constant__ CUtensorMap tmap_q2, const __grid_constant__ CUtensorMap tmap_g2,
@@ -148,9 +150,10 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int kb = 0; kb < nkb; ++kb) {
           if (cfg.prefetch > 0) {
             if (pf_t < ntiles) {
-              ptx::tma_prefetch_2d(&tmap_g, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
+              ptx::tma_prefetch_2d(&tmap_g, pf_kb * (kSplit ? kSplit : BKE),
+                                   (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
               if (kSplit)
-                ptx::tma_prefetch_2d(&tmap_g2, pf_kb * BKE, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
+                ptx::tma_prefetch_2d(&tmap_g2, pf_kb * kSplit, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
             }
             if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
           }
@@ -159,11 +162,13 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           if (stats_on) w_empty += clock64() - c0;
           const uint32_t dst = ring_u32 + (uint32_t)stage * cfg.stage_bytes;
           const uint32_t full_bar = full0 + (uint32_t)stage * 8u;
-          ptx::tma_load_2d_2sm_u32(dst, &tmap_g, full_bar, kb * BKE, col0, ptx::kEvictNormal);
+          constexpr int kBk = kSplit ? kSplit : BKE;                 // elements per k-block
+          constexpr uint32_t kKb = (uint32_t)(TM * kBk * 2);         // bytes of one 128-row k-block
+          ptx::tma_load_2d_2sm_u32(dst, &tmap_g, full_bar, kb * kBk, col0, ptx::kEvictNormal);
           if (kSplit) {  // stage = {G hi, G lo, Q hi, Q lo}
-            ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_g2, full_bar, kb * BKE, col0, ptx::kEvictNormal);
-            ptx::tma_load_2d_2sm_u32(dst + 2 * KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
-            ptx::tma_load_2d_2sm_u32(dst + 3 * KB_BYTES, &tmap_q2, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
+            ptx::tma_load_2d_2sm_u32(dst + kKb, &tmap_g2, full_bar, kb * kBk, col0, ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm_u32(dst + 2 * kKb, &tmap_q, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
+            ptx::tma_load_2d_2sm_u32(dst + 3 * kKb, &tmap_q2, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
           } else if (!cfg.resident)
             ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
           if (leader) ptx::mbar_arrive_expect_tx_u32(full_bar, tx_bytes);
@@ -207,23 +212,24 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           if (stats_on) w_full += clock64() - c0;
           if (issuer) {
             if (kSplit) {
-              constexpr uint32_t kPart = KB_BYTES >> 4;  // descriptor units between the parts of a stage
+              constexpr int kBk = kSplit ? kSplit : BKE;
+              constexpr uint32_t kPart = (uint32_t)(TM * kBk * 2) >> 4;  // descriptor units between the parts of a stage
+              auto desc = [](uint32_t lo) { return kSplit == 32 ? ptx::sw64_desc(lo) : ptx::sw128_desc(lo); };
 #pragma unroll
-              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_hi . g_hi
+              for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_hi . g_hi
                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 2 * kPart + ko), ptx::sw128_desc(b_lo + ko), idesc,
+                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 2 * kPart + ko), desc(b_lo + ko), idesc,
                                      (k != 0 || kb != 0) ? 1u : 0u);
               }
 #pragma unroll
-              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_lo . g_hi
+              for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_lo . g_hi
                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 3 * kPart + ko), ptx::sw128_desc(b_lo + ko), idesc, 1u);
+                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 3 * kPart + ko), desc(b_lo + ko), idesc, 1u);
               }
 #pragma unroll
-              for (int k = 0; k < BKE / UMMA_K; ++k) {   // q_hi . g_lo
+              for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_hi . g_lo
                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, ptx::sw128_desc(b_lo + 2 * kPart + ko), ptx::sw128_desc(b_lo + kPart + ko), idesc,
-                                     1u);
+                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 2 * kPart + ko), desc(b_lo + kPart + ko), idesc, 1u);
               }
             } else {
               const uint32_t a_lo = cfg.resident ? a_res : b_lo + (KB_BYTES >> 4);
@@ -326,20 +332,22 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   }
 }
 
-template <int E, bool kSplit>
+template <int E, int kSplit>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
   CUtensorMap tq, tg, tq2, tg2;
   const int dpart = kSplit ? p.d / 3 : p.d;  // columns of one operand part
-  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, dpart, TM, p.d);
+  constexpr int kBk = kSplit ? kSplit : BKE;  // elements per k-block (32: 64-byte swizzle)
+  constexpr uint32_t kKb = (uint32_t)(TM * kBk * 2);
+  int rc = make_tmap_bf16_rows(&tq, p.q, p.nq, dpart, TM, p.d, kBk);
   if (rc != KNN_OK) return rc;
-  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, dpart, TNH, p.d);
+  rc = make_tmap_bf16_rows(&tg, p.g, p.ng, dpart, TNH, p.d, kBk);
   if (rc != KNN_OK) return rc;
   if (kSplit) {  // queries [hi | lo | hi], gallery [hi | hi | lo]: the lo parts
     const __nv_bfloat16* qb = reinterpret_cast<const __nv_bfloat16*>(p.q);
     const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(p.g);
-    rc = make_tmap_bf16_rows(&tq2, qb + dpart, p.nq, dpart, TM, p.d);
+    rc = make_tmap_bf16_rows(&tq2, qb + dpart, p.nq, dpart, TM, p.d, kBk);
     if (rc != KNN_OK) return rc;
-    rc = make_tmap_bf16_rows(&tg2, gb + 2 * dpart, p.ng, dpart, TNH, p.d);
+    rc = make_tmap_bf16_rows(&tg2, gb + 2 * dpart, p.ng, dpart, TNH, p.d, kBk);
     if (rc != KNN_OK) return rc;
   } else {
     tq2 = tq;
@@ -347,11 +355,11 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   }
 
   PairCfg cfg;
-  cfg.nkb = (dpart + BKE - 1) / BKE;
+  cfg.nkb = (dpart + kBk - 1) / kBk;
   const size_t fixed = sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
   cfg.resident = (!kSplit && (size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
   cfg.a_bytes = cfg.resident ? (uint32_t)cfg.nkb * KB_BYTES : 0u;
-  cfg.stage_bytes = kSplit ? 4 * KB_BYTES : (cfg.resident ? KB_BYTES : 2 * KB_BYTES);
+  cfg.stage_bytes = kSplit ? 4 * kKb : (cfg.resident ? KB_BYTES : 2 * KB_BYTES);
   int stages = (int)((kSmemBudget - fixed - cfg.a_bytes) / cfg.stage_bytes);
   cfg.stages = stages > kMaxStages ? kMaxStages : stages;
   cfg.debug = 0;
@@ -386,7 +394,13 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
 
 template <int E>
 int launch_e(const SearchParams& p, cudaStream_t stream) {
-  return p.split3 ? launch_e<E, true>(p, stream) : launch_e<E, false>(p, stream);
+  static const int split_bk = [] {
+    const char* e = getenv("KNN_SPLIT_BK");   // 64 | 32: k-block width of the split filter (experiment knob)
+    const int v = e ? atoi(e) : 0;
+    return v == 32 ? 32 : 64;
+  }();
+  if (!p.split3) return launch_e<E, 0>(p, stream);
+  return split_bk == 32 ? launch_e<E, 32>(p, stream) : launch_e<E, 64>(p, stream);
 }
 
 }  // namespace
