@@ -233,10 +233,12 @@ constexpr int kTwoPhaseMaxRows = 1024;  // up to 8 query blocks: one merge CTA p
 constexpr int kTwoPhaseMinLists = 16;
 constexpr int kPreCap = 2048;           // keys per row the pre-filter may gather (more: the merge re-reads the lists)
 struct WsLayout {
-  size_t tau_bytes, precount_bytes, counts_bytes, lists_bytes, pre_bytes, maxima_bytes;
+  size_t tau_bytes, precount_bytes, counts_bytes, lists_bytes, pre_bytes, maxima_bytes, progress_bytes;
   int pre_cap;        // 0: one-phase merge
   bool seed_maxima;   // threshold seeding from list maxima
-  size_t total() const { return tau_bytes + precount_bytes + counts_bytes + lists_bytes + pre_bytes + maxima_bytes; }
+  size_t total() const {
+    return tau_bytes + precount_bytes + counts_bytes + lists_bytes + pre_bytes + maxima_bytes + progress_bytes;
+  }
 };
 static WsLayout ws_layout(const SearchGeom& g, int k) {
   WsLayout w;
@@ -257,6 +259,9 @@ static WsLayout ws_layout(const SearchGeom& g, int k) {
   const int mx = (w.seed_maxima ? seed_lists : 0) > (main_maxima ? main_lists : 0) ? seed_lists
                                                                                     : (main_maxima ? main_lists : 0);
   w.maxima_bytes = mx > 0 ? align_up(rows * (size_t)mx * sizeof(uint32_t), 256) : 0;
+  // soft lock-step of the CTA pairs sharing a gallery range (pair kernel: several query blocks)
+  w.progress_bytes = g.qblocks > 1 ? align_up((size_t)(g.splits > 0 ? g.splits : 1) * (g.qblocks / 2 + 1) * sizeof(int32_t), 256)
+                                   : 0;
   return w;
 }
 
@@ -330,6 +335,14 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.maxima = wl.maxima_bytes ? reinterpret_cast<uint32_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes +
                                                            wl.lists_bytes + wl.pre_bytes)
                              : nullptr;
+  static const int lockstep = [] {
+    const char* e = getenv("KNN_PAIR_LOCKSTEP");   // window in tiles (default 32), 0 = off
+    return e ? atoi(e) : 32;
+  }();
+  p.progress = (lockstep > 0 && wl.progress_bytes && dtype == KNN_BF16)
+                   ? reinterpret_cast<int32_t*>(wsb + wl.tau_bytes + wl.precount_bytes + wl.counts_bytes + wl.lists_bytes +
+                                                wl.pre_bytes + wl.maxima_bytes)
+                   : nullptr;
   const size_t tau_bytes = wl.tau_bytes + wl.precount_bytes;   // thresholds and pre-filter counts: zeroed together
   p.dense_out = nullptr;
 
@@ -344,8 +357,10 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
     if (prof) KNN_CHECK_CUDA(cudaEventRecord(pev[0], s));
     // Threshold seeding (see seed_geometry): search the sample into the scratch lists, merge in seeding mode.
     // The sample's candidates are discarded -- the main pass visits those rows again.
+    if (p.progress) KNN_CHECK_CUDA(cudaMemsetAsync(p.progress, 0xFF, wl.progress_bytes, s));   // -1 = not started
     if (geo.seed_splits > 0) {
       SearchParams ps = p;
+      ps.progress = nullptr;
       ps.ng = (int64_t)geo.seed_splits * geo.seed_len;
       ps.splits = geo.seed_splits;
       ps.split_len = geo.seed_len;

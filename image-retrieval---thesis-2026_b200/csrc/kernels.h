@@ -30,6 +30,8 @@ struct SearchParams {
   int32_t* precount;     // [qblocks*128] keys the pre-filter found (may exceed pre_cap: the merge then re-reads the lists)
   int pre_cap;
   uint32_t* maxima;      // [qblocks*128][splits*groups] best score of every list (threshold seeding from list maxima)
+  int32_t* progress;     // [splits][qblocks/2] tile index every CTA pair last published (soft lock-step of the pairs that
+                         // stream the same gallery range, pair kernel only); -1 = not started; nullptr = off
   float* dense_out;      // dense mode only
   double* stats_out;     // statistics mode only: [splits][qblocks][128][4] = sum, sum of squares, min, max
 };

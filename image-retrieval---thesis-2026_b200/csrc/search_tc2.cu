@@ -53,6 +53,8 @@ struct PairCfg {
   int debug;             // measurement knob (KNN_PAIR_DEBUG=1): the epilogue skips the selection (results are
                          // garbage; isolates the TMA + MMA pipeline in timing experiments); 2 = fast path only
   int prefetch;          // L2 prefetch distance of the gallery stream in k-blocks (0 = off)
+  int lockstep;          // soft lock-step window in tiles (0 = off), see SearchParams::progress
+  int lock_ignore;       // peers further behind than this many tiles are late starters: not waited for
   unsigned long long* stats;  // diagnostics (KNN_PAIR_STATS=1): stall-cycle counters, see knn_debug_stats()
 };
 
@@ -145,8 +147,27 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           ptx::tma_prefetch_2d(&tmap_g, (i % nkb) * BKE,
                                (int32_t)(c_begin + (int64_t)(i / nkb) * TN + (int64_t)rank * TNH));
       }
+      // Soft lock-step: the pairs of one gallery split start together and stream the same rows; nothing keeps them
+      // together, and once they drift further apart than L2 holds the gallery is re-read from HBM (2.6-3.8 x).  Every
+      // 16 tiles the leader publishes its tile index and waits (bounded) while it is more than `lockstep` tiles ahead
+      // of the slowest STARTED peer of its split that is not hopelessly behind (a late starter of a later wave).
+      int32_t* prog = (leader && cfg.lockstep > 0 && p.progress != nullptr)
+                          ? p.progress + (int64_t)sp * (p.qblocks / 2 + 1) : nullptr;
+      const int npairs = p.qblocks / 2, my_pair = qb >> 1;
       int32_t col0 = (int32_t)(c_begin + (int64_t)rank * TNH);
       for (int t = 0; t < ntiles; ++t, col0 += TN) {
+        if (prog != nullptr && (t & 15) == 0) {
+          *reinterpret_cast<volatile int32_t*>(prog + my_pair) = t;
+          for (int spin = 0; spin < 4000; ++spin) {
+            int mn = t;
+            for (int pp = 0; pp < npairs; ++pp) {
+              const int v = *reinterpret_cast<volatile int32_t*>(prog + pp);
+              if (v >= 0 && v >= t - cfg.lock_ignore && v < mn) mn = v;   // further behind: a late starter
+            }
+            if (t - mn <= cfg.lockstep) break;
+            __nanosleep(256);
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           if (cfg.prefetch > 0) {
             if (pf_t < ntiles) {
@@ -176,6 +197,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (prog != nullptr) *reinterpret_cast<volatile int32_t*>(prog + my_pair) = 0x7FFFFFFF;   // finished
       if (stats_on) atomicAdd(cfg.stats + 7, (unsigned long long)w_empty);
     }
   } else if (warp == 1) {
@@ -367,6 +389,21 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   cfg.stats = debug_stats_buffer();
   cfg.prefetch = 0;
   if (const char* e = getenv("KNN_PAIR_PREFETCH")) cfg.prefetch = atoi(e);
+  // soft lock-step (see the producer loop): only when all pairs of a gallery split can be co-resident and the units are
+  // long enough to drift (measured: 8192 x 50 M x 512 DRAM reads 131-195 GB -> 75 GB, +5 % throughput through the
+  // higher clock under the power cap; 25 000 queries = 98 pairs per split on 74 pair slots: 25 % slower if forced)
+  cfg.lockstep = 32;
+  if (const char* e = getenv("KNN_PAIR_LOCKSTEP")) cfg.lockstep = atoi(e);
+  {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t unit_tiles = (p.split_len + TN - 1) / TN;
+    // units must be much longer than the "late starter" distance below: a pair that begins when an earlier CTA of its
+    // split finishes must look hopelessly behind to the pairs still running, or they would wait for it
+    if (p.qblocks > sms || unit_tiles < 2048 || p.progress == nullptr) cfg.lockstep = 0;
+  }
+  cfg.lock_ignore = 1024;
+  if (const char* e = getenv("KNN_PAIR_LOCKSTEP_IGNORE")) cfg.lock_ignore = atoi(e);
   if (const char* e = getenv("KNN_PAIR_STAGES")) {
     const int want = atoi(e);
     if (want >= 2 && want < cfg.stages) cfg.stages = want;
