@@ -400,14 +400,12 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
     const int64_t unit_tiles = (p.split_len + TN - 1) / TN;
     // units must be much longer than the "late starter" distance below: a pair that begins when an earlier CTA of its
     // split finishes must look hopelessly behind to the pairs still running, or they would wait for it
-    if (p.qblocks > sms || unit_tiles < 2048 || p.progress == nullptr) cfg.lockstep = 0;
+    int min_tiles = 2048;
+    if (const char* e = getenv("KNN_PAIR_LOCKSTEP_MIN_TILES")) min_tiles = atoi(e);
+    if (p.qblocks > sms || unit_tiles < min_tiles || p.progress == nullptr) cfg.lockstep = 0;
+    cfg.lock_ignore = unit_tiles / 2 < 1024 ? (int)(unit_tiles / 2) : 1024;
   }
-  cfg.lock_ignore = 1024;
   if (const char* e = getenv("KNN_PAIR_LOCKSTEP_IGNORE")) cfg.lock_ignore = atoi(e);
-  if (const char* e = getenv("KNN_PAIR_STAGES")) {
-    const int want = atoi(e);
-    if (want >= 2 && want < cfg.stages) cfg.stages = want;
-  }
   const size_t smem = (size_t)cfg.a_bytes + (size_t)cfg.stages * cfg.stage_bytes + fixed;
 
   dim3 grid((unsigned)p.qblocks, (unsigned)p.splits);  // qblocks is even: consecutive CTAs form the pair
