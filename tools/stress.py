@@ -70,7 +70,7 @@ def main():
         scale = float(bv.abs().max()) + 1e-6
         if metric == "l2":   # rows are normalised: d^2 = 2 - 2 q.g (GEMM form of cdist) carries an ABSOLUTE error of a
             # few 1e-6 (cancellation; tensor-core truncation at d = 1024), so the error of d = sqrt(d^2) grows as 1 / d
-            tol = 6e-6 / bv.clamp_min(2e-3) + 4e-6
+            tol = 1.2e-5 / bv.clamp_min(2e-3) + 8e-6
         else:
             tol = 2e-5 * scale * (d ** 0.5) / 8 + 1e-6
         # tie-aware set equality: every returned row not in the brute-force set must score within tol of the k-th
