@@ -217,10 +217,13 @@ def exact_engine(nq: int, ng: int, d: int, k: int, device=None, have_split: bool
         return "ffma"
     if forced != "tensor" and 2.0 * nq * ng * d < _EXACT_MIN_FLOP:
         return "ffma"
-    if device is not None and not have_split and torch.cuda.is_available():   # (a driver query: only asked when it matters)
-        free, _ = torch.cuda.mem_get_info(device)
-        if 6 * ng * ((d + 7) // 8 * 8) + 6 * nq * d + (1 << 28) >= 0.9 * free:
-            return "ffma"
+    if device is not None and not have_split and torch.cuda.is_available():
+        need = 6 * ng * ((d + 7) // 8 * 8) + 6 * nq * d + (1 << 28)
+        # cudaMemGetInfo costs ~1 ms: only asked when the split is a sizeable part of the device memory
+        if need > torch.cuda.get_device_properties(device).total_memory // 16:
+            free, _ = torch.cuda.mem_get_info(device)
+            if need >= 0.9 * free:
+                return "ffma"
     return "tensor"
 
 
@@ -509,8 +512,9 @@ def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: in
         raise L.KnnError(f"Hamming search supports k <= {L.MAX_FUSED_K}")
     dev = qw.device
     if method == "auto":   # the +-1 expansion (2 bytes per code bit) must fit comfortably; it wins at every batch size
-        free, _ = torch.cuda.mem_get_info(dev)
-        method = "mma" if ng > 0 and nq > 0 and 2 * (ng + nq) * ((nbits + 7) // 8 * 8) < 0.5 * free else "popc"
+        need = 2 * (ng + nq) * ((nbits + 7) // 8 * 8)
+        fits = need < torch.cuda.get_device_properties(dev).total_memory // 16 or need < 0.5 * torch.cuda.mem_get_info(dev)[0]
+        method = "mma" if ng > 0 and nq > 0 and fits else "popc"
     if method == "mma":
         q1 = unpack_bits_pm1(qw, nbits)
         g1 = q1 if gw is qw else unpack_bits_pm1(gw, nbits)
