@@ -311,3 +311,100 @@ def fusion_evaluate_retrieval_metrics(full_idx: np.ndarray, labels: Sequence, k_
         m[f"mP@{k}"] = float(np.mean(P[k]) * 100.0)
         m[f"R@{k}"] = float(np.mean(R[k]) * 100.0)
     return m
+
+
+# ---- D12 --------------------------------------------------------------------------------------
+def medsiglip_evaluate_retrieval(topk_idx: np.ndarray, labels: np.ndarray, topk_values) -> Dict[str, float]:
+    """evaluate_medsiglip.py:142-163 from the row-wise ranking of ``f @ f.T`` with the diagonal at -1 [n, >= max k]:
+    R@k any-hit, majority by np.unique + argmax (smallest label on ties), accuracy and macro F1 in percent."""
+    from sklearn.metrics import accuracy_score, f1_score
+
+    out = {}
+    for k in topk_values:
+        retrieved = labels[topk_idx[:, :k]]
+        hit = (retrieved == labels[:, None]).any(axis=1).mean() * 100.0
+        majority = np.array([majority_vote(row.tolist(), tie="smallest") for row in retrieved])
+        out[f"r_at_{k}"] = float(hit)
+        out[f"majority_accuracy_at_{k}"] = accuracy_score(labels, majority) * 100.0
+        out[f"majority_macro_f1_at_{k}"] = f1_score(labels, majority, average="macro") * 100.0
+    return out
+
+
+# ---- D10' -------------------------------------------------------------------------------------
+def ath_train_retrieval_metrics(sorted_idx: np.ndarray, qlabels: np.ndarray, glabels: np.ndarray, topk_values):
+    """train_ath.py:171-218 from the ascending-distance ranking: mhr, map, mrr and majority accuracy with torch.mode
+    (smallest label on ties)."""
+    full = ath_compute_metrics(sorted_idx, qlabels, glabels, topk_values)
+    out = {}
+    for topk in topk_values:
+        vote = [float(majority_vote(glabels[sorted_idx[r, :topk]].tolist(), tie="smallest") == int(l))
+                for r, l in enumerate(qlabels)]
+        out[topk] = {"mhr": full[topk]["mhr"], "map": full[topk]["map"], "mrr": full[topk]["mrr"],
+                     "majority_acc": float(np.mean(vote))}
+    return out
+
+
+# ---- D14 --------------------------------------------------------------------------------------
+def chestmir_accuracy_from_ranks(ranks_rowmajor: np.ndarray, labels: np.ndarray, topk) -> np.ndarray:
+    """chestmir_eval.py:262-272 with the ranking given row-major [n, >= max k] (the reference indexes columns)."""
+    n = len(labels)
+    return np.array([(sum(bool(np.any(labels[ranks_rowmajor[i, :k]] == labels[i])) for i in range(n)) * 100.0) / max(1, n)
+                     for k in topk], dtype=np.float64)
+
+
+def chestmir_classification_from_ranks(labels: np.ndarray, ranks_rowmajor: np.ndarray, k_values):
+    """chestmir_eval.py:191-259: Counter majority vote + hand-rolled per-class P / R / F1 (f1 = 2pr / (p + r))."""
+    out = {}
+    n = len(labels)
+    for k in k_values:
+        y_pred = np.asarray([majority_vote(labels[ranks_rowmajor[i, :k]].tolist()) for i in range(n)], dtype=object)
+        y_true = np.asarray(list(labels), dtype=object)
+        classes = np.unique(np.concatenate([y_true, y_pred], axis=0))
+        P, R, F, S = [], [], [], []
+        for c in classes:
+            tp = int(np.sum((y_true == c) & (y_pred == c)))
+            fp = int(np.sum((y_true != c) & (y_pred == c)))
+            fn = int(np.sum((y_true == c) & (y_pred != c)))
+            p = tp / (tp + fp) if (tp + fp) > 0 else 0.0
+            r = tp / (tp + fn) if (tp + fn) > 0 else 0.0
+            P.append(p)
+            R.append(r)
+            F.append((2.0 * p * r / (p + r)) if (p + r) > 0 else 0.0)
+            S.append(int(np.sum(y_true == c)))
+        sup = np.asarray(S, dtype=np.float64)
+        w = sup / (float(np.sum(sup)) or 1.0)
+        out[k] = {"accuracy": float(np.mean(y_true == y_pred)) * 100.0,
+                  "precision_macro": float(np.mean(P)) * 100.0, "recall_macro": float(np.mean(R)) * 100.0,
+                  "f1_macro": float(np.mean(F)) * 100.0,
+                  "precision_weighted": float(np.sum(np.asarray(P) * w)) * 100.0,
+                  "recall_weighted": float(np.sum(np.asarray(R) * w)) * 100.0,
+                  "f1_weighted": float(np.sum(np.asarray(F) * w)) * 100.0}
+    return out
+
+
+# ---- lesion re-ranking (SURVEY 8(f)-1) ----------------------------------------------------------
+def lesion_rerank(base_val: np.ndarray, base_idx: np.ndarray, lesion_maps, query_choice, rerank_topk: int,
+                  global_weight: float) -> np.ndarray:
+    """rerank_with_specific_lesion / rerank_with_adaptive_lesion (chestmir_eval.py:507-650) on top-K lists:
+    ``base_val / base_idx`` [n, K] = the global self-excluded ranking, ``query_choice[i]`` = (lesion key, query vector) or
+    None.  The first ``rerank_topk`` entries are re-ordered by (gw * global + (1 - gw) * best region cosine, global)
+    descending (stable); untouched when the query has no vector or no candidate has a region of that lesion."""
+    out = base_idx.copy()
+    m = min(rerank_topk, base_idx.shape[1])
+    for i in range(base_idx.shape[0]):
+        if query_choice[i] is None:
+            continue
+        key, qv = query_choice[i]
+        scored, matched = [], 0
+        for pos in range(m):
+            j = int(base_idx[i, pos])
+            cands = lesion_maps[j].get(key, [])
+            region = max(float(np.dot(qv, c)) for c in cands) if len(cands) else -1.0
+            matched += region >= 0.0
+            scored.append((j, global_weight * float(base_val[i, pos]) + (1.0 - global_weight) * region,
+                           float(base_val[i, pos])))
+        if matched == 0:
+            continue
+        scored.sort(key=lambda x: (x[1], x[2]), reverse=True)
+        out[i, :m] = [s[0] for s in scored]
+    return out
