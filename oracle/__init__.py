@@ -139,3 +139,19 @@ def merge_topk(vals: np.ndarray, idx: np.ndarray, metric: str = "cosine"):
         for j in range(k):
             out_v[r, j], out_i[r, j] = cand[j][5], cand[j][6]
     return out_v, out_i
+
+
+def split_bf16x3(x: np.ndarray, role: str) -> np.ndarray:
+    """Restatement of knn_split_bf16x3 (csrc/exact_tc.cu): hi = bf16(x), lo = bf16(x - hi); rows [hi|lo|hi] for
+    role "queries", [hi|hi|lo] for "gallery", each part zero-padded to a multiple of 8 columns.  -> fp32 array holding
+    bf16-representable values."""
+    x = _f32(x)
+    n, d = x.shape
+    dpad = (d + 7) // 8 * 8
+    hi = bf16_round(x)
+    lo = bf16_round(x - hi)
+    parts = (hi, lo, hi) if role == "queries" else (hi, hi, lo)
+    out = np.zeros((n, 3 * dpad), dtype=np.float32)
+    for p, part in enumerate(parts):
+        out[:, p * dpad:p * dpad + d] = part
+    return out

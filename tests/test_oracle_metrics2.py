@@ -94,3 +94,21 @@ def test_lesion_rerank_restatement():
         choice.append((best, m[best][0]) if best is not None else None)
     got = rm.lesion_rerank(base_val, base_idx, maps, choice, c["rerank_topk"], c["global_weight"])
     assert np.array_equal(got, A["adaptive"])
+
+
+def test_split_filter_error_bound_holds_in_exact_arithmetic():
+    """The mathematical part of the exact engine's error bound (include/b200knn.h, knn_filter_error_bound): the three
+    kept products of the bf16x3 split differ from q.g by at most 3.02 * 2^-18 * |q||g| -- checked in float64, where the
+    split rows' inner product is exact."""
+    rs = np.random.RandomState(3)
+    for d, scale in ((64, 1.0), (1024, 1.0), (100, 1e3), (36, 1e-3)):
+        q = (rs.standard_normal((50, d)) * scale).astype(np.float32)
+        g = (rs.standard_normal((400, d)) * np.exp(rs.uniform(-3, 3, (400, 1)))).astype(np.float32)
+        q3, g3 = oracle.split_bf16x3(q, "queries"), oracle.split_bf16x3(g, "gallery")
+        assert q3.shape == (50, 3 * ((d + 7) // 8 * 8)) and np.array_equal(oracle.bf16_round(q3), q3)
+        approx = q3.astype(np.float64) @ g3.astype(np.float64).T
+        exact = q.astype(np.float64) @ g.astype(np.float64).T
+        qn = np.linalg.norm(q.astype(np.float64), axis=1)[:, None]
+        gn = np.linalg.norm(g.astype(np.float64), axis=1)[None, :]
+        bound = 3.02 * 2.0 ** -18 * qn * gn
+        assert np.all(np.abs(approx - exact) <= bound)
