@@ -11,10 +11,11 @@ from . import metrics
 from . import fusion
 from . import collection
 from . import formats
+from . import analysis
 from .sharded import ShardedFlatIndex
 
 __all__ = [
     "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
     "merge_topk_parts", "pack_bits", "rank_rows", "row_sqnorm", "scores_dense", "search", "search_hamming",
-    "split_bf16x3", "unpack_bits_pm1", "metrics", "fusion", "collection", "formats",
+    "split_bf16x3", "unpack_bits_pm1", "metrics", "fusion", "collection", "formats", "analysis",
 ]

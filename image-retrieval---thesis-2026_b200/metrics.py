@@ -389,9 +389,12 @@ def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Option
     return retrieval_metrics_from_ranking(idx, labels, k_values)
 
 
-def is_retrieval_correct(query_label, retrieved_labels: Sequence, top_k: int = 1) -> bool:
-    """retrieval_analysis/evaluator.py:18-26: any label equality among the first ``top_k`` hits."""
-    return any(lbl == query_label for lbl in list(retrieved_labels)[:top_k])
+def is_retrieval_correct(query_label, results, config=None) -> bool:
+    """retrieval_analysis/evaluator.py:18-26 (``is_retrieval_correct(query_label, results, config)``): lives in
+    :mod:`analysis` next to ``CorrectnessConfig`` and the four-way grouping; re-exported here with the metric rows."""
+    from .analysis import CorrectnessConfig, is_retrieval_correct as _impl
+
+    return _impl(query_label, results, config if config is not None else CorrectnessConfig())
 
 
 # --------------------------------------------------------------------------------------------------
