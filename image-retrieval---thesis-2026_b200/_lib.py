@@ -62,6 +62,12 @@ SIGNATURES = {
     "knn_map_full": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _p, _p, _p, _p]),
     "knn_ap_sklearn": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
     "knn_ap_sklearn_workspace": (_sz, [_i64, _i]),
+    "knn_rank_of_positives": (_i, [_p, _i64, _i64, _i64, _i, _i, _p, _p, _d, _i64, _i, _p, _p, _p, _i64, _p, _p, _p,
+                                   _p, _p, _p, _sz, _p]),
+    "knn_rank_of_positives_workspace": (_sz, [_i64, _i64]),
+    "knn_ap_from_ranks": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "knn_ap_sklearn_from_ranks": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
+    "knn_ap_sklearn_from_ranks_workspace": (_sz, [_i64, _i64]),
 }
 
 _lock = threading.Lock()

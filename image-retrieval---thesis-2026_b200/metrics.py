@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from . import fullrank as FR
 from .search import search_hamming, _ptr, _require_cuda, _stream, rank_rows, search
 
 _NAN = float("nan")
@@ -190,6 +191,24 @@ def compute_map(ranks, gnd, kappas=[]):
     return float(mAP), aps, np.asarray(pr, dtype=np.float64), prs_np
 
 
+def compute_map_from_embeddings(embeds: torch.Tensor, labels, kappas=(), metric: str = "l2", normalize: bool = False):
+    """``compute_map(argsort(dists, dim=0), labels, kappas)`` (test.py:1090-1091) straight from the embeddings, without
+    the N x N ``dists`` / ``ranks`` matrices: ``dists = -cdist(e, e)`` (``metric="l2"``) or ``e @ e.T`` with the
+    diagonal at -inf, the trapezoidal AP and mP@k of test.py:58-146 over the full ranking.  The query counts among its
+    own positives and ranks last.  Same return value as :func:`compute_map`."""
+    _require_cuda(embeds)
+    lab = _dev_i64(labels, embeds.device).view(-1)
+    st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, lab, lab, metric=metric, normalize=normalize,
+                               self_mode="exclude", drop_self=True, kappas=kappas, self_last_positive=True)
+    aps = st["ap_trapz"].cpu().numpy()
+    prs_np = st["prs"].cpu().numpy().reshape(len(aps), len(kappas))
+    valid = st["nres"].cpu().numpy() > 0
+    nq, nempty = len(aps), int((~valid).sum())
+    mAP = _seq_sum(aps[valid]) / (nq - nempty)
+    pr = _seq_sum(prs_np[valid], axis=0) / (nq - nempty) if len(kappas) else np.zeros(0)
+    return float(mAP), aps, np.asarray(pr, dtype=np.float64), prs_np
+
+
 # --------------------------------------------------------------------------------------------------
 # D3  compute_classification_metrics  (test.py:149-223)
 # --------------------------------------------------------------------------------------------------
@@ -332,26 +351,20 @@ def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch
 # --------------------------------------------------------------------------------------------------
 # D6 / D11 / D13: embeddings-in single-label evaluation (train.py:399-441; fusion_eval/metrics.py:41-94)
 # --------------------------------------------------------------------------------------------------
-def _self_retrieval_full(embeds: torch.Tensor, metric: str = "cosine", normalize: bool = True):
-    n = embeds.shape[0]
-    return search(embeds, embeds, n - 1, metric, normalize=normalize, exclude_self=True)
-
-
 def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10)):
     """train.py:399-441: cosine self-retrieval, standard AP over the full ranking / (#same-label - 1), R@K."""
     if len(labels) <= 1:
         return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
     _require_cuda(embeds)
     labels = _dev_i64(labels, embeds.device).view(-1)
-    _, idx = _self_retrieval_full(embeds)
-    rel, _ = relevance_single(idx, labels, labels)
-    hits, first, _, prec_sum = ranked_stats(rel)
-    hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
+    st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, labels, labels, metric="cosine", normalize=True,
+                               self_mode="exclude", drop_self=True)
+    hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
     aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)   # relevant_counts == hits over the full ranking
     metrics = {"mAP": float(np.mean(aps) * 100.0)}
-    first_np = first.cpu().numpy()
+    first_np = st["first"].cpu().numpy()
     for k in topk:
-        actual_k = min(k, rel.shape[1])
+        actual_k = min(k, len(labels) - 1)
         metrics[f"R@{k}"] = float(np.mean(((first_np > 0) & (first_np <= actual_k)).astype(np.float32))) * 100.0
     return metrics
 
@@ -380,13 +393,45 @@ def retrieval_metrics_from_ranking(idx: torch.Tensor, labels: Sequence,
 
 def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Optional[Sequence] = None,
                                k_values: Iterable[int] = (1, 5, 10)) -> Dict[str, float]:
-    """fusion_eval/metrics.py:26-94 (labels may be strings; image paths are assumed unique, as the reference's
-    aligned embedding sets are)."""
+    """fusion_eval/metrics.py:26-94 (labels may be strings): cosine self-retrieval, standard AP over the full ranking
+    divided by (#same-label - 1), ``mP@k = hits/k``, ``R@k`` any-hit, 0.0 for queries without relevant items.  Every
+    gallery row that shares the query's image path is left out of the ranking (``ranked_indices[image_paths[...] !=
+    image_paths[q]]``, metrics.py:67) -- with unique paths that is the query itself.  No N x N matrix is built."""
     emb = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not isinstance(embeddings, torch.Tensor) \
         else embeddings
     emb = emb.cuda() if not emb.is_cuda else emb
-    _, idx = _self_retrieval_full(emb)
-    return retrieval_metrics_from_ranking(idx, labels, k_values)
+    n = emb.shape[0]
+    if len(labels) != n or (image_paths is not None and len(image_paths) != n):
+        raise ValueError("Labels, image_paths, and similarity matrix must have matching sizes")
+    _, inv = np.unique(np.asarray(labels), return_inverse=True)
+    inv = inv.reshape(-1)
+    lab = torch.as_tensor(inv, dtype=torch.int64, device=emb.device)
+    grp = None
+    if image_paths is not None:
+        upaths, pinv = np.unique(np.asarray(image_paths), return_inverse=True)
+        if len(upaths) != n:   # shared paths: drop by group
+            grp = torch.as_tensor(pinv.reshape(-1), dtype=torch.int64, device=emb.device)
+    k_values = sorted(set(int(k) for k in k_values))
+    relevant_count = np.bincount(inv)[inv] - 1            # np.sum(labels == labels[q]) - 1
+    metrics: Dict[str, float] = {"num_samples": float(n)}
+    aps = np.zeros(n)
+    hits_k = {}
+    for c in range(0, max(len(k_values), 1), 8):          # the kernel takes up to 8 cut-offs per pass
+        ks = k_values[c:c + 8]
+        st = FR.full_ranking_stats(emb, emb, FR.REL_SINGLE, lab, lab, metric="cosine", normalize=True,
+                                   self_mode="exclude", drop_self=True, q_group=grp, g_group=grp, kappas=ks)
+        if c == 0:
+            hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
+            ok = (relevant_count > 0) & (hits_np > 0)
+            aps = np.where(ok, ps / np.maximum(relevant_count, 1), 0.0)
+        ha = st["hits_at"].cpu().numpy()
+        for j, k in enumerate(ks):
+            hits_k[k] = np.where(relevant_count > 0, ha[:, j], 0)
+    metrics["mAP"] = float(np.mean(aps) * 100.0)
+    for k in k_values:
+        metrics[f"mP@{k}"] = float(np.mean(hits_k[k] / k) * 100.0)
+        metrics[f"R@{k}"] = float(np.mean((hits_k[k] > 0).astype(np.float64)) * 100.0)
+    return metrics
 
 
 def is_retrieval_correct(query_label, results, config=None) -> bool:
@@ -406,11 +451,10 @@ def compute_map_multilabel_from_embeddings(embeds: torch.Tensor, labels_multihot
     queries without relevant items skipped."""
     _require_cuda(embeds)
     m = pack_multihot(labels_multihot.to(embeds.device))
-    _, idx = _self_retrieval_full(embeds)
-    rel, _ = relevance_multilabel(idx, m, m, threshold, arith="fp32")
-    hits, _, ap, _ = ranked_stats(rel)
-    hits_np = hits.cpu().numpy()
-    aps = ap.cpu().numpy()[hits_np > 0]
+    st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
+                               self_mode="exclude", drop_self=True, jaccard_threshold=float(threshold))
+    hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
+    aps = (ps / np.maximum(hits_np, 1))[hits_np > 0]
     return float(np.mean(aps)) if len(aps) else 0
 
 
@@ -437,14 +481,14 @@ def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Te
         return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
     _require_cuda(embeds)
     m = pack_multihot(labels.to(embeds.device))
-    vals, idx = _self_retrieval_full(embeds)
-    rel, _ = relevance_multilabel(idx, m, m, relevance_threshold, arith="fp32")
-    hits, first, _, _ = ranked_stats(rel)
-    hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
-    aps = ap_sklearn(vals, rel).cpu().numpy()[hits_np > 0]
+    st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
+                               self_mode="exclude", drop_self=True, jaccard_threshold=float(relevance_threshold),
+                               sklearn_ap=True)
+    hits_np, first_np = st["npos"].cpu().numpy(), st["first"].cpu().numpy()
+    aps = st["ap_sklearn"].cpu().numpy()[hits_np > 0]
     metrics = {"mAP": float(np.mean(aps) * 100.0) if len(aps) > 0 else 0.0}
     for k in topk:
-        actual_k = min(k, rel.shape[1])
+        actual_k = min(k, len(labels) - 1)
         metrics[f"R@{k}"] = float(np.mean(((first_np > 0) & (first_np <= actual_k)).astype(np.float64)) * 100.0)
     return metrics
 
@@ -453,12 +497,12 @@ def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jacc
     """nih_multilabel_training.py:66-99 on given embeddings: self is KEPT with similarity -1 and counts as a
     relevant item (J(self, self) = 1 > threshold) ranked wherever -1 falls."""
     _require_cuda(embeddings)
-    n = embeddings.shape[0]
     m = pack_multihot(labels.to(embeddings.device))
-    vals, idx = search(embeddings, embeddings, n, "cosine", normalize=True, self_mode="minus1")
-    rel, _ = relevance_multilabel(idx, m, m, jaccard_threshold, arith="fp32")
-    hits = ranked_stats(rel)[0].cpu().numpy()
-    aps = ap_sklearn(vals, rel).cpu().numpy()[hits > 0]
+    st = FR.full_ranking_stats(embeddings, embeddings, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
+                               self_mode="minus1", drop_self=False, jaccard_threshold=float(jaccard_threshold),
+                               sklearn_ap=True)
+    hits = st["npos"].cpu().numpy()
+    aps = st["ap_sklearn"].cpu().numpy()[hits > 0]
     if len(aps) == 0:
         return 0.0
     return float(np.mean(aps) * 100.0)
@@ -626,24 +670,29 @@ def evaluate_embeddings(embeds: torch.Tensor, labels, metric: str = "l2", kappas
     diagonal at -inf; R@K; the trapezoidal mAP and mP@K over the column-wise full ranking; majority-vote classification
     metrics; optionally the ``np.savez`` bundle of test.py:1122-1126.
     -> {"acc": float32 [len(kappas)], "mAP": float, "pr": float64 [len(kappas)], "classification": {k: {...}}}.
-    Dense in N (the reference's own formulation needs the full ranking); for large N use the top-k entry points."""
+    Nothing of size N x N is built (unless ``save_path`` asks for the bundle, which stores ``dists``): R@K and the vote
+    come from one fused top-k search, the full-ranking mAP from the ranks of the positives (fullrank.py)."""
     _require_cuda(embeds)
-    from .search import scores_dense
-
     kappas, k_values = list(kappas), list(k_values)
-    if metric == "l2":
-        dists = -scores_dense(embeds, embeds, "l2", self_mode="exclude")          # -cdist, diagonal -inf
-    else:
-        dists = scores_dense(embeds, embeds, metric, self_mode="exclude")
-    lab = _dev_i64(labels, dists.device).view(-1)
-    ranks = rank_rows(dists.t().contiguous(), largest_first=True)                  # [nq, db]: argsort(dim=0) per query
-    acc = torch.stack(retrieval_accuracy(dists, lab, topk=kappas)).numpy()        # rows (topk dim=1), as test.py:44
-    mAP, _, pr, _ = compute_map(ranks.t(), lab, kappas)
-    classification = classification_metrics_from_topk(ranks[:, : max(k_values)].contiguous(), lab, lab, k_values)
+    lab = _dev_i64(labels, embeds.device).view(-1)
+    n = embeds.shape[0]
+    # R@K and the majority vote read the first max(k) neighbours: one fused top-k search (rows = columns: the engine's
+    # scores are symmetric, so the column ranking of test.py:1090 is the row ranking)
+    kmax = max(1, min(max(kappas + k_values), n - 1))
+    _, idx = search(embeds, embeds, kmax, metric, exclude_self=True)
+    acc = torch.stack(recall_at_k_from_topk(idx, lab, lab, kappas)).numpy()
+    # trapezoidal mAP / mP@K over the FULL ranking from the ranks of the positives -- no N x N matrix
+    mAP, _, pr, _ = compute_map_from_embeddings(embeds, lab, kappas, metric=metric)
+    classification = classification_metrics_from_topk(idx, lab, lab, k_values)
     out = {"acc": acc, "mAP": mAP, "pr": pr, "classification": classification}
-    if save_path is not None:
+    if save_path is not None:   # the bundle of test.py:1122-1126 stores the dense `dists`: only built when asked for
         from .formats import save_evaluation_npz
+        from .search import scores_dense
 
+        if metric == "l2":
+            dists = -scores_dense(embeds, embeds, "l2", self_mode="exclude")      # -cdist, diagonal -inf
+        else:
+            dists = scores_dense(embeds, embeds, metric, self_mode="exclude")
         save_evaluation_npz(save_path, embeds, lab, kappas, acc, mAP, pr, classification, dists=dists)
     return out
 

@@ -268,6 +268,60 @@ KNN_API int    knn_ap_sklearn(const float* val, const uint8_t* rel, int64_t nq, 
                       void* workspace, size_t workspace_bytes, void* stream);
 KNN_API size_t knn_ap_sklearn_workspace(int64_t nq, int k);
 
+/* Full-ranking metrics without the N x N ranking (SURVEY 8(b) knn_rank_of_positives).  The reference sorts whole score
+ * rows -- torch.argsort(dists, dim=0) test.py:1090, np.argsort(-dists, axis=0) test.py:962, topk(N-1) train.py:409,455,
+ * sklearn's internal argsort nih_multilabel_training.py:95 -- only to read off where the RELEVANT rows ended up.  For
+ * every row of a dense score block scores [nq, ld_scores >= ng] (one query each) this call returns the 0-based ranks of
+ * the relevant gallery rows in the full ranking (best first: largest score, or smallest with largest_first = 0; ties by
+ * ascending gallery row -- the order of knn_search / knn_rank_rows), ascending, in pos_ranks [nq, ld_out] with
+ * npos[q] of them valid (ld_out >= the largest npos; ng always suffices).
+ *   rel_mode 0: single label, relevant iff g_rel[g] == q_rel[q] (int64 labels; test.py:119, train.py:412)
+ *            1: multi-label masks (uint64), Jaccard |a&b| / (|a|b| + 1e-8) > jaccard_thr in fp32 tensor arithmetic
+ *               (train.py:462-466, nih_multilabel_training.py:90-93, test.py:956-965)
+ *            2: the same in Python-float arithmetic (evaluate_nih_zilliz.py:12-17);  3: shares >= 1 label (test.py:1045)
+ *   drop_self != 0: gallery row self_offset + q is neither ranked nor relevant for query q (the fill_diagonal_(-inf) /
+ *               masked self of test.py:1081, train.py:406,452,468); 0: it is an ordinary row (nih_multilabel_training.py:86
+ *               keeps it at score -1 and relevant).
+ *   q_group [nq], g_group [ng] (int64, both or neither): gallery rows whose group equals the query's are not ranked
+ *               either -- fusion_eval/metrics.py:67 drops every row that shares the query's image path.
+ *   nranked[q] (nullable) = rows ranked (ng minus the dropped ones).
+ *   pos_ge, pos_tgroup [nq, ld_out], ngroups [nq] (all three or none): per positive the number of ranked rows whose score
+ *               is >= its own (the end of its run of equal scores) and the number of DISTINCT score values above it;
+ *               ngroups = distinct score values in the row -- the threshold structure of sklearn's
+ *               average_precision_score, consumed by knn_ap_sklearn_from_ranks.
+ * Workspace: knn_rank_of_positives_workspace(nq, ng) bytes (two 64-bit key rows per resident CTA). */
+KNN_API int knn_rank_of_positives(const float* scores, int64_t ld_scores, int64_t nq, int64_t ng, int largest_first,
+                          int rel_mode, const void* q_rel, const void* g_rel, double jaccard_thr,
+                          int64_t self_offset, int drop_self, const int64_t* q_group, const int64_t* g_group,
+                          int32_t* pos_ranks, int64_t ld_out,
+                          int32_t* pos_ge, int32_t* pos_tgroup, int32_t* npos, int32_t* nranked, int32_t* ngroups,
+                          void* workspace, size_t workspace_bytes, void* stream);
+KNN_API size_t knn_rank_of_positives_workspace(int64_t nq, int64_t ng);
+
+/* AP variants from the ranks of the positives (pos_ranks / npos / nranked of knn_rank_of_positives), IEEE double in the
+ * reference's operation order, accumulated in rank order.  All outputs nullable.
+ *   ap_trapz [nq], prs [nq,nkappa], nres [nq]: compute_ap / compute_map, test.py:58-146 (trapezoidal AP, precision at
+ *       kappas with kq = min(max(pos), kappa)); self_last_positive != 0 appends the query itself as one more positive at
+ *       rank nranked[q] -- test.py:119 counts the query among its positives and its -inf score ranks it last.
+ *       NaN when a query has no positive.
+ *   prec_sum [nq]: sum over the positives of (positives so far) / (1-based rank) -- the numerator of the rank-by-rank AP
+ *       of test.py:974-981, train.py:424-433, fusion_eval/metrics.py:78-83 (the caller divides by its relevant count).
+ *   first [nq]: 1-based rank of the best positive, 0 = none (R@K of train.py:436-439).
+ *   hits_at [nq,nkappa]: positives with rank < kappas[t] (mP@k of fusion_eval/metrics.py:85-88). */
+KNN_API int knn_ap_from_ranks(const int32_t* pos_ranks, int64_t ld, const int32_t* npos, const int32_t* nranked,
+                      int64_t nq, int self_last_positive, const int32_t* kappas, int nkappa, double* ap_trapz,
+                      double* prs, int32_t* nres, double* prec_sum, int32_t* first, int32_t* hits_at, void* stream);
+
+/* sklearn.metrics.average_precision_score over the FULL ranking (train.py:473, nih_multilabel_training.py:95) from the
+ * tie structure of the positives: thresholds are the runs of equal scores, AP = -sum(diff(recall) * precision[:-1]) on
+ * the reversed curves, summed with numpy's pairwise summation over all ngroups thresholds (only runs that hold a positive
+ * contribute a non-zero term, but every run keeps its position in the summation tree).  ap [nq] f64, NaN = no positive.
+ * Workspace: knn_ap_sklearn_from_ranks_workspace(nq, ld) bytes. */
+KNN_API int knn_ap_sklearn_from_ranks(const int32_t* pos_ge, const int32_t* pos_tgroup, int64_t ld, const int32_t* npos,
+                              const int32_t* ngroups, int64_t nq, double* ap, void* workspace, size_t workspace_bytes,
+                              void* stream);
+KNN_API size_t knn_ap_sklearn_from_ranks_workspace(int64_t nq, int64_t ld);
+
 #ifdef __cplusplus
 }
 #endif
