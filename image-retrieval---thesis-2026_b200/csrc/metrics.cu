@@ -155,27 +155,54 @@ __global__ void map_full_kernel(const int64_t* __restrict__ ranks, int64_t nq, i
 }
 
 // numpy's pairwise summation of n doubles (numpy/_core/src/umath/loops_utils.h.src), as used by
-// np.sum inside sklearn.metrics.average_precision_score.
-__device__ double np_pairwise_sum(const double* a, int n) {
+// np.sum inside sklearn.metrics.average_precision_score.  One block of the tree (n <= 128):
+__device__ double np_block_sum(const double* a, int n) {
   if (n < 8) {
     double res = 0.0;
     for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
     return res;
   }
-  if (n <= 128) {
-    double r[8];
-    for (int i = 0; i < 8; ++i) r[i] = a[i];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8)
-      for (int t = 0; t < 8; ++t) r[t] = __dadd_rn(r[t], a[i + t]);
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-    return res;
+  double r[8];
+  for (int i = 0; i < 8; ++i) r[i] = a[i];
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8)
+    for (int t = 0; t < 8; ++t) r[t] = __dadd_rn(r[t], a[i + t]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+// sum(a, n) = sum(a, n2) + sum(a + n2, n - n2), n2 = n/2 rounded down to a multiple of 8, walked with an explicit stack
+// (device recursion needs a run-time stack size: the recursive form overflowed the default 1 KB at k ~ 3000).
+__device__ double np_pairwise_sum(const double* a, int n) {
+  int lo_s[24], n_s[24];
+  double left_s[24];
+  unsigned char phase_s[24];
+  int sp = 0;
+  lo_s[0] = 0; n_s[0] = n; phase_s[0] = 0;
+  double ret = 0.0;
+  while (sp >= 0) {
+    const int lo = lo_s[sp], m = n_s[sp];
+    if (phase_s[sp] == 0) {
+      if (m <= 128) { ret = np_block_sum(a + lo, m); --sp; continue; }
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      phase_s[sp] = 1;
+      ++sp;
+      lo_s[sp] = lo; n_s[sp] = n2; phase_s[sp] = 0;
+    } else if (phase_s[sp] == 1) {
+      left_s[sp] = ret;
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      phase_s[sp] = 2;
+      ++sp;
+      lo_s[sp] = lo + n2; n_s[sp] = m - n2; phase_s[sp] = 0;
+    } else {
+      ret = __dadd_rn(left_s[sp], ret);
+      --sp;
+    }
   }
-  int n2 = n / 2;
-  n2 -= n2 % 8;
-  return __dadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+  return ret;
 }
 
 // average_precision_score over one ranked list (scores non-increasing): thresholds at the last index of

@@ -61,6 +61,7 @@ struct RankParams {
   int nslabs;            // the row is scattered / resolved in this many slabs of bins (live scratch stays L2 resident)
   uint64_t* scratch;     // [grid][ng]
   uint64_t* tmp;         // [grid][ng]
+  unsigned int* next_row;   // rows are claimed dynamically: a CTA slowed down by a co-running kernel takes fewer
   int32_t* pos_ranks;
   int64_t ld_out;
   int32_t* pos_ge;
@@ -111,6 +112,7 @@ struct Shared {
   unsigned long long red[2 * kWarps];
   float fred[2 * kWarps];
   uint32_t work_head, work_tail;
+  uint32_t row_claim;
   uint32_t slab_bin[34];    // first bin of every slab (+ nbins at the end)
   uint16_t plist[kChunk];   // chunk offsets of the relevant positions (resolve without ties)
   uint8_t rel_table[65 * 65];
@@ -253,7 +255,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) rank_positives_kernel(Ra
   }
   __syncthreads();
 
-  for (int64_t row = blockIdx.x; row < p.nq; row += gridDim.x) {
+  while (true) {
+    if (tid == 0) sh.row_claim = atomicAdd(p.next_row, 1u);
+    __syncthreads();
+    const int64_t row = sh.row_claim;
+    if (row >= p.nq) break;
     const float* srow = p.scores + row * p.ld_scores;
     const int64_t self = p.drop_self ? p.self_offset + row : -1;
     const int64_t ql = p.qlab[row];
@@ -742,13 +748,14 @@ __device__ double np_block_sparse(const SparseTerms& a, int lo, int n, int& cur)
   return res;
 }
 // The recursion `sum(lo, n) = sum(lo, n2) + sum(lo + n2, n - n2)`, n2 = n/2 rounded down to a multiple of 8, walked with
-// an explicit stack (depth <= 32 for n < 2^30; device recursion would need a run-time stack size).
-__device__ double np_pairwise_sparse(const SparseTerms& a, int total_n) {
+// an explicit stack (depth <= 32 for n < 2^30; device recursion would need a run-time stack size) over the index range
+// [lo0, lo0 + n0) of the sparse array; `cur` = first non-zero at or after lo0.
+__device__ double np_pairwise_sparse(const SparseTerms& a, int lo0, int n0, int cur) {
   int lo_s[32], n_s[32];
   double left_s[32];
   unsigned char phase_s[32];
-  int sp = 0, cur = 0;
-  lo_s[0] = 0; n_s[0] = total_n; phase_s[0] = 0;
+  int sp = 0;
+  lo_s[0] = lo0; n_s[0] = n0; phase_s[0] = 0;
   double ret = 0.0;
   while (sp >= 0) {
     const int lo = lo_s[sp], n = n_s[sp];
@@ -778,12 +785,14 @@ __device__ double np_pairwise_sparse(const SparseTerms& a, int total_n) {
 // sklearn.metrics.average_precision_score over the FULL ranking from the positives' tie structure
 // (train.py:473, nih_multilabel_training.py:95): thresholds = runs of equal scores, AP = -sum(diff(recall) *
 // precision[:-1]) on the reversed curves -- only runs holding a positive contribute a non-zero term.
+// One warp per query.  The lanes build the non-zero terms (one per run of equal scores that holds a positive).  numpy's
+// summation tree over all `ngroups` thresholds is then split at depth 5: lane L follows the bits of L down from the
+// root (register arithmetic), sums ITS subtree exactly as numpy would, and the five top levels are combined with
+// shuffles -- `left + right` at every node, the same additions in the same pairing.
 __global__ void ap_sklearn_ranks_kernel(const int32_t* __restrict__ pos_ge, const int32_t* __restrict__ pos_tg,
                                         int64_t ld, const int32_t* __restrict__ npos,
                                         const int32_t* __restrict__ ngroups, int64_t nq, int32_t* __restrict__ ws_idx,
                                         double* __restrict__ ws_val, double* __restrict__ ap) {
-  // one warp per query: the lanes build the non-zero terms (one per run of equal scores that holds a positive), lane 0
-  // walks numpy's summation tree over them
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
@@ -816,10 +825,28 @@ __global__ void ap_sklearn_ranks_kernel(const int32_t* __restrict__ pos_ge, cons
     m += __popc(bal);
   }
   __syncwarp();
-  if (lane == 0) {
-    SparseTerms a{idx, val, m};
-    ap[q] = -np_pairwise_sparse(a, T);
+  const SparseTerms a{idx, val, m};
+  if (T <= 8192) {   // a tree this small may have leaves above depth 5: one lane walks all of it
+    if (lane == 0) ap[q] = -np_pairwise_sparse(a, 0, T, 0);
+    return;
   }
+  int lo = 0, n = T;   // every node above depth 5 holds more than 128 thresholds: the tree is complete down to there
+#pragma unroll
+  for (int bit = 4; bit >= 0; --bit) {
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    if ((lane >> bit) & 1) { lo += n2; n -= n2; }
+    else n = n2;
+  }
+  int lo_e = 0, hi_e = m;   // first non-zero at or after lo (terms ascend in the reversed view)
+  while (lo_e < hi_e) {
+    const int mid = (lo_e + hi_e) >> 1;
+    if (a.index(mid) >= lo) hi_e = mid; else lo_e = mid + 1;
+  }
+  double v = np_pairwise_sparse(a, lo, n, lo_e);
+#pragma unroll
+  for (int level = 0; level < 5; ++level) v = __dadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1 << level));
+  if (lane == 0) ap[q] = -v;
 }
 
 int sm_count_rp() {
@@ -864,7 +891,7 @@ extern "C" __attribute__((visibility("default"))) int knn_rank_timing(unsigned l
 
 extern "C" size_t knn_rank_of_positives_workspace(int64_t nq, int64_t ng) {
   if (nq <= 0 || ng <= 0) return 0;
-  return (size_t)rank_grid(nq) * (size_t)ng * 2 * sizeof(uint64_t);
+  return (size_t)rank_grid(nq) * (size_t)ng * 2 * sizeof(uint64_t) + 256;   // key rows + the row counter
 }
 
 extern "C" int knn_rank_of_positives(const float* scores, int64_t ld_scores, int64_t nq, int64_t ng, int largest_first,
@@ -912,6 +939,8 @@ extern "C" int knn_rank_of_positives(const float* scores, int64_t ld_scores, int
   }
   p.scratch = reinterpret_cast<uint64_t*>(workspace);
   p.tmp = p.scratch + (size_t)grid * (size_t)ng;
+  p.next_row = reinterpret_cast<unsigned int*>(p.tmp + (size_t)grid * (size_t)ng);
+  KNN_CHECK_CUDA(cudaMemsetAsync(p.next_row, 0, sizeof(unsigned int), (cudaStream_t)stream));
   p.pos_ranks = pos_ranks; p.ld_out = ld_out; p.pos_ge = pos_ge; p.pos_tgroup = pos_tgroup;
   p.npos = npos; p.nranked = nranked; p.ngroups = ngroups;
   const size_t smem = rank_smem_bytes(p.nbins);

@@ -24,7 +24,7 @@ from . import _lib as L
 from .search import _METRICS, _SELF, _prepare, _ptr, _require_cuda, _scores_dense_prepared, _stream
 
 REL_SINGLE, REL_JACCARD_F32, REL_JACCARD_F64, REL_ANY = 0, 1, 2, 3
-_CHUNK_BYTES = 3 << 30   # transient memory budget of one query chunk
+_CHUNK_BYTES = 8 << 30   # transient memory budget of the query chunks in flight
 
 
 def rank_of_positives(scores: torch.Tensor, rel_mode: int, q_rel: torch.Tensor, g_rel: torch.Tensor, *,
@@ -79,10 +79,15 @@ def rank_of_positives(scores: torch.Tensor, rel_mode: int, q_rel: torch.Tensor, 
     return out
 
 
-def ap_from_ranks(rp: Dict[str, torch.Tensor], kappas: Sequence[int] = (), self_last_positive: bool = False):
+_AP_OUTPUTS = ("ap_trapz", "prs", "nres", "prec_sum", "first", "hits_at")
+
+
+def ap_from_ranks(rp: Dict[str, torch.Tensor], kappas: Sequence[int] = (), self_last_positive: bool = False,
+                  outputs: Optional[Sequence[str]] = None):
     """``knn_ap_from_ranks``: -> {"ap_trapz" f64 [Q] (compute_ap, test.py:58-92), "prs" f64 [Q, len(kappas)]
     (test.py:137-140), "nres" int32 [Q], "prec_sum" f64 [Q], "first" int32 [Q] (1-based, 0 = none),
-    "hits_at" int32 [Q, len(kappas)]}."""
+    "hits_at" int32 [Q, len(kappas)]}; ``outputs`` selects a subset (the two AP sums are chains of dependent double
+    additions over all positives: ask only for the one a metric needs)."""
     pr = rp["pos_ranks"]
     nq, ld = pr.shape
     dev = pr.device
@@ -90,19 +95,24 @@ def ap_from_ranks(rp: Dict[str, torch.Tensor], kappas: Sequence[int] = (), self_
     if nk > 8:
         raise ValueError("at most 8 cut-offs per call")
     kap = torch.as_tensor([int(k) for k in kappas], dtype=torch.int32, device=dev)
-    out = {"ap_trapz": torch.empty((nq,), dtype=torch.float64, device=dev),
-           "prs": torch.empty((nq, max(nk, 1)), dtype=torch.float64, device=dev),
-           "nres": torch.empty((nq,), dtype=torch.int32, device=dev),
-           "prec_sum": torch.empty((nq,), dtype=torch.float64, device=dev),
-           "first": torch.empty((nq,), dtype=torch.int32, device=dev),
-           "hits_at": torch.empty((nq, max(nk, 1)), dtype=torch.int32, device=dev)}
+    want = set(_AP_OUTPUTS if outputs is None else outputs)
+    if not want <= set(_AP_OUTPUTS):
+        raise ValueError(f"outputs must be among {_AP_OUTPUTS}")
+    shapes = {"ap_trapz": ((nq,), torch.float64), "prs": ((nq, max(nk, 1)), torch.float64), "nres": ((nq,), torch.int32),
+              "prec_sum": ((nq,), torch.float64), "first": ((nq,), torch.int32),
+              "hits_at": ((nq, max(nk, 1)), torch.int32)}
+    out = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in _AP_OUTPUTS if k in want}
+    if not out:
+        return out
     with torch.cuda.device(dev):
         rc = L.load().knn_ap_from_ranks(_ptr(pr), ld, _ptr(rp["npos"]), _ptr(rp["nranked"]), nq,
-                                        1 if self_last_positive else 0, _ptr(kap), nk, _ptr(out["ap_trapz"]),
-                                        _ptr(out["prs"]), _ptr(out["nres"]), _ptr(out["prec_sum"]), _ptr(out["first"]),
-                                        _ptr(out["hits_at"]), _stream(pr))
+                                        1 if self_last_positive else 0, _ptr(kap), nk, _ptr(out.get("ap_trapz")),
+                                        _ptr(out.get("prs")), _ptr(out.get("nres")), _ptr(out.get("prec_sum")),
+                                        _ptr(out.get("first")), _ptr(out.get("hits_at")), _stream(pr))
     L.check(rc, "knn_ap_from_ranks")
-    out["prs"], out["hits_at"] = out["prs"][:, :nk], out["hits_at"][:, :nk]
+    for k in ("prs", "hits_at"):
+        if k in out:
+            out[k] = out[k][:, :nk]
     return out
 
 
@@ -123,11 +133,14 @@ def ap_sklearn_from_ranks(rp: Dict[str, torch.Tensor]) -> torch.Tensor:
     return ap
 
 
-def chunk_rows(ng: int, ties: bool, budget: int = _CHUNK_BYTES) -> int:
-    """Queries per chunk so that the [chunk, N] transients (scores + ranks, + tie outputs and the sklearn workspace)
-    stay inside ``budget`` bytes."""
-    per_row = ng * (4 + 4 + (8 + 12 if ties else 0))
-    return int(max(1, min(8192, budget // max(per_row, 1))))
+def chunk_rows(ng: int, ties: bool, budget: int = _CHUNK_BYTES, device=None) -> int:
+    """Queries per chunk so that the [chunk, N] transients (scores + ranks, + tie outputs and the sklearn workspace) of
+    the two chunks in flight stay inside ``budget`` bytes; a multiple of the rank kernel's persistent grid (two CTAs per
+    SM) so that its last wave is full."""
+    per_row = 2 * ng * (4 + 4 + (8 + 12 if ties else 0))
+    rows = int(max(1, min(8192, budget // max(per_row, 1))))
+    wave = 2 * torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 296
+    return rows - rows % wave if rows >= wave else rows
 
 
 def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: int, q_rel: torch.Tensor,
@@ -135,12 +148,17 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
                        self_mode: str = "keep", drop_self: bool = False, query_offset: int = 0,
                        q_group: Optional[torch.Tensor] = None, g_group: Optional[torch.Tensor] = None,
                        jaccard_threshold: float = 0.0, kappas: Sequence[int] = (), sklearn_ap: bool = False,
-                       self_last_positive: bool = False, eps: float = 1e-12, eps_mode: str = "clamp",
+                       self_last_positive: bool = False, outputs: Optional[Sequence[str]] = None,
+                       eps: float = 1e-12, eps_mode: str = "clamp",
                        rows_per_chunk: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Per-query full-ranking statistics of ``queries`` against the whole ``gallery`` (exact fp32 scores), chunked over
     the queries.  ``self_mode`` is the score the query's own gallery row gets (``fill_diagonal_``: "exclude" = -inf,
     "minus1" = -1, "keep"); ``drop_self`` removes that row from the ranking and from the relevant set.
-    -> the outputs of :func:`ap_from_ranks` (+ "ap_sklearn" with ``sklearn_ap``) and "npos", each ``[Q]`` / ``[Q, k]``."""
+    -> the outputs of :func:`ap_from_ranks` (all, or the subset ``outputs``; + "ap_sklearn" with ``sklearn_ap``) and
+    "npos", each ``[Q]`` / ``[Q, k]``.
+
+    The AP kernels of a chunk are chains of dependent double additions in rank order (latency bound, a fraction of the
+    SMs): they run on a side stream while the distance and rank kernels of the next chunk fill the machine."""
     _require_cuda(queries, gallery)
     if metric not in _METRICS:
         raise ValueError(f"metric must be one of {sorted(_METRICS)}")
@@ -150,24 +168,43 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     q, qsq = _prepare(queries, normalize, "fp32", eps, eps_mode, want_sq)
     g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, "fp32", eps, eps_mode, want_sq)
     nq, ng = q.shape[0], g.shape[0]
-    step = int(rows_per_chunk) if rows_per_chunk else chunk_rows(ng, sklearn_ap)
+    if nq == 0:
+        raise ValueError("no queries")
+    dev = q.device
+    step = int(rows_per_chunk) if rows_per_chunk else chunk_rows(ng, sklearn_ap, device=dev)
+    main = torch.cuda.current_stream(dev)
+    nchunks = (nq + step - 1) // step
+    side = torch.cuda.Stream(dev) if nchunks > 1 else main
     parts: Dict[str, list] = {}
-    for s in range(0, max(nq, 1), step):
+    pending = []   # (rank outputs, event recorded after the chunk's AP kernels): at most two chunks in flight
+    for s in range(0, nq, step):
         e = min(nq, s + step)
-        if e <= s:
-            break
+        if len(pending) >= 2:   # the buffers of chunk i-2 are free once its AP kernels have run
+            old_rp, old_done = pending.pop(0)
+            main.wait_event(old_done)
+            del old_rp
         sc = _scores_dense_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, metric, self_mode,
                                     query_offset + s)
         rp = rank_of_positives(sc, rel_mode, q_rel[s:e], g_rel, largest_first=(metric != "l2"),
                                jaccard_threshold=jaccard_threshold, self_offset=query_offset + s, drop_self=drop_self,
                                q_group=None if q_group is None else q_group[s:e], g_group=g_group, ties=sklearn_ap)
-        st = ap_from_ranks(rp, kappas, self_last_positive)
-        st["npos"] = rp["npos"]
-        if sklearn_ap:
-            st["ap_sklearn"] = ap_sklearn_from_ranks(rp)
+        del sc
+        ranked = torch.cuda.Event()
+        ranked.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ranked)
+            st = ap_from_ranks(rp, kappas, self_last_positive, outputs)
+            st["npos"] = rp["npos"]
+            if sklearn_ap:
+                st["ap_sklearn"] = ap_sklearn_from_ranks(rp)
+            done = torch.cuda.Event()
+            done.record(side)
+        if side is not main:
+            for t in rp.values():
+                t.record_stream(side)
+        pending.append((rp, done))
         for key, val in st.items():
             parts.setdefault(key, []).append(val)
-        del sc, rp
-    if not parts:
-        raise ValueError("no queries")
-    return {key: torch.cat(vals, 0) for key, vals in parts.items()}
+    main.wait_stream(side)
+    out = {key: torch.cat(vals, 0) for key, vals in parts.items()}
+    return out

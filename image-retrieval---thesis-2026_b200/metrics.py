@@ -199,7 +199,8 @@ def compute_map_from_embeddings(embeds: torch.Tensor, labels, kappas=(), metric:
     _require_cuda(embeds)
     lab = _dev_i64(labels, embeds.device).view(-1)
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, lab, lab, metric=metric, normalize=normalize,
-                               self_mode="exclude", drop_self=True, kappas=kappas, self_last_positive=True)
+                               self_mode="exclude", drop_self=True, kappas=kappas, self_last_positive=True,
+                               outputs=("ap_trapz", "prs", "nres"))
     aps = st["ap_trapz"].cpu().numpy()
     prs_np = st["prs"].cpu().numpy().reshape(len(aps), len(kappas))
     valid = st["nres"].cpu().numpy() > 0
@@ -358,7 +359,7 @@ def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.
     _require_cuda(embeds)
     labels = _dev_i64(labels, embeds.device).view(-1)
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, labels, labels, metric="cosine", normalize=True,
-                               self_mode="exclude", drop_self=True)
+                               self_mode="exclude", drop_self=True, outputs=("prec_sum", "first"))
     hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
     aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)   # relevant_counts == hits over the full ranking
     metrics = {"mAP": float(np.mean(aps) * 100.0)}
@@ -419,7 +420,8 @@ def evaluate_retrieval_metrics(embeddings, labels: Sequence, image_paths: Option
     for c in range(0, max(len(k_values), 1), 8):          # the kernel takes up to 8 cut-offs per pass
         ks = k_values[c:c + 8]
         st = FR.full_ranking_stats(emb, emb, FR.REL_SINGLE, lab, lab, metric="cosine", normalize=True,
-                                   self_mode="exclude", drop_self=True, q_group=grp, g_group=grp, kappas=ks)
+                                   self_mode="exclude", drop_self=True, q_group=grp, g_group=grp, kappas=ks,
+                                   outputs=("prec_sum", "hits_at") if c == 0 else ("hits_at",))
         if c == 0:
             hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
             ok = (relevant_count > 0) & (hits_np > 0)
@@ -452,7 +454,8 @@ def compute_map_multilabel_from_embeddings(embeds: torch.Tensor, labels_multihot
     _require_cuda(embeds)
     m = pack_multihot(labels_multihot.to(embeds.device))
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
-                               self_mode="exclude", drop_self=True, jaccard_threshold=float(threshold))
+                               self_mode="exclude", drop_self=True, jaccard_threshold=float(threshold),
+                               outputs=("prec_sum",))
     hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
     aps = (ps / np.maximum(hits_np, 1))[hits_np > 0]
     return float(np.mean(aps)) if len(aps) else 0
@@ -483,7 +486,7 @@ def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Te
     m = pack_multihot(labels.to(embeds.device))
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
                                self_mode="exclude", drop_self=True, jaccard_threshold=float(relevance_threshold),
-                               sklearn_ap=True)
+                               sklearn_ap=True, outputs=("first",))
     hits_np, first_np = st["npos"].cpu().numpy(), st["first"].cpu().numpy()
     aps = st["ap_sklearn"].cpu().numpy()[hits_np > 0]
     metrics = {"mAP": float(np.mean(aps) * 100.0) if len(aps) > 0 else 0.0}
@@ -500,7 +503,7 @@ def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jacc
     m = pack_multihot(labels.to(embeddings.device))
     st = FR.full_ranking_stats(embeddings, embeddings, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
                                self_mode="minus1", drop_self=False, jaccard_threshold=float(jaccard_threshold),
-                               sklearn_ap=True)
+                               sklearn_ap=True, outputs=())
     hits = st["npos"].cpu().numpy()
     aps = st["ap_sklearn"].cpu().numpy()[hits > 0]
     if len(aps) == 0:
