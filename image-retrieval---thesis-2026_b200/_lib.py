@@ -58,7 +58,9 @@ SIGNATURES = {
     "knn_relevance_single": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
     "knn_relevance_multilabel": (_i, [_p, _i64, _i, _p, _p, _i64, _d, _i, _p, _p, _p]),
     "knn_ranked_stats": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
+    "knn_ranked_stats_multi": (_i, [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p]),
     "knn_majority_vote": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
+    "knn_majority_vote_multi": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p]),
     "knn_map_full": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _p, _p, _p, _p]),
     "knn_ap_sklearn": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
     "knn_ap_sklearn_workspace": (_sz, [_i64, _i]),

@@ -71,6 +71,39 @@ __global__ void ranked_stats_kernel(const uint8_t* __restrict__ rel, int64_t nq,
   if (ap_topk) ap_topk[q] = pos > 0 ? __ddiv_rn(ps, (double)pos) : 0.0;
 }
 
+// All cut-offs of a metric table in ONE launch: thread q walks its row once and snapshots the running statistics at
+// every kks[t] (any order, each <= k).  Outputs are [nq, nk] (first: [nq], the rank of the first relevant item).
+constexpr int kMaxCutoffs = 16;
+__global__ void ranked_stats_multi_kernel(const uint8_t* __restrict__ rel, int64_t nq, int k,
+                                          const int32_t* __restrict__ kks, int nk, int32_t* __restrict__ hits,
+                                          int32_t* __restrict__ first, double* __restrict__ ap_topk,
+                                          double* __restrict__ prec_sum) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const uint8_t* r = rel + q * k;
+  int cut[kMaxCutoffs], kmax = 0;
+  for (int t = 0; t < nk; ++t) {
+    cut[t] = kks[t] < k ? kks[t] : k;
+    kmax = cut[t] > kmax ? cut[t] : kmax;
+  }
+  int pos = 0, f = 0;
+  double ps = 0.0;
+  for (int j = 0; j < kmax; ++j) {
+    if (r[j]) {
+      ++pos;
+      ps = __dadd_rn(ps, __ddiv_rn((double)pos, (double)(j + 1)));  // precision_sum += positives / rank
+      if (f == 0) f = j + 1;
+    }
+    for (int t = 0; t < nk; ++t)
+      if (cut[t] == j + 1) {
+        if (hits) hits[q * nk + t] = pos;
+        if (prec_sum) prec_sum[q * nk + t] = ps;
+        if (ap_topk) ap_topk[q * nk + t] = pos > 0 ? __ddiv_rn(ps, (double)pos) : 0.0;
+      }
+  }
+  if (first) first[q] = f;   // over the first max(kks) items
+}
+
 __global__ void majority_vote_kernel(const int64_t* __restrict__ lab, int64_t nq, int k, int kk, int tie_mode,
                                      int64_t* __restrict__ vote) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,6 +121,29 @@ __global__ void majority_vote_kernel(const int64_t* __restrict__ lab, int64_t nq
     if (c > best || (tie_mode == 1 && c == best && lj < bl)) { best = c; bl = lj; }
   }
   vote[q] = bl;
+}
+
+// one thread per (query, cut-off): votes [nq, nk]
+__global__ void majority_vote_multi_kernel(const int64_t* __restrict__ lab, int64_t nq, int k,
+                                           const int32_t* __restrict__ kks, int nk, int tie_mode,
+                                           int64_t* __restrict__ vote) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nq * nk) return;
+  const int64_t q = e / nk;
+  const int kk = kks[e % nk] < k ? kks[e % nk] : k;
+  const int64_t* l = lab + q * k;
+  int best = 0;
+  int64_t bl = INT64_MIN;
+  for (int j = 0; j < kk; ++j) {
+    const int64_t lj = l[j];
+    bool seen = false;  // count each distinct label once, at its first occurrence (Counter insertion order)
+    for (int i = 0; i < j; ++i) seen |= (l[i] == lj);
+    if (seen) continue;
+    int c = 0;
+    for (int i = j; i < kk; ++i) c += (l[i] == lj);
+    if (c > best || (tie_mode == 1 && c == best && lj < bl)) { best = c; bl = lj; }
+  }
+  vote[e] = bl;
 }
 
 // compute_ap / compute_map (test.py:58-146), one warp per query.
@@ -292,6 +348,30 @@ extern "C" int knn_ranked_stats(const uint8_t* rel, int64_t nq, int k, int kk, i
   KNN_REQUIRE(rel, "knn_ranked_stats: null pointer");
   ranked_stats_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(rel, nq, k, kk, hits, first, ap_topk,
                                                                             prec_sum);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+extern "C" int knn_ranked_stats_multi(const uint8_t* rel, int64_t nq, int k, const int32_t* kks, int nk, int32_t* hits,
+                                      int32_t* first, double* ap_topk, double* prec_sum, void* stream) {
+  KNN_REQUIRE(nq >= 0 && k >= 1 && nk >= 1 && nk <= kMaxCutoffs, "knn_ranked_stats_multi: bad sizes (1 <= nk <= %d)",
+              kMaxCutoffs);
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(rel && kks, "knn_ranked_stats_multi: null pointer");
+  ranked_stats_multi_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(rel, nq, k, kks, nk, hits, first,
+                                                                                  ap_topk, prec_sum);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+extern "C" int knn_majority_vote_multi(const int64_t* lab, int64_t nq, int k, const int32_t* kks, int nk, int tie_mode,
+                                       int64_t* vote, void* stream) {
+  KNN_REQUIRE(nq >= 0 && k >= 1 && nk >= 1, "knn_majority_vote_multi: bad sizes");
+  KNN_REQUIRE(tie_mode == 0 || tie_mode == 1, "knn_majority_vote_multi: bad tie_mode");
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(lab && kks && vote, "knn_majority_vote_multi: null pointer");
+  majority_vote_multi_kernel<<<blocks_for(nq * nk, 128), 128, 0, (cudaStream_t)stream>>>(lab, nq, k, kks, nk, tie_mode,
+                                                                                        vote);
   KNN_LAUNCHED();
   return KNN_OK;
 }

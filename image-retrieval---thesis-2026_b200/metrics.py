@@ -92,6 +92,58 @@ def ranked_stats(rel: torch.Tensor, kk: Optional[int] = None):
     return hits, first, ap, ps
 
 
+def ranked_stats_multi(rel: torch.Tensor, cutoffs: Sequence[int]):
+    """The statistics of :func:`ranked_stats` at every cut-off in ONE launch (``knn_ranked_stats_multi``) and one
+    read-back: -> numpy (hits int32 [Q, nk], first int32 [Q] over the first max(cutoffs) items, ap_topk f64 [Q, nk],
+    prec_sum f64 [Q, nk]).  Cut-offs beyond the list length are clamped to it."""
+    _require_cuda(rel)
+    rel = rel.contiguous()
+    nq, k = rel.shape
+    dev = rel.device
+    cuts = [int(c) for c in cutoffs]
+    outs = []
+    for c0 in range(0, len(cuts), 16):
+        part = cuts[c0:c0 + 16]
+        nk = len(part)
+        kks = torch.as_tensor(part, dtype=torch.int32, device=dev)
+        hits = torch.empty((nq, nk), dtype=torch.int32, device=dev)
+        first = torch.empty((nq,), dtype=torch.int32, device=dev)
+        ap = torch.empty((nq, nk), dtype=torch.float64, device=dev)
+        ps = torch.empty((nq, nk), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.load().knn_ranked_stats_multi(_ptr(rel), nq, k, _ptr(kks), nk, _ptr(hits), _ptr(first), _ptr(ap),
+                                                 _ptr(ps), _stream(rel))
+        L.check(rc, "knn_ranked_stats_multi")
+        outs.append((hits, first, ap, ps))
+    # one packed read-back: [hits | ap | ps] per part as float64 columns + first
+    packed = torch.cat([torch.cat([h.double(), a, p], 1) for h, _, a, p in outs] +
+                       [torch.stack([o[1] for o in outs], 1).double()], 1).cpu().numpy()
+    hits_l, ap_l, ps_l, col = [], [], [], 0
+    for h, _, _, _ in outs:
+        nk = h.shape[1]
+        hits_l.append(packed[:, col:col + nk].astype(np.int32))
+        ap_l.append(packed[:, col + nk:col + 2 * nk])
+        ps_l.append(packed[:, col + 2 * nk:col + 3 * nk])
+        col += 3 * nk
+    first = packed[:, col:].astype(np.int32)
+    first_any = np.where((first > 0).any(1), np.where(first > 0, first, np.iinfo(np.int32).max).min(1), 0).astype(np.int32)
+    return np.concatenate(hits_l, 1), first_any, np.concatenate(ap_l, 1), np.concatenate(ps_l, 1)
+
+
+def majority_vote_multi(retrieved_labels: torch.Tensor, cutoffs: Sequence[int], tie: str = "first") -> np.ndarray:
+    """Majority label at every cut-off in one launch + one read-back (``knn_majority_vote_multi``) -> int64 [Q, nk]."""
+    _require_cuda(retrieved_labels)
+    lab = retrieved_labels.contiguous().long()
+    nq, k = lab.shape
+    kks = torch.as_tensor([int(c) for c in cutoffs], dtype=torch.int32, device=lab.device)
+    vote = torch.empty((nq, len(cutoffs)), dtype=torch.int64, device=lab.device)
+    with torch.cuda.device(lab.device):
+        rc = L.load().knn_majority_vote_multi(_ptr(lab), nq, k, _ptr(kks), len(cutoffs), 0 if tie == "first" else 1,
+                                              _ptr(vote), _stream(lab))
+    L.check(rc, "knn_majority_vote_multi")
+    return vote.cpu().numpy()
+
+
 def majority_vote_labels(retrieved_labels: torch.Tensor, kk: int, tie: str = "first") -> torch.Tensor:
     """Majority label of the first kk retrieved labels.  tie='first': collections.Counter.most_common
     (test.py:149-161); tie='smallest': torch.mode / np.unique+argmax (train_ath.py:208)."""
@@ -245,11 +297,8 @@ def classification_metrics_from_topk(indices: torch.Tensor, qlabels, glabels, k_
                                      tie: str = "first") -> Dict[int, Dict[str, float]]:
     _, lab = relevance_single(indices, qlabels, glabels)
     true = _dev_i64(qlabels, indices.device).view(-1).cpu().numpy()
-    out = {}
-    for k in k_values:
-        pred = majority_vote_labels(lab, k, tie).cpu().numpy()
-        out[k] = _prf_from_predictions(true, pred)
-    return out
+    votes = majority_vote_multi(lab, list(k_values), tie)          # every k in one launch, one read-back
+    return {k: _prf_from_predictions(true, votes[:, j]) for j, k in enumerate(k_values)}
 
 
 def compute_classification_metrics(labels: torch.Tensor, dists: torch.Tensor, k_values=[1, 5, 10, 15, 20]):
@@ -281,20 +330,23 @@ def compute_metrics(query_codes, query_labels, gallery_codes, gallery_labels, qu
     pos = torch.searchsorted(uniq, ql).clamp(max=uniq.numel() - 1)
     total_rel = torch.where(uniq[pos] == ql, counts[pos], torch.zeros_like(counts[pos])).cpu().numpy()
     retrieval = {}
-    for topk in topk_values:
-        hits, first, ap, _ = ranked_stats(rel, topk)
-        hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
-        vote = majority_vote_labels(lab, topk, "first")
+    cuts = [int(t) for t in topk_values]
+    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts)    # every cut-off: one launch, one read-back
+    votes = majority_vote_multi(lab, cuts, "first")
+    ql_np = ql.cpu().numpy()
+    for j, topk in enumerate(topk_values):
+        hits_np = hits_all[:, j]
+        first_k = np.where((first_np > 0) & (first_np <= cuts[j]), first_np, 0)   # first hit inside this cut-off
         with np.errstate(divide="ignore", invalid="ignore"):
-            rr = np.where(first_np > 0, 1.0 / np.maximum(first_np, 1), 0.0)
+            rr = np.where(first_k > 0, 1.0 / np.maximum(first_k, 1), 0.0)
             rec = np.where(total_rel > 0, hits_np / np.maximum(total_rel, 1), 0.0)
         retrieval[topk] = {
             "mhr": float(np.mean((hits_np > 0).astype(np.float64))),
-            "map": float(np.mean(ap.cpu().numpy())),
+            "map": float(np.mean(ap_all[:, j])),
             "mrr": float(np.mean(rr)),
             "mp@k": float(np.mean(hits_np / topk)),
             "r@k": float(np.mean(rec)),
-            "majority_acc": float(np.mean((vote == ql).cpu().numpy().astype(np.float64))),
+            "majority_acc": float(np.mean((votes[:, j] == ql_np).astype(np.float64))),
         }
     classification_acc = None
     if query_logits is not None:
@@ -321,9 +373,11 @@ def evaluate_results_from_topk(vals: torch.Tensor, indices: torch.Tensor, qlabel
         "num_queries": float(rel.shape[0]),
         "num_valid_ap_queries": float(len(aps)),
     }
-    for k in ks:
+    ks = list(ks)
+    hits_all = ranked_stats_multi(rel, [min(int(k), nhits) for k in ks])[0] if ks else None
+    for j, k in enumerate(ks):
         kk = min(int(k), nhits)
-        hk = ranked_stats(rel, kk)[0].cpu().numpy().astype(np.float64)
+        hk = hits_all[:, j].astype(np.float64)
         # precision_at_k = float(np.mean(relevances[:k])) over float64 0/1 entries: sum is exact, one division
         p = hk / kk
         with np.errstate(divide="ignore", invalid="ignore"):
@@ -341,8 +395,9 @@ def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch
     _, rel_any = relevance_multilabel(indices, qm, gm, 0.0)
     nq = rel_any.shape[0]
     out = {}
-    for k in k_values:
-        hk = ranked_stats(rel_any, k)[0].cpu().numpy()
+    hits_all = ranked_stats_multi(rel_any, list(k_values))[0]
+    for j, k in enumerate(k_values):
+        hk = hits_all[:, j]
         total_precision = _seq_sum(hk.astype(np.float64) / k)   # total_precision += num_matches / k
         total_recall = int((hk > 0).sum())
         out[k] = (float(total_precision / nq * 100), float(total_recall / nq * 100))
@@ -384,9 +439,9 @@ def retrieval_metrics_from_ranking(idx: torch.Tensor, labels: Sequence,
     hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
     aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)
     metrics: Dict[str, float] = {"num_samples": float(len(inv)), "mAP": float(np.mean(aps) * 100.0)}
-    for k in k_values:
-        hk = ranked_stats(rel, k)[0].cpu().numpy()
-        hk = np.where(hits_np > 0, hk, 0)
+    hits_all = ranked_stats_multi(rel, k_values)[0] if k_values else None
+    for j, k in enumerate(k_values):
+        hk = np.where(hits_np > 0, hits_all[:, j], 0)
         metrics[f"mP@{k}"] = float(np.mean(hk / k) * 100.0)
         metrics[f"R@{k}"] = float(np.mean((hk > 0).astype(np.float64)) * 100.0)
     return metrics
@@ -526,10 +581,12 @@ def evaluate_retrieval(image_features: torch.Tensor, labels, topk_values) -> Dic
     rel, lab = relevance_single(idx, lab_dev, lab_dev)
     true = lab_dev.cpu().numpy()
     results: Dict[str, float] = {}
-    for k in topk_values:
-        hits = ranked_stats(rel, int(k))[0].cpu().numpy()
-        pred = majority_vote_labels(lab, int(k), "smallest").cpu().numpy()
-        prf = _prf_from_predictions(true, pred)
+    cuts = [int(k) for k in topk_values]
+    hits_all = ranked_stats_multi(rel, cuts)[0]
+    votes = majority_vote_multi(lab, cuts, "smallest")
+    for j, k in enumerate(topk_values):
+        hits = hits_all[:, j]
+        prf = _prf_from_predictions(true, votes[:, j])
         results[f"r_at_{k}"] = float(np.mean(hits > 0) * 100.0)
         results[f"majority_accuracy_at_{k}"] = prf["accuracy"]
         results[f"majority_macro_f1_at_{k}"] = prf["f1_macro"]
@@ -552,16 +609,19 @@ def compute_retrieval_metrics(query_codes, query_labels, gallery_codes, gallery_
     ql, gl = _dev_i64(query_labels, idx.device).view(-1), _dev_i64(gallery_labels, idx.device).view(-1)
     rel, lab = relevance_single(idx, ql, gl)
     results = {}
-    for topk in topk_values:
-        hits, first, ap, _ = ranked_stats(rel, int(topk))
-        hits_np, first_np = hits.cpu().numpy(), first.cpu().numpy()
-        vote = majority_vote_labels(lab, int(topk), "smallest")
-        rr = np.where(first_np > 0, 1.0 / np.maximum(first_np, 1), 0.0)
+    cuts = [int(t) for t in topk_values]
+    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts)
+    votes = majority_vote_multi(lab, cuts, "smallest")
+    ql_np = ql.cpu().numpy()
+    for j, topk in enumerate(topk_values):
+        hits_np = hits_all[:, j]
+        first_k = np.where((first_np > 0) & (first_np <= cuts[j]), first_np, 0)
+        rr = np.where(first_k > 0, 1.0 / np.maximum(first_k, 1), 0.0)
         results[topk] = {
             "mhr": float(np.mean((hits_np > 0).astype(np.float64))),
-            "map": float(np.mean(ap.cpu().numpy())),
+            "map": float(np.mean(ap_all[:, j])),
             "mrr": float(np.mean(rr)),
-            "majority_acc": float(np.mean((vote == ql).cpu().numpy().astype(np.float64))),
+            "majority_acc": float(np.mean((votes[:, j] == ql_np).astype(np.float64))),
         }
     return results
 
@@ -591,10 +651,8 @@ def retrieval_accuracy_from_ranks(ranks: np.ndarray, labels, topk, device=None) 
     idx = _ranks_topk_device(ranks, kmax, device)
     lab = torch.from_numpy(codes).to(device)
     rel, _ = relevance_single(idx, lab, lab)
-    out = []
-    for k in topk:
-        correct = int((ranked_stats(rel, min(int(k), kmax))[0] > 0).sum().item())
-        out.append((correct * 100.0) / max(1, n))
+    hits_all = ranked_stats_multi(rel, [min(int(k), kmax) for k in topk])[0]
+    out = [(int((hits_all[:, j] > 0).sum()) * 100.0) / max(1, n) for j in range(len(topk))]
     return np.array(out, dtype=np.float64)
 
 
@@ -608,8 +666,9 @@ def compute_classification_metrics_from_ranks(labels, ranks: np.ndarray, k_value
     lab = torch.from_numpy(codes).to(device)
     _, retrieved = relevance_single(idx, lab, lab)
     results = {}
-    for k in k_values:
-        y_pred = majority_vote_labels(retrieved, min(int(k), kmax), "first").cpu().numpy()
+    votes = majority_vote_multi(retrieved, [min(int(k), kmax) for k in k_values], "first")
+    for j, k in enumerate(k_values):
+        y_pred = votes[:, j]
         y_true = codes
         classes = np.unique(np.concatenate([y_true, y_pred], axis=0))
         per_p, per_r, per_f, supports = [], [], [], []

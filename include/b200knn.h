@@ -246,12 +246,21 @@ KNN_API int knn_relevance_multilabel(const int64_t* idx, int64_t nq, int k, cons
 KNN_API int knn_ranked_stats(const uint8_t* rel, int64_t nq, int k, int kk,
                      int32_t* hits, int32_t* first, double* ap_topk, double* prec_sum, void* stream);
 
+/* The same statistics at nk <= 16 cut-offs kks[t] (device int32, each clamped to k) in ONE launch -- the k-loops of
+ * test_ath.py:112-170 (`for topk in topk_values`), evaluate_nih_zilliz.py:56-62, test.py:1031-1056 without a launch and
+ * a read-back per cut-off.  hits / ap_topk / prec_sum: [nq,nk]; first: [nq] over the first max(kks) items. */
+KNN_API int knn_ranked_stats_multi(const uint8_t* rel, int64_t nq, int k, const int32_t* kks, int nk, int32_t* hits,
+                           int32_t* first, double* ap_topk, double* prec_sum, void* stream);
+
 /* Majority vote over the first kk retrieved labels (lab [nq,k] int64).
  * tie_mode 0: first label reaching the max count in rank order (collections.Counter.most_common,
  *             test.py:149-161, test_ath.py:153);  tie_mode 1: smallest label (torch.mode train_ath.py:208,
  *             np.unique+argmax evaluate_medsiglip.py:156-157). vote [nq] int64. */
 KNN_API int knn_majority_vote(const int64_t* lab, int64_t nq, int k, int kk, int tie_mode, int64_t* vote,
                       void* stream);
+/* ... for nk cut-offs kks[t] (device int32) in one launch: vote [nq,nk] (`for k in k_values`, test.py:186-205). */
+KNN_API int knn_majority_vote_multi(const int64_t* lab, int64_t nq, int k, const int32_t* kks, int nk, int tie_mode,
+                            int64_t* vote, void* stream);
 
 /* Trapezoidal AP of compute_ap/compute_map (test.py:58-146) from a full ranking.
  * ranks [nq,ng] int64 row-major = for query i the gallery rows best-first (the reference passes the
