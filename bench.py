@@ -326,8 +326,9 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         return sharded_prepared.search(q_dev, k)
 
     def step_e2e():
-        qd = q_host.to(dev, non_blocking=True)
-        v, i = sharded.search(qd, k)                      # public API: normalise+cast, search, exchange, merge
+        # public API on a HOST batch: this rank copies its 1/N slice, normalises + casts it, the prepared slices are
+        # all-gathered over NVLink; then search, candidate exchange, shard merge, results back to the host
+        v, i = sharded.search_host(q_host, k)
         out_val_host.copy_(v, non_blocking=True)
         out_idx_host.copy_(i, non_blocking=True)
         return v, i
@@ -359,9 +360,12 @@ def run_workload(name, args, ctx, steps, warmup, primary):
     # ---- timed region: device-resident, clocks sampled; the library records CUDA events around its kernels on the
     # launching stream during these very steps (no synchronisation), read back after the region has ended ----------
     lib.knn_profile_enable(1)
+    sharded_prepared.profile(world > 1)
     launches0 = lib.knn_launch_count()
     with ClockSampler(ctx["local_rank"]) as clocks:
         total_ms = timed(step_resident, steps)
+    xprof = sharded_prepared.profile_read()[-steps:] if world > 1 else []
+    sharded_prepared.profile(False)
     launches = lib.knn_launch_count() - launches0            # counted by the library at every launch site
     kern_ms = []
     n_prof = lib.knn_profile_count()
@@ -418,8 +422,10 @@ def run_workload(name, args, ctx, steps, warmup, primary):
             "algorithmic_bytes": algo_bytes,
             "peak_source": peaks["source"],
         }),
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
-                "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / steps},
+        # every rank copies its 1/N slice of the fp32 batch in and the whole result out
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": ((nq + world - 1) // world) * d * 4,
+                "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / steps,
+                "note": "bytes per rank; the prepared query slices travel between the GPUs over NVLink (all-gather)"},
         # per step: seeding pre-pass + seeding merge + distance/selection kernel + unit merge
         # (+ k-way shard merge after the exchange)
         "gpu_launches": int(launches),
@@ -438,13 +444,21 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         line["roofline"]["mma_frac_of_peak"] = 3.0 * achieved / peaks["tflops"]
         line["config"]["unverified_queries_rerun_on_ffma"] = S._search_exact_tensor.last_unverified
     if world > 1:  # per-rank view of the same timed region: which rank the max-over-ranks step time waits for
-        mine = torch.tensor([dist_ms, seed_ms, merge_ms, float(clocks.summary()["sm_mhz"] or 0)], device=dev)
-        allr = torch.empty((world, 4), device=dev)
+        n = max(len(xprof), 1)
+        local_ms = sum(x[0] for x in xprof) / n            # local search (seeding + kernel + unit merge) of a step
+        wait_ms = sum(x[1] for x in xprof) / n             # device barrier of the exchange = wait for the slowest shard
+        xmerge_ms = sum(x[2] for x in xprof) / n           # shard merge reading the peers' candidates over NVLink
+        mine = torch.tensor([dist_ms, seed_ms, merge_ms, float(clocks.summary()["sm_mhz"] or 0), local_ms, wait_ms,
+                             xmerge_ms], device=dev)
+        allr = torch.empty((world, 7), device=dev)
         dist.all_gather_into_tensor(allr, mine)
         line["per_rank"] = {"kernel_ms": [round(x, 3) for x in allr[:, 0].tolist()],
                             "seeding_ms": [round(x, 3) for x in allr[:, 1].tolist()],
                             "unit_merge_ms": [round(x, 3) for x in allr[:, 2].tolist()],
-                            "sm_mhz": [int(x) for x in allr[:, 3].tolist()]}
+                            "sm_mhz": [int(x) for x in allr[:, 3].tolist()],
+                            "local_search_ms": [round(x, 3) for x in allr[:, 4].tolist()],
+                            "barrier_wait_ms": [round(x, 3) for x in allr[:, 5].tolist()],
+                            "exchange_merge_ms": [round(x, 3) for x in allr[:, 6].tolist()]}
     # ---- correctness of this very configuration (after the timed regions) ------------------------------------
     try:
         result = step_resident()

@@ -176,8 +176,21 @@ class FlatIndex:
         if self.rows is None:
             raise L.KnnError("FlatIndex is empty")
         _require_cuda(queries)
-        q, qsq = _prepare(queries.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
-                          self.metric == "l2")
+        q, qsq = self.prepare_queries(queries)
+        return self.search_prepared(q, qsq, k, exclude_self=exclude_self, self_mode=self_mode,
+                                    query_offset=query_offset, out=out)
+
+    def prepare_queries(self, queries: torch.Tensor):
+        """The query-side half of :meth:`search`: rows in the search dtype (normalised when the index normalises) and
+        their squared norms (L2 metric only).  Row-wise, so a batch may be prepared in slices (sharded.search_host)."""
+        return _prepare(queries.to(self.device), self.normalize, self.precision, self.eps, self.eps_mode,
+                        self.metric == "l2")
+
+    def search_prepared(self, q: torch.Tensor, qsq: Optional[torch.Tensor], k: int, *, exclude_self: bool = False,
+                        self_mode: Optional[str] = None, query_offset: int = 0, out=None):
+        """:meth:`search` for queries that went through :meth:`prepare_queries` already."""
+        if self.rows is None:
+            raise L.KnnError("FlatIndex is empty")
         mode = self_mode or ("exclude" if exclude_self else "keep")
         if self.precision == "fp32" and exact_engine(q.shape[0], self.ntotal, self.dim, int(k), self.device,
                                                      self._filter is not None) == "tensor":

@@ -110,6 +110,7 @@ class ShardedFlatIndex:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.exchange = exchange
         self._peer: Optional[PeerExchange] = None
+        self._prof = None
 
     @classmethod
     def from_full(cls, gallery: torch.Tensor, metric: str = "cosine", precision: str = "fp32", *,
@@ -125,7 +126,10 @@ class ShardedFlatIndex:
         return cls(idx, group, exchange)
 
     # --- the two device steps; tests replace them to exercise the exchange logic without a GPU ---------
-    def _search_local(self, queries, k, self_mode, query_offset, out=None):
+    def _search_local(self, queries, k, self_mode, query_offset, out=None, prepared=None):
+        if prepared is not None:
+            return self.local.search_prepared(prepared[0], prepared[1], k, self_mode=self_mode,
+                                              query_offset=query_offset, out=out)
         return self.local.search(queries, k, self_mode=self_mode, query_offset=query_offset, out=out)
 
     def _merge_parts(self, bufs, nq, k):
@@ -136,28 +140,101 @@ class ShardedFlatIndex:
         base = [b.data_ptr() for b in bufs]
         return merge_topk_parts([p + 8 * n for p in base], base, nq, k, self.local.metric, bufs[0].device)
 
+    # --- optional timing of the steps of a search (CUDA events on the search stream, read back by the caller) ---
+    def profile(self, on: bool = True) -> None:
+        """Record events around the local search / the exchange barrier (or all-gather) / the shard merge of every
+        following search; :meth:`profile_read` returns the per-call durations."""
+        self._prof = [] if on else None
+
+    def profile_read(self):
+        """-> list of (local_ms, exchange_wait_ms, merge_ms) per profiled search.  ``exchange_wait_ms`` is the device
+        barrier of the peer exchange -- the time this rank waited for the slowest shard -- or the all-gather."""
+        out = []
+        for ev in self._prof or []:
+            ev[3].synchronize()
+            out.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+        return out
+
+    def _mark(self, marks):
+        if self._prof is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
     def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
-               query_offset: int = 0, broadcast_queries: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (distances [Q,k], indices [Q,k] global rows), identical on every rank and for every shard count."""
+               query_offset: int = 0, broadcast_queries: bool = False, prepared=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (distances [Q,k], indices [Q,k] global rows), identical on every rank and for every shard count.
+        ``prepared`` = (rows, squared norms) from ``FlatIndex.prepare_queries``: skips the query-side normalise + cast."""
         if broadcast_queries and self.world_size > 1:
             dist.broadcast(queries, src=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
         mode = self_mode or ("exclude" if exclude_self else "keep")
         if self.world_size == 1:
-            return self._search_local(queries, k, mode, query_offset)
-        nq = queries.shape[0]
+            return self._search_local(queries, k, mode, query_offset, prepared=prepared)
+        nq = (prepared[0] if prepared is not None else queries).shape[0]
+        dev = (prepared[0] if prepared is not None else queries).device
         words = 3 * nq * k
+        marks = []
+        self._mark(marks)
         if self.exchange == "peer":
             if self._peer is None:
                 self._peer = PeerExchange(self.group, self.local.device)
             send = self._peer.slot(nq, k)
-            self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k))
+            self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k), prepared=prepared)
             from .search import merge_topk_parts
 
-            val_ptrs, idx_ptrs = self._peer.peer_pointers(nq, k)
-            return merge_topk_parts(val_ptrs, idx_ptrs, nq, k, self.local.metric, self.local.device)
-        # the search writes straight into the send buffer; the gathered buffer is merged where it lies
-        send = torch.empty((words + (words & 1),), dtype=torch.int32, device=queries.device)
-        self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k))
-        gathered = torch.empty((self.world_size * send.numel(),), dtype=torch.int32, device=queries.device)
-        dist.all_gather_into_tensor(gathered, send, group=self.group)
-        return self._merge_parts(list(gathered.view(self.world_size, send.numel())), nq, k)
+            self._mark(marks)
+            val_ptrs, idx_ptrs = self._peer.peer_pointers(nq, k)      # device-side barrier
+            self._mark(marks)
+            res = merge_topk_parts(val_ptrs, idx_ptrs, nq, k, self.local.metric, self.local.device)
+        else:
+            # the search writes straight into the send buffer; the gathered buffer is merged where it lies
+            send = torch.empty((words + (words & 1),), dtype=torch.int32, device=dev)
+            self._search_local(queries, k, mode, query_offset, out=candidate_views(send, nq, k), prepared=prepared)
+            self._mark(marks)
+            gathered = torch.empty((self.world_size * send.numel(),), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gathered, send, group=self.group)
+            self._mark(marks)
+            res = self._merge_parts(list(gathered.view(self.world_size, send.numel())), nq, k)
+        self._mark(marks)
+        if self._prof is not None:
+            self._prof.append(marks)
+            if len(self._prof) > 64:
+                self._prof.pop(0)
+        return res
+
+    def search_host(self, queries_host: torch.Tensor, k: int, *, exclude_self: bool = False,
+                    self_mode: Optional[str] = None, query_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """:meth:`search` for a query batch that lives in HOST memory on every rank (the same batch everywhere): each
+        rank copies only ITS 1/W slice to the device, normalises + casts it to the search dtype, and the prepared slices
+        are all-gathered over NVLink (bf16: Q*D*2 bytes in total) -- instead of W host-to-device copies of the whole fp32
+        batch and W redundant normalisations."""
+        nq = queries_host.shape[0]
+        dev = self.local.device
+        if self.world_size == 1:
+            return self.search(queries_host.to(dev, non_blocking=True), k, exclude_self=exclude_self,
+                               self_mode=self_mode, query_offset=query_offset)
+        per = (nq + self.world_size - 1) // self.world_size          # equal slices (the last ones may be short / empty)
+        s, e = min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+        mine = queries_host[s:e].to(dev, non_blocking=True)
+        want_sq = self.local.metric == "l2"
+        if e > s:
+            q, qsq = self.local.prepare_queries(mine)
+        else:
+            q, qsq = None, None
+        dtype = torch.bfloat16 if self.local.precision == "bf16" else torch.float32
+        dpad = self.local.rows.shape[1]
+        send = torch.zeros((per, dpad), dtype=dtype, device=dev)
+        if q is not None:
+            send[: e - s] = q
+        full = torch.empty((self.world_size * per, dpad), dtype=dtype, device=dev)
+        dist.all_gather_into_tensor(full, send, group=self.group)
+        full_sq = None
+        if want_sq:
+            sq_send = torch.zeros((per,), dtype=torch.float32, device=dev)
+            if qsq is not None:
+                sq_send[: e - s] = qsq
+            full_sq = torch.empty((self.world_size * per,), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(full_sq, sq_send, group=self.group)
+            full_sq = full_sq[:nq]
+        return self.search(None, k, exclude_self=exclude_self, self_mode=self_mode, query_offset=query_offset,
+                           prepared=(full[:nq], full_sq))

@@ -50,6 +50,14 @@ def _worker(rank, world, port, out_dir):
                 v, i = sh.search(q, k)
                 if not (torch.equal(i, want_i) and torch.equal(v, want_v)):
                     failures.append((precision, exchange, rep, int((i != want_i).sum())))
+            # a HOST batch: every rank copies / prepares its slice only, the prepared slices are all-gathered
+            sh.profile(True)
+            v, i = sh.search_host(q.cpu().pin_memory(), k)
+            if not (torch.equal(i, want_i) and torch.equal(v, want_v)):
+                failures.append((precision, exchange, "search_host", int((i != want_i).sum())))
+            prof = sh.profile_read()
+            if len(prof) != 1 or min(prof[0]) < 0.0:
+                failures.append((precision, exchange, "profile", prof))
     torch.cuda.synchronize()
     with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as fh:
         fh.write(repr(failures))

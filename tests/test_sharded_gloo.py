@@ -58,17 +58,22 @@ def _worker(rank, world, port, out_dir):
     rs = np.random.RandomState(0)
     g = oracle.normalize(rs.standard_normal((301, 32)).astype(np.float32))
     g[17] = g[250]  # a tie across the shard boundary: must resolve to the lower global row
-    q = g[:40].copy()
+    q = g[:41].copy()
     start, count = shard_rows(g.shape[0], world)[rank]
+    raw = (q * np.linspace(0.5, 3.0, q.shape[0], dtype=np.float32)[:, None]).astype(np.float32)   # un-normalised copies
 
     class OracleShard(ShardedFlatIndex):
         def __init__(self):
             self.local = FlatIndex.__new__(FlatIndex)
-            self.local.metric = "cosine"
+            self.local.metric, self.local.precision, self.local.device = "cosine", "fp32", torch.device("cpu")
+            self.local.rows = torch.from_numpy(g[start:start + count])
+            # the query-side normalise + cast of the CUDA index, replaced by the oracle's (row-wise, like the kernel)
+            self.local.prepare_queries = lambda x: (torch.from_numpy(oracle.normalize(x.numpy())), None)
             self.group, self.world_size, self.rank = None, world, rank
-            self.exchange, self._peer = "allgather", None
+            self.exchange, self._peer, self._prof = "allgather", None, None
 
-        def _search_local(self, queries, k, self_mode, query_offset, out=None):
+        def _search_local(self, queries, k, self_mode, query_offset, out=None, prepared=None):
+            queries = prepared[0] if prepared is not None else queries
             v, i = oracle.search(queries.numpy(), g[start:start + count], k, "cosine", self_mode, query_offset, start)
             out[0].copy_(torch.from_numpy(v))      # straight into the exchange buffer, as the CUDA search does
             out[1].copy_(torch.from_numpy(i))
@@ -80,8 +85,11 @@ def _worker(rank, world, port, out_dir):
                                      "cosine")
             return torch.from_numpy(v), torch.from_numpy(i)
 
-    v, i = OracleShard().search(torch.from_numpy(q), 10, exclude_self=True)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), v=v.numpy(), i=i.numpy())
+    shard = OracleShard()
+    v, i = shard.search(torch.from_numpy(q), 10, exclude_self=True)
+    # host-resident batch: every rank prepares only its slice (21 + 20 rows), the slices are all-gathered
+    vh, ih = shard.search_host(torch.from_numpy(raw), 10, exclude_self=True)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), v=v.numpy(), i=i.numpy(), vh=vh.numpy(), ih=ih.numpy())
     dist.destroy_process_group()
 
 
@@ -94,7 +102,11 @@ def test_two_rank_search_equals_single_shard(tmp_path):
     rs = np.random.RandomState(0)
     g = oracle.normalize(rs.standard_normal((301, 32)).astype(np.float32))
     g[17] = g[250]
-    v1, i1 = oracle.search(g[:40].copy(), g, 10, "cosine", "exclude", 0)
+    q = g[:41].copy()
+    v1, i1 = oracle.search(q, g, 10, "cosine", "exclude", 0)
+    raw = (q * np.linspace(0.5, 3.0, q.shape[0], dtype=np.float32)[:, None]).astype(np.float32)
+    v2, i2 = oracle.search(oracle.normalize(raw), g, 10, "cosine", "exclude", 0)
     for r in range(world):
         z = np.load(tmp_path / f"r{r}.npz")
         assert np.array_equal(z["i"], i1) and np.array_equal(z["v"], v1)
+        assert np.array_equal(z["ih"], i2) and np.array_equal(z["vh"], v2)      # search_host == one-shard search
