@@ -446,8 +446,8 @@ def run_workload(name, args, ctx, steps, warmup, primary):
     if world > 1:  # per-rank view of the same timed region: which rank the max-over-ranks step time waits for
         n = max(len(xprof), 1)
         local_ms = sum(x[0] for x in xprof) / n            # local search (seeding + kernel + unit merge) of a step
-        wait_ms = sum(x[1] for x in xprof) / n             # device barrier of the exchange = wait for the slowest shard
-        xmerge_ms = sum(x[2] for x in xprof) / n           # shard merge reading the peers' candidates over NVLink
+        wait_ms = sum(x[1] for x in xprof) / n             # all-gather exchange: the NCCL all-gather; peer exchange: ~0
+        xmerge_ms = sum(x[2] for x in xprof) / n           # peer exchange: wait for the slowest shard + merge over NVLink
         mine = torch.tensor([dist_ms, seed_ms, merge_ms, float(clocks.summary()["sm_mhz"] or 0), local_ms, wait_ms,
                              xmerge_ms], device=dev)
         allr = torch.empty((world, 7), device=dev)
@@ -457,8 +457,8 @@ def run_workload(name, args, ctx, steps, warmup, primary):
                             "unit_merge_ms": [round(x, 3) for x in allr[:, 2].tolist()],
                             "sm_mhz": [int(x) for x in allr[:, 3].tolist()],
                             "local_search_ms": [round(x, 3) for x in allr[:, 4].tolist()],
-                            "barrier_wait_ms": [round(x, 3) for x in allr[:, 5].tolist()],
-                            "exchange_merge_ms": [round(x, 3) for x in allr[:, 6].tolist()]}
+                            "allgather_ms": [round(x, 3) for x in allr[:, 5].tolist()],
+                            "exchange_wait_plus_merge_ms": [round(x, 3) for x in allr[:, 6].tolist()]}
     # ---- correctness of this very configuration (after the timed regions) ------------------------------------
     try:
         result = step_resident()

@@ -55,6 +55,7 @@ SIGNATURES = {
     "knn_rank_rows_workspace": (_sz, [_i64, _i64]),
     "knn_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
     "knn_merge_topk_parts": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
+    "knn_merge_topk_parts_sync": (_i, [_p, _p, _i, _i64, _i, _i, _p, _i, _i, _p, _p, _p]),
     "knn_relevance_single": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
     "knn_relevance_multilabel": (_i, [_p, _i64, _i, _p, _p, _i64, _d, _i, _p, _p, _p]),
     "knn_ranked_stats": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),

@@ -339,11 +339,35 @@ struct MergeParts {
   const int64_t* idx[kMaxMergeParts];
   const float* val[kMaxMergeParts];
 };
+struct PeerFlags {
+  int32_t* flags[kMaxMergeParts];   // flags[p] = rank p's flag array (int32 [parts]) as mapped into this process
+};
+
+// Peer exchange without a separate barrier kernel: every rank publishes the number of the current search (`epoch`) into
+// slot [rank] of EVERY rank's flag array once its candidates are written (release, system scope); the merge kernel's CTAs
+// wait until all slots of THEIR rank's array have reached the epoch (acquire) before they read the peers' lists.
+__global__ void peer_signal_kernel(PeerFlags pf, int parts, int rank, int epoch) {
+  if ((int)threadIdx.x < parts) {
+    __threadfence_system();   // the candidate lists (written by the kernels before this one) before the flag
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(pf.flags[threadIdx.x] + rank), "r"(epoch) : "memory");
+  }
+}
 
 __global__ void __launch_bounds__(256) merge_topk_kernel(MergeParts mp, int parts, int64_t nq, int k, int l2,
                                                         float* __restrict__ out_val,
-                                                        int64_t* __restrict__ out_idx) {
+                                                        int64_t* __restrict__ out_idx,
+                                                        const int32_t* __restrict__ my_flags, int epoch) {
   extern __shared__ __align__(16) uint8_t sm[];
+  if (my_flags != nullptr) {
+    if ((int)threadIdx.x < parts) {
+      int v;
+      do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(my_flags + threadIdx.x) : "memory");
+        if (v < epoch) __nanosleep(64);
+      } while (v < epoch);
+    }
+    __syncthreads();
+  }
   int64_t* sid = reinterpret_cast<int64_t*>(sm);                 // [parts*k]
   uint32_t* so = reinterpret_cast<uint32_t*>(sid + parts * k);   // [parts*k]
   float* sv = reinterpret_cast<float*>(so + parts * k);          // [parts*k]
@@ -380,12 +404,18 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(MergeParts mp, int part
 }
 
 static int launch_merge_parts(const MergeParts& mp, int parts, int64_t nq, int k, int metric, float* out_val,
-                              int64_t* out_idx, cudaStream_t stream) {
+                              int64_t* out_idx, cudaStream_t stream, const PeerFlags* pf = nullptr, int rank = 0,
+                              int epoch = 0) {
   const size_t smem = (size_t)parts * k * 16;
   KNN_REQUIRE(smem <= 200 * 1024, "knn_merge_topk: parts*k=%d too large (max %d)", parts * k, 200 * 1024 / 16);
+  if (pf != nullptr) {   // published even for an empty batch: the peers wait for it
+    peer_signal_kernel<<<1, 32, 0, stream>>>(*pf, parts, rank, epoch);
+    KNN_LAUNCHED();
+  }
   if (nq == 0) return KNN_OK;
   KNN_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<(unsigned)nq, 256, smem, stream>>>(mp, parts, nq, k, metric == KNN_L2 ? 1 : 0, out_val, out_idx);
+  merge_topk_kernel<<<(unsigned)nq, 256, smem, stream>>>(mp, parts, nq, k, metric == KNN_L2 ? 1 : 0, out_val, out_idx,
+                                                         pf ? pf->flags[rank] : nullptr, epoch);
   KNN_LAUNCHED();
   return KNN_OK;
 }
@@ -633,6 +663,25 @@ extern "C" int knn_merge_topk_parts(const float* const* val_parts_host, const in
     mp.val[p] = val_parts_host[p];
   }
   return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream);
+}
+
+extern "C" int knn_merge_topk_parts_sync(const float* const* val_parts_host, const int64_t* const* idx_parts_host,
+                                         int parts, int64_t nq, int k, int metric, int32_t* const* flags_host, int rank,
+                                         int epoch, float* out_val, int64_t* out_idx, void* stream) {
+  KNN_REQUIRE(val_parts_host && idx_parts_host && flags_host && (nq == 0 || (out_val && out_idx)),
+              "knn_merge_topk_parts_sync: null pointer");
+  KNN_REQUIRE(parts >= 1 && parts <= kMaxMergeParts && parts <= 32 && k >= 1 && nq >= 0 && rank >= 0 && rank < parts,
+              "knn_merge_topk_parts_sync: bad sizes parts=%d (max %d) rank=%d k=%d nq=%lld", parts, kMaxMergeParts, rank, k,
+              (long long)nq);
+  MergeParts mp;
+  PeerFlags pf;
+  for (int p = 0; p < parts; ++p) {
+    KNN_REQUIRE(val_parts_host[p] && idx_parts_host[p] && flags_host[p], "knn_merge_topk_parts_sync: null part %d", p);
+    mp.idx[p] = idx_parts_host[p];
+    mp.val[p] = val_parts_host[p];
+    pf.flags[p] = flags_host[p];
+  }
+  return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream, &pf, rank, epoch);
 }
 
 static int64_t rank_npad(int64_t ng) {

@@ -574,9 +574,12 @@ def rank_rows(scores: torch.Tensor, largest_first: bool = True) -> torch.Tensor:
     return ranks
 
 
-def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device) -> Tuple[torch.Tensor, torch.Tensor]:
+def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device, flag_ptrs=None, rank: int = 0,
+                     epoch: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """k-way merge of separately placed per-shard lists given as raw DEVICE addresses (``knn_merge_topk_parts``):
-    slices of an all-gathered buffer, or the peers' symmetric-memory buffers (fused exchange + merge)."""
+    slices of an all-gathered buffer, or the peers' symmetric-memory buffers (fused exchange + merge).  With
+    ``flag_ptrs`` (every rank's flag array as mapped here) the synchronisation of the exchange runs inside
+    (``knn_merge_topk_parts_sync``): this rank publishes ``epoch``, the merge waits for every peer's."""
     import ctypes
 
     parts = len(val_ptrs)
@@ -585,8 +588,13 @@ def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device) -
     vp = (ctypes.c_void_p * parts)(*[int(p) for p in val_ptrs])
     ip = (ctypes.c_void_p * parts)(*[int(p) for p in idx_ptrs])
     with torch.cuda.device(device):
-        rc = L.load().knn_merge_topk_parts(vp, ip, parts, nq, k, _METRICS[metric], _ptr(out_val), _ptr(out_idx),
-                                           torch.cuda.current_stream(device).cuda_stream)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if flag_ptrs is None:
+            rc = L.load().knn_merge_topk_parts(vp, ip, parts, nq, k, _METRICS[metric], _ptr(out_val), _ptr(out_idx), stream)
+        else:
+            fp = (ctypes.c_void_p * parts)(*[int(p) for p in flag_ptrs])
+            rc = L.load().knn_merge_topk_parts_sync(vp, ip, parts, nq, k, _METRICS[metric], fp, int(rank), int(epoch),
+                                                    _ptr(out_val), _ptr(out_idx), stream)
     L.check(rc, "knn_merge_topk_parts")
     return out_val, out_idx
 

@@ -52,10 +52,12 @@ def candidate_views(buf: torch.Tensor, nq: int, k: int) -> Tuple[torch.Tensor, t
 
 class PeerExchange:
     """Candidate exchange over NVLink peer memory instead of an all-gather: every rank's search writes its ``[Q,k]``
-    candidates into ITS symmetric-memory buffer; after one device-side barrier every rank's merge kernel
-    (``knn_merge_topk_parts``) reads all W buffers directly through the peer mappings.  Two alternating slots make
-    ONE barrier per search sufficient: a slot is rewritten two searches later, i.e. after the next search's barrier,
-    which a rank's stream reaches only behind its own merge of this slot -- so every peer has finished reading it."""
+    candidates into ITS symmetric-memory buffer, publishes the number of the search in every rank's flag array, and
+    every rank's merge kernel (``knn_merge_topk_parts_sync``) waits for all flags and then reads all W buffers directly
+    through the peer mappings -- signal, wait and merge are two launches, no barrier kernel (the library barrier of
+    torch's symmetric memory cost ~1 ms per search on 8 GPUs).  Two alternating slots: a slot is rewritten two searches
+    later, and a peer publishes search e+1 only behind its own merge of search e, so when this rank's merge e+1 has seen
+    every flag, every peer has finished reading slot e."""
 
     def __init__(self, group, device: torch.device):
         self.group = group if group is not None else dist.group.WORLD
@@ -64,13 +66,21 @@ class PeerExchange:
         self.buf = None
         self.hdl = None
         self.turn = 0
+        self.epoch = 0
+        self.flags = None
+        self.flag_hdl = None
         self._retired = []       # outgrown buffers stay mapped: a peer's merge may still be reading them
 
     def _ensure(self, words: int) -> None:
-        if words <= self.capacity:
-            return
         import torch.distributed._symmetric_memory as symm_mem
 
+        if self.flags is None:
+            self.flags = symm_mem.empty((64,), dtype=torch.int32, device=self.device)
+            self.flags.zero_()
+            self.flag_hdl = symm_mem.rendezvous(self.flags, self.group)
+            self.flag_hdl.barrier(channel=0)   # once: every rank's flags are zero before anybody publishes
+        if words <= self.capacity:
+            return
         # the capacity must be identical on every rank: it only depends on (Q, k), which are
         cap = max(words, 1 << 16)
         if self.buf is not None:
@@ -85,14 +95,14 @@ class PeerExchange:
         words = 3 * nq * k
         self._ensure(words + (words & 1))
         self.turn ^= 1
+        self.epoch += 1
         return self.buf[self.turn * self.capacity: self.turn * self.capacity + words]
 
     def peer_pointers(self, nq: int, k: int):
-        """Device-side barrier (orders the merge after every peer's search), then the W (val, idx) addresses."""
-        self.hdl.barrier(channel=self.turn)
+        """-> the W (val, idx) addresses of the current slot and the W flag arrays (all as mapped into this process)."""
         n = nq * k
         base = [int(p) + self.turn * self.capacity * 4 for p in self.hdl.buffer_ptrs]
-        return [b + 8 * n for b in base], base
+        return [b + 8 * n for b in base], base, [int(p) for p in self.flag_hdl.buffer_ptrs]
 
 
 class ShardedFlatIndex:
@@ -147,8 +157,9 @@ class ShardedFlatIndex:
         self._prof = [] if on else None
 
     def profile_read(self):
-        """-> list of (local_ms, exchange_wait_ms, merge_ms) per profiled search.  ``exchange_wait_ms`` is the device
-        barrier of the peer exchange -- the time this rank waited for the slowest shard -- or the all-gather."""
+        """-> list of (local_ms, gather_ms, merge_ms) per profiled search.  Peer exchange: ``merge_ms`` holds the wait
+        for the slowest shard + the merge over NVLink (one kernel), ``gather_ms`` is ~0; all-gather exchange:
+        ``gather_ms`` is the NCCL all-gather."""
         out = []
         for ev in self._prof or []:
             ev[3].synchronize()
@@ -183,9 +194,11 @@ class ShardedFlatIndex:
             from .search import merge_topk_parts
 
             self._mark(marks)
-            val_ptrs, idx_ptrs = self._peer.peer_pointers(nq, k)      # device-side barrier
+            val_ptrs, idx_ptrs, flag_ptrs = self._peer.peer_pointers(nq, k)
             self._mark(marks)
-            res = merge_topk_parts(val_ptrs, idx_ptrs, nq, k, self.local.metric, self.local.device)
+            # publish this search's number, wait for every peer's, merge over NVLink: inside the library call
+            res = merge_topk_parts(val_ptrs, idx_ptrs, nq, k, self.local.metric, self.local.device,
+                                   flag_ptrs=flag_ptrs, rank=self.rank, epoch=self._peer.epoch)
         else:
             # the search writes straight into the send buffer; the gathered buffer is merged where it lies
             send = torch.empty((words + (words & 1),), dtype=torch.int32, device=dev)

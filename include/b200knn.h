@@ -221,6 +221,16 @@ KNN_API int knn_merge_topk(const float* vals, const int64_t* idx, int parts, int
  * (the caller orders it after every peer's search with a device-side barrier). */
 KNN_API int knn_merge_topk_parts(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
                          int64_t nq, int k, int metric, float* out_val, int64_t* out_idx, void* stream);
+/* ... with the synchronisation of the exchange inside: flags_host[p] = DEVICE address of rank p's flag array
+ * (int32 [parts], zero-initialised peer-mapped memory), rank = this process, epoch = the number of this search (strictly
+ * increasing from 1).  A one-warp kernel first publishes `epoch` into slot [rank] of EVERY rank's array -- ordered after
+ * this rank's candidates, which the preceding kernels on `stream` wrote -- and every CTA of the merge kernel waits until
+ * all `parts` slots of THIS rank's array have reached it before reading the peers' lists: no separate barrier, the wait of
+ * one query's merge overlaps nothing but the slowest shard.  (A buffer may be rewritten two searches later: a peer
+ * publishes epoch e+1 only behind its own merge of epoch e.) */
+KNN_API int knn_merge_topk_parts_sync(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
+                              int64_t nq, int k, int metric, int32_t* const* flags_host, int rank, int epoch,
+                              float* out_val, int64_t* out_idx, void* stream);
 
 /* Single-label relevance of retrieved lists: rel[i,j] = (glab[idx[i,j]] == qlab[i]), 0 for idx < 0.
  * Building block of retrieval_accuracy (test.py:38-54), compute_metrics (test_ath.py:90-172),
