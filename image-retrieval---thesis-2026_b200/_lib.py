@@ -71,6 +71,10 @@ SIGNATURES = {
     "knn_ap_from_ranks": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "knn_ap_sklearn_from_ranks": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
     "knn_ap_sklearn_from_ranks_workspace": (_sz, [_i64, _i64]),
+    "knn_triplet_mine": (_i, [_p, _p, _i64, _f, _p, _p, _p, _p, _p]),
+    "knn_jaccard_matrix": (_i, [_p, _p, _i64, _i64, _f, _p, _p]),
+    "knn_class_means": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p]),
+    "knn_centroid_min_dist": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
 }
 
 _lock = threading.Lock()

@@ -341,6 +341,29 @@ KNN_API int knn_ap_sklearn_from_ranks(const int32_t* pos_ge, const int32_t* pos_
                               void* stream);
 KNN_API size_t knn_ap_sklearn_from_ranks_workspace(int64_t nq, int64_t ld);
 
+/* Training-time pairwise operations over a batch, forward values only.
+ * knn_triplet_mine: dist [n,n] = the dense pairwise distance matrix of the batch (knn_scores_dense, KNN_L2 -- what
+ *   torch.cdist(embeddings, embeddings) returns in loss.py:61,87), labels [n] int64.
+ *     hard [n] fp32 (nullable): max((hardest positive - hardest negative) + margin, 0) per anchor with the reference's masks
+ *       and fp32 operation order (batch_hard_triplet_loss, loss.py:60-83; the loss is their mean);
+ *     all_sum [n] f64, all_pos [n], all_valid [n] int64 (all three or none): per anchor the sum of the positive triplet
+ *       terms max((d(a,p) - d(a,n)) + margin, 0), how many exceed 1e-16 and how many triplets are valid
+ *       (batch_all_triplet_loss, loss.py:86-112: loss = sum / (positives + 1e-16), fraction = positives / (valid + 1e-16)). */
+KNN_API int knn_triplet_mine(const float* dist, const int64_t* labels, int64_t n, float margin, float* hard,
+                     double* all_sum, long long* all_pos, long long* all_valid, void* stream);
+/* out [nq,ng] fp32 = |a & b| / (|a| + |b| - |a & b| + eps) over 64-bit multi-hot label masks, fp32 tensor arithmetic:
+ * JaccardSupConLoss.compute_jaccard_sim (loss.py:237-242), WeightedMultiLabelTripletLoss.compute_jaccard_sim
+ * (loss.py:158-173). */
+KNN_API int knn_jaccard_matrix(const uint64_t* q_masks, const uint64_t* g_masks, int64_t nq, int64_t ng, float eps,
+                       float* out, void* stream);
+/* Nearest-centroid anomaly score (anomaly/test_anomaly.py:31-48).  knn_class_means: means [nclasses,d] fp32 = numpy's
+ * `x[labels == c].mean(axis=0)` for every c in classes (rows added in index order, fp32), counts [nclasses] (nullable).
+ * knn_centroid_min_dist: out [n] f64 = scipy `cdist(x, centroids).min(axis=1)` (float64, direct form). */
+KNN_API int knn_class_means(const float* x, const int64_t* labels, int64_t n, int d, const int64_t* classes, int nclasses,
+                    float* means, int64_t* counts, void* stream);
+KNN_API int knn_centroid_min_dist(const float* x, const float* centroids, int64_t n, int d, int ncentroids, double* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

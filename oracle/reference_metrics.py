@@ -408,3 +408,68 @@ def lesion_rerank(base_val: np.ndarray, base_idx: np.ndarray, lesion_maps, query
         scored.sort(key=lambda x: (x[1], x[2]), reverse=True)
         out[i, :m] = [s[0] for s in scored]
     return out
+
+
+# ---- 8(f)-4 tail: training-time pairwise operations (forward values) -------------------------------
+def triplet_batch_hard(dist: np.ndarray, labels: np.ndarray, margin: float) -> float:
+    """loss.py:60-83 on a given fp32 distance matrix: mean_i max(hardest positive - hardest negative + margin, 0)."""
+    d = dist.astype(np.float32)
+    n = len(labels)
+    same = labels[None, :] == labels[:, None]
+    ap = (same & ~np.eye(n, dtype=bool)).astype(np.float32)
+    hp = (ap * d).max(axis=1)
+    rmax = d.max(axis=1, keepdims=True)
+    hn = (d + rmax * (np.float32(1.0) - (~same).astype(np.float32))).min(axis=1)
+    t = (hp - hn) + np.float32(margin)
+    return float(np.maximum(t, np.float32(0.0)).astype(np.float64).mean())
+
+
+def triplet_batch_all(dist: np.ndarray, labels: np.ndarray, margin: float):
+    """loss.py:86-112 on a given fp32 distance matrix -> (loss, fraction of positive triplets)."""
+    d = dist.astype(np.float32)
+    n = len(labels)
+    total, npos, nvalid = 0.0, 0, 0
+    for i in range(n):
+        pos = np.flatnonzero((labels == labels[i]) & (np.arange(n) != i))
+        neg = np.flatnonzero(labels != labels[i])
+        if len(pos) == 0 or len(neg) == 0:
+            continue
+        t = (d[i, pos][:, None] - d[i, neg][None, :]) + np.float32(margin)
+        nvalid += t.size
+        t = np.maximum(t, np.float32(0.0))
+        total += float(t.astype(np.float64).sum())
+        npos += int((t > 1e-16).sum())
+    return total / (npos + 1e-16), npos / (nvalid + 1e-16)
+
+
+def jaccard_sim_matrix(labels_multihot: np.ndarray, eps: float = 1e-8) -> np.ndarray:
+    """loss.py:237-242 in float32."""
+    lab = labels_multihot.astype(np.float32)
+    inter = lab @ lab.T
+    sums = lab.sum(axis=1, keepdims=True)
+    return inter / ((sums + sums.T - inter) + np.float32(eps))
+
+
+def nearest_centroid_scores(train: np.ndarray, train_labels: np.ndarray, test: np.ndarray, classes=(0, 1)) -> np.ndarray:
+    """anomaly/test_anomaly.py:31-48: float32 class means (rows added in order), float64 direct-form distances, min,
+    division by the maximum."""
+    cents = []
+    for c in classes:
+        rows = train[train_labels == c].astype(np.float32)
+        acc = rows[0].copy()
+        for r in rows[1:]:
+            acc = acc + r
+        cents.append(acc / np.float32(len(rows)))
+    cents = np.stack(cents).astype(np.float64)
+    x = test.astype(np.float64)
+    out = np.empty(len(x))
+    for i in range(len(x)):
+        best = np.inf
+        for c in cents:
+            s = 0.0
+            for k in range(x.shape[1]):
+                df = x[i, k] - c[k]
+                s += df * df
+            best = min(best, float(np.sqrt(s)))
+        out[i] = best
+    return out / out.max()
