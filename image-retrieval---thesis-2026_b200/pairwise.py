@@ -43,7 +43,7 @@ def batch_hard_triplet_loss(labels: torch.Tensor, embeddings: torch.Tensor, marg
     if p != 2.0:
         raise ValueError("only the Euclidean distance (p=2) of the reference's configurations is built")
     hard, _, _, _ = _mine(embeddings, labels, margin, False)
-    return float(hard.double().mean().item()), -1
+    return float(hard.cpu().numpy().astype(np.float64).mean()), -1   # per-anchor fp32 terms, float64 mean on the host
 
 
 def batch_all_triplet_loss(labels: torch.Tensor, embeddings: torch.Tensor, margin: float, p: float = 2.0) -> Tuple[float, float]:
