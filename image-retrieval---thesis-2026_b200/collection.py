@@ -51,12 +51,17 @@ class LocalCollection:
     """An exact (FLAT) collection: embeddings in HBM, scalar fields on the host."""
 
     def __init__(self, name: str, dim: int, metric_type: str = "COSINE", precision: str = "fp32",
-                 vector_field: str = "embedding", id_field: str = "id", device=None):
+                 vector_field: str = "embedding", id_field: str = "id", device=None, l2_squared: bool = False):
         if metric_type not in _METRIC_OF:
             raise ValueError(f"metric_type must be one of {sorted(_METRIC_OF)}")
         self.name, self.dim, self.metric_type = name, int(dim), metric_type
         self.vector_field, self.id_field = vector_field, id_field
         self._precision, self._device = precision, device
+        # NOTE on L2: ``hit.distance`` is the EUCLIDEAN distance -- what the reference's own mapping
+        # ``similarity = 1 - d^2 / 2`` (milvus/milvus_retrieval.py:102-107) assumes and what its in-process search ranks
+        # by (torch.cdist, test_ath.py:87).  A real Milvus L2 collection and faiss.IndexFlatL2 return the SQUARED
+        # distance (same ranking): ``l2_squared=True`` reports that instead.
+        self.l2_squared = bool(l2_squared)
         self._index: Optional[FlatIndex] = None    # created by the first search (metadata-only use needs no device)
         self.columns: Dict[str, List[Any]] = {}
         self._raw_rows: List[torch.Tensor] = []   # vectors as inserted (host)
@@ -147,6 +152,8 @@ class LocalCollection:
         k = max(1, min(int(limit), self.num_entities))
         vals, idx = self.index.search(q.to(self.index.device), k)
         vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+        if self.metric_type == "L2" and self.l2_squared:
+            vals = vals * vals
         out: List[List[Hit]] = []
         idcol = self.columns.get(self.id_field)
         for r in range(idx.shape[0]):

@@ -277,6 +277,9 @@ static int check_common(const void* q, const void* g, const float* qs, const flo
   KNN_REQUIRE(nq >= 0 && ng >= 0 && d >= 1, "bad shape nq=%lld ng=%lld d=%d", (long long)nq, (long long)ng, d);
   KNN_REQUIRE(ng < 0xFFFFFFFEll, "gallery shard too large for 32-bit local rows: %lld", (long long)ng);
   KNN_REQUIRE(dtype == KNN_F32 || dtype == KNN_BF16, "bad dtype %d", dtype);
+  // the tcgen05 kernels address gallery rows with int32 TMA coordinates
+  KNN_REQUIRE(dtype != KNN_BF16 || ng <= 0x7FFFFFFFll, "bf16 gallery shard too large for int32 TMA row coordinates: %lld",
+              (long long)ng);
   KNN_REQUIRE(metric == KNN_COSINE || metric == KNN_IP || metric == KNN_L2, "bad metric %d", metric);
   KNN_REQUIRE(self_mode >= KNN_SELF_KEEP && self_mode <= KNN_SELF_MINUS1, "bad self_mode %d", self_mode);
   KNN_REQUIRE(!(metric == KNN_L2 && self_mode == KNN_SELF_MINUS1), "KNN_SELF_MINUS1 is a similarity convention");

@@ -96,12 +96,26 @@ __device__ __forceinline__ uint64_t exact_key(float dot, float qn, const float* 
   return make_key(s, (uint32_t)row);
 }
 
+// Run-time check of the hardware model behind eps (the one assumption of the proof: the accumulation error of the tensor
+// cores): every candidate carries BOTH its filter value and its exact value, so |filter - exact| is observed on kc rows
+// per query for free.  A candidate whose difference exceeds half the bound flags the query as unverified (it is re-run
+// through the FFMA engine): the engine never relies on the bound where the data contradicts it.
+template <bool kL2>
+__device__ __forceinline__ bool filter_value_off(float approx, float dot, float qn, const float* __restrict__ gsq,
+                                                 int64_t row, float eps) {
+  if (!kL2) return fabsf(approx - dot) > 0.5f * eps;
+  const float e2 = fmaxf(-fmaf(2.0f, dot, -(qn + __ldg(gsq + row))), 0.0f);   // exact d^2 (the bound is on d^2)
+  const float a2 = approx * approx;
+  return fabsf(a2 - e2) > 0.5f * eps + 4.8e-7f * (a2 + e2);                   // + the sqrt rounding of the filter value
+}
+
 // Sort the re-scored keys, emit the best k, and decide whether the candidate set provably contains the answer.
 template <bool kL2>
 __device__ __forceinline__ void emit_and_verify(uint64_t* keys, int npad, int nvalid_cands, int64_t r, int kc, int k,
                                                 int64_t index_base, const float* __restrict__ cand_val,
                                                 const float* __restrict__ eps, float* __restrict__ out_val,
-                                                int64_t* __restrict__ out_idx, int32_t* __restrict__ unverified) {
+                                                int64_t* __restrict__ out_idx, int32_t* __restrict__ unverified,
+                                                bool model_off) {
   bitonic_desc(keys, npad);
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const uint64_t key = j < npad ? keys[j] : 0ull;
@@ -138,7 +152,7 @@ __device__ __forceinline__ void emit_and_verify(uint64_t* keys, int npad, int nv
         ok = (double)(0.0f - key_score(kk)) < lb;
       }
     }
-    unverified[r] = ok ? 0 : 1;
+    unverified[r] = (ok && !model_off) ? 0 : 1;
   }
 }
 
@@ -164,6 +178,8 @@ rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, c
   const int64_t self_row = (self_mode != KNN_SELF_KEEP) ? self_offset + r : -1;  // local gallery row of this query
   const float qn = kL2 ? __ldg(qsq + r) : 0.0f;
   int nvalid = 0;
+  int off = 0;
+  const float e_r = __ldg(eps + r);
   for (int j = threadIdx.x; j < npad; j += blockDim.x) {
     uint64_t key = 0ull;
     if (j < kc) {
@@ -174,13 +190,15 @@ rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, c
         float dot = 0.0f;
         for (int e = 0; e < d; ++e) dot = fmaf(qs[e], __ldg(grow + e), dot);
         key = exact_key<kL2>(dot, qn, gsq, row, self_row, self_mode);
+        if (row != self_row) off |= filter_value_off<kL2>(__ldg(cand_val + r * kc + j), dot, qn, gsq, row, e_r) ? 1 : 0;
       }
     }
     keys[j] = key;
   }
   if (nvalid) atomicAdd(&s_nvalid, nvalid);
-  __syncthreads();
-  emit_and_verify<kL2>(keys, npad, s_nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified);
+  const bool model_off = __syncthreads_or(off) != 0;
+  emit_and_verify<kL2>(keys, npad, s_nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified,
+                       model_off);
 }
 
 // Streaming form (d % 4 == 0, kc <= 256): one CTA per query, ONE THREAD PER CANDIDATE.  The candidates' gallery rows
@@ -267,8 +285,11 @@ rescore_exact_stream_kernel(const float* __restrict__ q, const float* __restrict
   const int64_t self_row = (self_mode != KNN_SELF_KEEP) ? self_offset + r : -1;
   const float qn = kL2 ? __ldg(qsq + r) : 0.0f;
   keys[c] = active ? exact_key<kL2>(dot, qn, gsq, row, self_row, self_mode) : 0ull;
-  __syncthreads();
-  emit_and_verify<kL2>(keys, npad, nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified);
+  const int off = (active && row != self_row &&
+                   filter_value_off<kL2>(__ldg(cand_val + r * kc + c), dot, qn, gsq, row, __ldg(eps + r))) ? 1 : 0;
+  const bool model_off = __syncthreads_or(off) != 0;
+  emit_and_verify<kL2>(keys, npad, nvalid, r, kc, k, index_base, cand_val, eps, out_val, out_idx, unverified,
+                       model_off);
 }
 
 // ---------------------------------------------------------------------------------------------- error bound
@@ -288,8 +309,11 @@ __global__ void __launch_bounds__(256) error_bound_kernel(const float* __restric
   if (i >= nq) return;
   const int dpad = (d + 7) & ~7;
   const double steps = (double)(3 * dpad / 16 + 1);
+  // split error + tensor-core accumulation + rounding of the exact fp32 chain + rounding of the fp32 squared norms the
+  // bound itself is built from ((d/32 + 6) * 2^-24: the per-lane chains and the butterfly of normalize.cu)
   const double u = 3.02 * 3.814697265625e-06 /*2^-18*/ + steps * 4.76837158203125e-07 /*2^-21*/ * 1.012 +
-                   (double)d * 5.9604644775390625e-08 /*2^-24*/ * 1.001;
+                   (double)d * 5.9604644775390625e-08 /*2^-24*/ * 1.001 +
+                   ((double)d / 32.0 + 6.0) * 5.9604644775390625e-08;
   const double qn2 = (double)__ldg(qsq + i), gn2 = (double)__ldg(gmax);
   double e = u * sqrt(qn2 * gn2) * (1.0 + 1e-6) + 1e-30;
   if (l2) e = 2.0 * e + 4.76837158203125e-07 * 1.01 * (qn2 + gn2);

@@ -46,13 +46,17 @@ def save_evaluation_npz(path: str, embeds, labels, kappas, acc, mAP, pr, classif
 
 def rank_retrieval(results: Mapping[str, np.ndarray], topk: int = 1):
     """compute_saliency.py:19-29 on a loaded bundle: ``(pred labels [N, topk], idx [N, topk])``.  Dense bundles are
-    ranked like the reference (NaN diagonal, ascending distance, here with the stable tie order); sparse bundles just
-    slice the stored ranking."""
+    ranked like the reference -- the query's own column dropped (its NaN sorts last), ascending distance, stable tie
+    order -- by the library (``knn_rank_rows`` on the device, not numpy); sparse bundles just slice the stored ranking."""
     labels = np.asarray(results["labels"])
     if "dists" in results:
-        d = np.array(results["dists"], dtype=np.float64, copy=True)
-        np.fill_diagonal(d, np.nan)
-        idx = np.argsort(d, axis=1, kind="stable")[:, :topk]
+        import torch
+
+        from .search import rank_rows
+
+        d = torch.as_tensor(np.asarray(results["dists"], dtype=np.float32)).cuda()
+        d.fill_diagonal_(float("inf"))                      # np.argsort puts the NaN diagonal last
+        idx = rank_rows(d, largest_first=False)[:, :topk].cpu().numpy()
     else:
         idx = np.asarray(results["topk_idx"])[:, :topk]
     return labels[idx], idx

@@ -521,18 +521,25 @@ def search_hamming(query_codes: torch.Tensor, gallery_codes: torch.Tensor, k: in
         raise ValueError(f"bits={nbits} does not match {words} words per code")
     if k < 1:
         raise ValueError("k must be >= 1")
-    if k > L.MAX_FUSED_K:
-        raise L.KnnError(f"Hamming search supports k <= {L.MAX_FUSED_K}")
     dev = qw.device
     if method == "auto":   # the +-1 expansion (2 bytes per code bit) must fit comfortably; it wins at every batch size
         need = 2 * (ng + nq) * ((nbits + 7) // 8 * 8)
         fits = need < torch.cuda.get_device_properties(dev).total_memory // 16 or need < 0.5 * torch.cuda.mem_get_info(dev)[0]
         method = "mma" if ng > 0 and nq > 0 and fits else "popc"
+        # the popcount kernel is instantiated for 1, 2, 3, 4 or 8 words and the fused list sizes: anything else (the
+        # reference ranks the whole matrix for any code length / topk, test_ath.py:100) goes through the +-1 rows,
+        # whose search has the dense + full-ranking path for k beyond the fused limit
+        if ng > 0 and nq > 0 and (k > L.MAX_FUSED_K or words not in (1, 2, 3, 4, 8)):
+            method = "mma"
+    if method == "popc" and k > L.MAX_FUSED_K:
+        raise L.KnnError(f"the popcount Hamming kernel supports k <= {L.MAX_FUSED_K}; use method='mma' (or 'auto')")
     if method == "mma":
         q1 = unpack_bits_pm1(qw, nbits)
         g1 = q1 if gw is qw else unpack_bits_pm1(gw, nbits)
         score, idx = _search_prepared(q1, None, g1, None, int(k), "ip", "exclude" if exclude_self else "keep",
                                       int(query_offset), 0)
+        if k > ng:   # the large-k path pads with (-inf, -1) like the fused one
+            score, idx = score[:, :k], idx[:, :k]
         # d = (bits - score) / 2: exact small integers; empty slots (score -inf) -> +inf like the popcount path
         dist_out = torch.empty_like(score)
         with torch.cuda.device(dev):

@@ -112,7 +112,9 @@ KNN_API int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* o
  * scalar).  knn_filter_error_bound: eps[q] (rounded up) = u * |q| * max|g|  with
  *   u = 3.02 * 2^-18 (dropped terms of the split) + (3 * dpad / 16 + 1) * 2^-21 * 1.012 (tensor-core accumulation:
  *   at most 2^-21 of the magnitude sum per K = 16 MMA step -- the one hardware assumption, checked against observed
- *   errors by tests/test_gpu_exact_tensor.py) + d * 2^-24 * 1.001 (rounding of the exact fp32 chain itself);
+ *   errors by tests/test_gpu_exact_tensor.py AND at run time: knn_rescore_exact flags a query whose candidates show
+ *   |filter value - exact value| > eps / 2) + d * 2^-24 * 1.001 (rounding of the exact fp32 chain itself)
+ *   + (d / 32 + 6) * 2^-24 (rounding of the fp32 squared norms the bound is built from);
  * KNN_L2: 2 * that + 2^-21 * 1.01 * (|q|^2 + max|g|^2) for the two fp32 roundings of -(|q|^2 + |g|^2 - 2 q.g). */
 KNN_API int knn_max_sqnorm(const float* sqnorm, int64_t n, float* out, void* stream);
 KNN_API int knn_filter_error_bound(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max, int d, int metric,

@@ -188,3 +188,22 @@ def test_retriever_result_dicts(gc):
     assert len(r.batch_search([x[1], x[2]], top_k=3)) == 2
     with pytest.raises(ValueError):
         r.search("some/image.png")
+
+
+@pytest.mark.gpu
+def test_l2_collection_distance_conventions():
+    """hit.distance of an L2 collection is the Euclidean distance (what milvus_retrieval.py:102-107 assumes);
+    l2_squared=True reports the squared distance a real Milvus / faiss.IndexFlatL2 returns -- same ranking."""
+    from b200knn.collection import LocalCollection
+
+    rs = np.random.RandomState(3)
+    x = rs.standard_normal((50, 16)).astype(np.float32)
+    rows = [{"image_path": f"p{i}", "label": "a", "embedding": v} for i, v in enumerate(x)]
+    plain, squared = LocalCollection("a", 16, "L2"), LocalCollection("b", 16, "L2", l2_squared=True)
+    plain.insert(rows)
+    squared.insert(rows)
+    h1, h2 = plain.search([x[3]], limit=5)[0], squared.search([x[3]], limit=5)[0]
+    assert [h.id for h in h1] == [h.id for h in h2]
+    want = np.sqrt(((x[[h.id for h in h1]] - x[3]) ** 2).sum(1))
+    assert np.allclose([h.distance for h in h1], want, atol=1e-5)
+    assert np.allclose([h.distance for h in h2], want ** 2, atol=1e-5)

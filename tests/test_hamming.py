@@ -83,3 +83,23 @@ def test_hamming_self_exclusion_large_k_and_mass_ties():
     assert (i.cpu().numpy()[:, 40:] == -1).all() and np.isposinf(v.cpu().numpy()[:, 40:]).all()
     v, i = b200knn.search_hamming(t[1000:1003], t, 5, exclude_self=True, query_offset=1000)
     assert not (i.cpu().numpy() == np.arange(1000, 1003)[:, None]).any()
+
+
+@pytest.mark.gpu
+def test_hamming_any_code_length_and_k_beyond_the_fused_limit():
+    """The reference ranks the whole Hamming matrix (test_ath.py:80-100), so any code length and any topk work: 300-bit
+    codes (5 words: no popcount instantiation) and k = 300 > 256 go through the +-1 rows (dense + full ranking)."""
+    import b200knn
+
+    rs = np.random.RandomState(9)
+    q = (rs.rand(37, 300) < 0.5).astype(np.float32)
+    g = (rs.rand(900, 300) < 0.5).astype(np.float32)
+    g[5] = g[700]                                             # ties
+    dist = (q[:, None, :] != g[None, :, :]).sum(2).astype(np.float32)
+    for k in (10, 300):
+        v, i = b200knn.search_hamming(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), k)
+        order = np.argsort(dist, axis=1, kind="stable")[:, :k]
+        assert np.array_equal(i.cpu().numpy(), order)
+        assert np.array_equal(v.cpu().numpy(), np.take_along_axis(dist, order, 1))
+    with pytest.raises(b200knn.KnnError):
+        b200knn.search_hamming(torch.from_numpy(q).cuda(), torch.from_numpy(g).cuda(), 300, method="popc")
