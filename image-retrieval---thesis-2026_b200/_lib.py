@@ -60,6 +60,7 @@ SIGNATURES = {
     "knn_relevance_multilabel": (_i, [_p, _i64, _i, _p, _p, _i64, _d, _i, _p, _p, _p]),
     "knn_ranked_stats": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "knn_ranked_stats_multi": (_i, [_p, _i64, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "knn_recall_counts": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _i, _p, _p]),
     "knn_majority_vote": (_i, [_p, _i64, _i, _i, _i, _p, _p]),
     "knn_majority_vote_multi": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p]),
     "knn_map_full": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _p, _p, _p, _p]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "knn_ap_from_ranks": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "knn_ap_sklearn_from_ranks": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _sz, _p]),
     "knn_ap_sklearn_from_ranks_workspace": (_sz, [_i64, _i64]),
+    "knn_first_relevant_rank": (_i, [_p, _i64, _i64, _i64, _i, _p, _p, _p, _p]),
     "knn_triplet_mine": (_i, [_p, _p, _i64, _f, _p, _p, _p, _p, _p]),
     "knn_jaccard_matrix": (_i, [_p, _p, _i64, _i64, _f, _p, _p]),
     "knn_class_means": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libb200knn.so")
-SOURCES = ["api.cu", "normalize.cu", "search_f32.cu", "search_tc.cu", "search_tc2.cu", "search_ts.cu", "search_hamming.cu", "exact_tc.cu", "rerank.cu", "merge.cu", "metrics.cu", "rank_positives.cu", "pairwise.cu"]
+SOURCES = ["api.cu", "normalize.cu", "search_f32.cu", "search_tc.cu", "search_tc2.cu", "search_ts.cu", "search_hamming.cu", "exact_tc.cu", "rerank.cu", "merge.cu", "metrics.cu", "rank_positives.cu", "pairwise.cu", "small.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

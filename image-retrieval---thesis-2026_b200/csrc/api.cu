@@ -125,6 +125,19 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// fp32 problems whose 128 x 128 tiling would occupy less than half of the SMs (and whose score rows fit the shared-memory
+// sort): dense scores on 32 x 32 tiles + one sort per row (csrc/small.cu).  Same scores, same order, same bits.
+static bool small_problem(int64_t nq, int64_t ng, int dtype) {
+  if (dtype != KNN_F32 || nq <= 0 || ng <= 0 || ng > 4096) return false;
+  static const int forced = [] {
+    const char* e = getenv("KNN_SMALL_PATH");   // 0 / 1: off / on wherever it fits (tests compare the two paths)
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }();
+  if (forced >= 0) return forced == 1 && nq * ng <= (1ll << 24);
+  const int64_t tiles = ((nq + 127) / 128) * ((ng + 127) / 128);
+  return tiles * 2 < sm_count();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -269,7 +282,10 @@ extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype,
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
   if (dtype == KNN_BF16X3) dtype = KNN_BF16;  // same geometry: the split rows are bf16 rows of 3 * dpad columns
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
-  return ws_layout(g, k).total();
+  size_t need = ws_layout(g, k).total();
+  if (small_problem(nq, ng, dtype) && (size_t)nq * (size_t)ng * sizeof(float) > need)
+    need = (size_t)nq * (size_t)ng * sizeof(float);   // the dense score block of the small path
+  return need;
 }
 
 static int check_common(const void* q, const void* g, const float* qs, const float* gs, int64_t nq, int64_t ng,
@@ -315,6 +331,17 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   }
   KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
+  if (!split3 && small_problem(nq, ng, dtype)) {
+    SearchParams ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.q = q; ps.g = g; ps.qsq = q_sqnorm; ps.gsq = g_sqnorm;
+    ps.nq = nq; ps.ng = ng; ps.d = d; ps.metric = metric; ps.self_mode = self_mode;
+    ps.self_offset = self_offset - index_base;
+    ps.dense_out = reinterpret_cast<float*>(workspace);
+    rc = launch_dense_small(ps, s);
+    if (rc != KNN_OK) return rc;
+    return launch_topk_dense(ps.dense_out, nq, ng, k, metric, self_mode, ps.self_offset, index_base, out_val, out_idx, s);
+  }
   const SearchGeom geo = make_geom(nq, ng, d, dtype, k);
   const bool ts = use_ts(dtype, d, geo.qblocks);
 
@@ -634,5 +661,6 @@ extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqn
   p.split_len = tps * 128;
   p.splits = (int)((ntiles + tps - 1) / tps);
   p.dense_out = out;
+  if (((nq + 127) / 128) * ((ng + 127) / 128) * 2 < sm_count()) return launch_dense_small(p, (cudaStream_t)stream);
   return launch_search_f32(p, true, (cudaStream_t)stream);
 }

@@ -55,6 +55,12 @@ int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream
 int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
                      int64_t* out_idx, cudaStream_t stream);
 
+// Small problems (csrc/small.cu): dense scores on 32 x 32 tiles (same bits as launch_search_f32's dense mode) and the
+// best k of every dense row (<= 4096 columns) in knn_search's output format
+int launch_dense_small(const SearchParams& p, cudaStream_t stream);
+int launch_topk_dense(const float* dense, int64_t nq, int64_t ng, int k, int metric, int self_mode, int64_t self_offset,
+                      int64_t index_base, float* out_val, int64_t* out_idx, cudaStream_t stream);
+
 // Hamming distance over packed 64-bit code words (csrc/search_hamming.cu); p.q / p.g point at uint64 [rows, words]
 int launch_search_hamming(const SearchParams& p, int words, cudaStream_t stream);
 int launch_hamming_from_scores(const float* score, int64_t n, int bits, float* out, cudaStream_t stream);

@@ -104,6 +104,26 @@ __global__ void ranked_stats_multi_kernel(const uint8_t* __restrict__ rel, int64
   if (first) first[q] = f;   // over the first max(kks) items
 }
 
+// R@K in one launch: counts[t] = number of queries with a label match among their first kks[t] retrieved rows
+// (retrieval_accuracy, test.py:38-54: `correct[:k].any()` summed over the batch).  counts must be zeroed by the caller.
+__global__ void recall_counts_kernel(const int64_t* __restrict__ idx, int64_t nq, int k, const int64_t* __restrict__ qlab,
+                                     const int64_t* __restrict__ glab, int64_t ng, const int32_t* __restrict__ kks,
+                                     int nk, int32_t* __restrict__ counts) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int first = 0;
+  if (q < nq) {
+    const int64_t ql = qlab[q];
+    for (int j = 0; j < k && first == 0; ++j) {
+      const int64_t id = idx[q * k + j];
+      if (id >= 0 && id < ng && glab[id] == ql) first = j + 1;
+    }
+  }
+  for (int t = 0; t < nk; ++t) {
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, first > 0 && first <= kks[t]);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counts + t, __popc(b));
+  }
+}
+
 __global__ void majority_vote_kernel(const int64_t* __restrict__ lab, int64_t nq, int k, int kk, int tie_mode,
                                      int64_t* __restrict__ vote) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,6 +380,18 @@ extern "C" int knn_ranked_stats_multi(const uint8_t* rel, int64_t nq, int k, con
   KNN_REQUIRE(rel && kks, "knn_ranked_stats_multi: null pointer");
   ranked_stats_multi_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(rel, nq, k, kks, nk, hits, first,
                                                                                   ap_topk, prec_sum);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+extern "C" int knn_recall_counts(const int64_t* idx, int64_t nq, int k, const int64_t* qlab, const int64_t* glab,
+                                 int64_t ng, const int32_t* kks, int nk, int32_t* counts, void* stream) {
+  KNN_REQUIRE(nq >= 0 && k >= 1 && ng >= 0 && nk >= 1, "knn_recall_counts: bad sizes");
+  KNN_REQUIRE(counts && kks, "knn_recall_counts: null pointer");
+  KNN_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)nk, (cudaStream_t)stream));
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(idx && qlab && (glab || ng == 0), "knn_recall_counts: null pointer");
+  recall_counts_kernel<<<blocks_for(nq, 128), 128, 0, (cudaStream_t)stream>>>(idx, nq, k, qlab, glab, ng, kks, nk, counts);
   KNN_LAUNCHED();
   return KNN_OK;
 }

@@ -92,42 +92,41 @@ def ranked_stats(rel: torch.Tensor, kk: Optional[int] = None):
     return hits, first, ap, ps
 
 
-def ranked_stats_multi(rel: torch.Tensor, cutoffs: Sequence[int]):
-    """The statistics of :func:`ranked_stats` at every cut-off in ONE launch (``knn_ranked_stats_multi``) and one
-    read-back: -> numpy (hits int32 [Q, nk], first int32 [Q] over the first max(cutoffs) items, ap_topk f64 [Q, nk],
-    prec_sum f64 [Q, nk]).  Cut-offs beyond the list length are clamped to it."""
+def ranked_stats_multi(rel: torch.Tensor, cutoffs: Sequence[int], want: Sequence[str] = ("hits", "first", "ap", "ps")):
+    """The statistics of :func:`ranked_stats` at every cut-off in ONE launch (``knn_ranked_stats_multi``):
+    -> numpy (hits int32 [Q, nk], first int32 [Q] over the first max(cutoffs) items, ap_topk f64 [Q, nk],
+    prec_sum f64 [Q, nk]); entries not named in ``want`` are neither computed nor read back (None).  Cut-offs beyond
+    the list length are clamped to it."""
     _require_cuda(rel)
     rel = rel.contiguous()
     nq, k = rel.shape
     dev = rel.device
     cuts = [int(c) for c in cutoffs]
-    outs = []
+    res = {"hits": [], "first": [], "ap": [], "ps": []}
     for c0 in range(0, len(cuts), 16):
         part = cuts[c0:c0 + 16]
         nk = len(part)
         kks = torch.as_tensor(part, dtype=torch.int32, device=dev)
-        hits = torch.empty((nq, nk), dtype=torch.int32, device=dev)
-        first = torch.empty((nq,), dtype=torch.int32, device=dev)
-        ap = torch.empty((nq, nk), dtype=torch.float64, device=dev)
-        ps = torch.empty((nq, nk), dtype=torch.float64, device=dev)
+        bufs = {"hits": torch.empty((nq, nk), dtype=torch.int32, device=dev) if "hits" in want else None,
+                "first": torch.empty((nq,), dtype=torch.int32, device=dev) if "first" in want else None,
+                "ap": torch.empty((nq, nk), dtype=torch.float64, device=dev) if "ap" in want else None,
+                "ps": torch.empty((nq, nk), dtype=torch.float64, device=dev) if "ps" in want else None}
         with torch.cuda.device(dev):
-            rc = L.load().knn_ranked_stats_multi(_ptr(rel), nq, k, _ptr(kks), nk, _ptr(hits), _ptr(first), _ptr(ap),
-                                                 _ptr(ps), _stream(rel))
+            rc = L.load().knn_ranked_stats_multi(_ptr(rel), nq, k, _ptr(kks), nk, _ptr(bufs["hits"]), _ptr(bufs["first"]),
+                                                 _ptr(bufs["ap"]), _ptr(bufs["ps"]), _stream(rel))
         L.check(rc, "knn_ranked_stats_multi")
-        outs.append((hits, first, ap, ps))
-    # one packed read-back: [hits | ap | ps] per part as float64 columns + first
-    packed = torch.cat([torch.cat([h.double(), a, p], 1) for h, _, a, p in outs] +
-                       [torch.stack([o[1] for o in outs], 1).double()], 1).cpu().numpy()
-    hits_l, ap_l, ps_l, col = [], [], [], 0
-    for h, _, _, _ in outs:
-        nk = h.shape[1]
-        hits_l.append(packed[:, col:col + nk].astype(np.int32))
-        ap_l.append(packed[:, col + nk:col + 2 * nk])
-        ps_l.append(packed[:, col + 2 * nk:col + 3 * nk])
-        col += 3 * nk
-    first = packed[:, col:].astype(np.int32)
-    first_any = np.where((first > 0).any(1), np.where(first > 0, first, np.iinfo(np.int32).max).min(1), 0).astype(np.int32)
-    return np.concatenate(hits_l, 1), first_any, np.concatenate(ap_l, 1), np.concatenate(ps_l, 1)
+        for key, buf in bufs.items():
+            if buf is not None:
+                res[key].append(buf)
+    out = {}
+    for key in ("hits", "ap", "ps"):
+        out[key] = torch.cat(res[key], 1).cpu().numpy() if res[key] else None
+    if res["first"]:
+        f = torch.stack(res["first"], 1).cpu().numpy()
+        out["first"] = np.where((f > 0).any(1), np.where(f > 0, f, np.iinfo(np.int32).max).min(1), 0).astype(np.int32)
+    else:
+        out["first"] = None
+    return out["hits"], out["first"], out["ap"], out["ps"]
 
 
 def majority_vote_multi(retrieved_labels: torch.Tensor, cutoffs: Sequence[int], tie: str = "first") -> np.ndarray:
@@ -185,24 +184,44 @@ def _seq_sum(x: np.ndarray, axis=None):
 # --------------------------------------------------------------------------------------------------
 def recall_at_k_from_topk(indices: torch.Tensor, qlabels, glabels, topk: Sequence[int] = (1,)) -> List[torch.Tensor]:
     """R@K from retrieved indices [Q, >=max(topk)]: list of 0-d fp32 tensors, 100 * mean[any label match in top-k]."""
-    rel, _ = relevance_single(indices, qlabels, glabels)
-    _, first, _, _ = ranked_stats(rel)
-    nq = rel.shape[0]
-    first_np = first.cpu().numpy()                      # one read-back: rank of the first match settles every k
-    res = []
-    for k in topk:
-        correct_k = torch.tensor(float(((first_np > 0) & (first_np <= int(k))).sum()), dtype=torch.float32)
-        res.append(correct_k * (100.0 / nq))            # fp32, as `correct_k.sum(dtype=float32) * (100.0 / batch)`
-    return res
+    _require_cuda(indices)
+    idx = indices.contiguous().long()
+    nq, k = idx.shape
+    dev = idx.device
+    ql, gl = _dev_i64(qlabels, dev).view(-1), _dev_i64(glabels, dev).view(-1)
+    kks = torch.as_tensor([int(t) for t in topk], dtype=torch.int32, device=dev)
+    counts = torch.empty((len(topk),), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.load().knn_recall_counts(_ptr(idx), nq, k, _ptr(ql), _ptr(gl), gl.numel(), _ptr(kks), len(topk),
+                                        _ptr(counts), _stream(idx))
+    L.check(rc, "knn_recall_counts")
+    scale = torch.tensor(100.0 / nq, dtype=torch.float32)
+    # fp32, as `correct_k.sum(dtype=float32) * (100.0 / batch)`; one read-back for every k
+    return [c * scale for c in counts.cpu().to(torch.float32)]
 
 
 def retrieval_accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)) -> List[torch.Tensor]:
     """Reference signature: ``output`` is the dense [N,N] score matrix (larger = more similar, diagonal already
     masked), ``target`` the labels.  Row-wise top-maxk with ties broken by ascending column."""
     _require_cuda(output)
-    maxk = max(topk)
-    pred = rank_rows(output, largest_first=True)[:, :maxk].contiguous()
-    return recall_at_k_from_topk(pred, target, target, topk)
+    out = output.float()
+    if out.stride(1) != 1:
+        out = out.contiguous()
+    nq, ng = out.shape
+    lab = _dev_i64(target, out.device).view(-1)
+    first = torch.empty((nq,), dtype=torch.int32, device=out.device)
+    with torch.cuda.device(out.device):
+        # R@K only asks whether the best-scoring row with the query's label sits in the first K: one launch gives its
+        # rank (ties by ascending column, the order of rank_rows), one read-back settles every K
+        rc = L.load().knn_first_relevant_rank(_ptr(out), out.stride(0), nq, ng, 1, _ptr(lab), _ptr(lab), _ptr(first),
+                                              _stream(out))
+    L.check(rc, "knn_first_relevant_rank")
+    first_np = first.cpu().numpy()
+    res = []
+    for k in topk:
+        correct_k = torch.tensor(float(((first_np > 0) & (first_np <= int(k))).sum()), dtype=torch.float32)
+        res.append(correct_k * (100.0 / nq))            # fp32, as `correct_k.sum(dtype=float32) * (100.0 / batch)`
+    return res
 
 
 # --------------------------------------------------------------------------------------------------
@@ -267,11 +286,12 @@ def compute_map_from_embeddings(embeds: torch.Tensor, labels, kappas=(), metric:
 # --------------------------------------------------------------------------------------------------
 def _prf_from_predictions(true: np.ndarray, pred: np.ndarray) -> Dict[str, float]:
     """macro / weighted precision, recall, F1 (zero_division=0) and accuracy from the confusion counts, with
-    sklearn's formulas (precision_recall_fscore_support): host math on a C x C matrix."""
-    labels = np.unique(np.concatenate([true, pred]))
-    tp = np.array([np.sum((true == c) & (pred == c)) for c in labels], dtype=np.float64)
-    pred_sum = np.array([np.sum(pred == c) for c in labels], dtype=np.float64)
-    true_sum = np.array([np.sum(true == c) for c in labels], dtype=np.float64)
+    sklearn's formulas (precision_recall_fscore_support): host math on a C x C matrix built by ONE bincount."""
+    labels, codes = np.unique(np.concatenate([true, pred]), return_inverse=True)
+    c = len(labels)
+    tc, pc = codes[: len(true)], codes[len(true):]
+    conf = np.bincount(tc * c + pc, minlength=c * c).reshape(c, c).astype(np.float64)   # [true, predicted]
+    tp, pred_sum, true_sum = np.diag(conf).copy(), conf.sum(axis=0), conf.sum(axis=1)
 
     def div(a, b):
         out = np.zeros_like(a)
@@ -289,7 +309,7 @@ def _prf_from_predictions(true: np.ndarray, pred: np.ndarray) -> Dict[str, float
         "precision_macro": avg(precision) * 100.0, "recall_macro": avg(recall) * 100.0, "f1_macro": avg(f1) * 100.0,
         "precision_weighted": avg(precision, w) * 100.0, "recall_weighted": avg(recall, w) * 100.0,
         "f1_weighted": avg(f1, w) * 100.0,
-        "accuracy": float(np.mean(true == pred)) * 100.0,
+        "accuracy": float(tp.sum() / len(true)) * 100.0,
     }
 
 
@@ -331,7 +351,7 @@ def compute_metrics(query_codes, query_labels, gallery_codes, gallery_labels, qu
     total_rel = torch.where(uniq[pos] == ql, counts[pos], torch.zeros_like(counts[pos])).cpu().numpy()
     retrieval = {}
     cuts = [int(t) for t in topk_values]
-    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts)    # every cut-off: one launch, one read-back
+    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts, want=("hits", "first", "ap"))    # every cut-off: one launch, one read-back
     votes = majority_vote_multi(lab, cuts, "first")
     ql_np = ql.cpu().numpy()
     for j, topk in enumerate(topk_values):
@@ -374,7 +394,7 @@ def evaluate_results_from_topk(vals: torch.Tensor, indices: torch.Tensor, qlabel
         "num_valid_ap_queries": float(len(aps)),
     }
     ks = list(ks)
-    hits_all = ranked_stats_multi(rel, [min(int(k), nhits) for k in ks])[0] if ks else None
+    hits_all = ranked_stats_multi(rel, [min(int(k), nhits) for k in ks], want=("hits",))[0] if ks else None
     for j, k in enumerate(ks):
         kk = min(int(k), nhits)
         hk = hits_all[:, j].astype(np.float64)
@@ -395,7 +415,7 @@ def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch
     _, rel_any = relevance_multilabel(indices, qm, gm, 0.0)
     nq = rel_any.shape[0]
     out = {}
-    hits_all = ranked_stats_multi(rel_any, list(k_values))[0]
+    hits_all = ranked_stats_multi(rel_any, list(k_values), want=("hits",))[0]
     for j, k in enumerate(k_values):
         hk = hits_all[:, j]
         total_precision = _seq_sum(hk.astype(np.float64) / k)   # total_precision += num_matches / k
@@ -439,7 +459,7 @@ def retrieval_metrics_from_ranking(idx: torch.Tensor, labels: Sequence,
     hits_np, ps = hits.cpu().numpy(), prec_sum.cpu().numpy()
     aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)
     metrics: Dict[str, float] = {"num_samples": float(len(inv)), "mAP": float(np.mean(aps) * 100.0)}
-    hits_all = ranked_stats_multi(rel, k_values)[0] if k_values else None
+    hits_all = ranked_stats_multi(rel, k_values, want=("hits",))[0] if k_values else None
     for j, k in enumerate(k_values):
         hk = np.where(hits_np > 0, hits_all[:, j], 0)
         metrics[f"mP@{k}"] = float(np.mean(hk / k) * 100.0)
@@ -582,7 +602,7 @@ def evaluate_retrieval(image_features: torch.Tensor, labels, topk_values) -> Dic
     true = lab_dev.cpu().numpy()
     results: Dict[str, float] = {}
     cuts = [int(k) for k in topk_values]
-    hits_all = ranked_stats_multi(rel, cuts)[0]
+    hits_all = ranked_stats_multi(rel, cuts, want=("hits",))[0]
     votes = majority_vote_multi(lab, cuts, "smallest")
     for j, k in enumerate(topk_values):
         hits = hits_all[:, j]
@@ -610,7 +630,7 @@ def compute_retrieval_metrics(query_codes, query_labels, gallery_codes, gallery_
     rel, lab = relevance_single(idx, ql, gl)
     results = {}
     cuts = [int(t) for t in topk_values]
-    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts)
+    hits_all, first_np, ap_all, _ = ranked_stats_multi(rel, cuts, want=("hits", "first", "ap"))
     votes = majority_vote_multi(lab, cuts, "smallest")
     ql_np = ql.cpu().numpy()
     for j, topk in enumerate(topk_values):
@@ -651,7 +671,7 @@ def retrieval_accuracy_from_ranks(ranks: np.ndarray, labels, topk, device=None) 
     idx = _ranks_topk_device(ranks, kmax, device)
     lab = torch.from_numpy(codes).to(device)
     rel, _ = relevance_single(idx, lab, lab)
-    hits_all = ranked_stats_multi(rel, [min(int(k), kmax) for k in topk])[0]
+    hits_all = ranked_stats_multi(rel, [min(int(k), kmax) for k in topk], want=("hits",))[0]
     out = [(int((hits_all[:, j] > 0).sum()) * 100.0) / max(1, n) for j in range(len(topk))]
     return np.array(out, dtype=np.float64)
 

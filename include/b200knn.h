@@ -264,6 +264,12 @@ KNN_API int knn_ranked_stats(const uint8_t* rel, int64_t nq, int k, int kk,
 KNN_API int knn_ranked_stats_multi(const uint8_t* rel, int64_t nq, int k, const int32_t* kks, int nk, int32_t* hits,
                            int32_t* first, double* ap_topk, double* prec_sum, void* stream);
 
+/* R@K straight from retrieved indices, one launch: counts[t] (device int32 [nk], zeroed by the call) = queries with a
+ * label match among their first kks[t] rows -- `correct[:k].any()` summed over the batch (retrieval_accuracy,
+ * test.py:38-54).  The caller multiplies by 100 / nq in fp32 as the reference does. */
+KNN_API int knn_recall_counts(const int64_t* idx, int64_t nq, int k, const int64_t* qlab, const int64_t* glab, int64_t ng,
+                      const int32_t* kks, int nk, int32_t* counts, void* stream);
+
 /* Majority vote over the first kk retrieved labels (lab [nq,k] int64).
  * tie_mode 0: first label reaching the max count in rank order (collections.Counter.most_common,
  *             test.py:149-161, test_ath.py:153);  tie_mode 1: smallest label (torch.mode train_ath.py:208,
@@ -365,6 +371,13 @@ KNN_API int knn_class_means(const float* x, const int64_t* labels, int64_t n, in
                     float* means, int64_t* counts, void* stream);
 KNN_API int knn_centroid_min_dist(const float* x, const float* centroids, int64_t n, int d, int ncentroids, double* out,
                           void* stream);
+
+/* 1-based rank of the best-scoring gallery row that carries the query's label over a dense score row (0 = none), ranks
+ * as knn_rank_rows orders them -- everything R@K reads off `output.topk(maxk)` + `target[pred] == target`
+ * (retrieval_accuracy, test.py:38-54; train.py:560-577) in one launch: R@K = mean(0 < first <= K).
+ * scores [nq, ld_scores >= ng] fp32, q_labels [nq], g_labels [ng] int64, first [nq] int32. */
+KNN_API int knn_first_relevant_rank(const float* scores, int64_t ld_scores, int64_t nq, int64_t ng, int largest_first,
+                            const int64_t* q_labels, const int64_t* g_labels, int32_t* first, void* stream);
 
 #ifdef __cplusplus
 }
