@@ -12,7 +12,9 @@
  *   - no allocation / ownership transfer inside the library: the caller passes outputs and a workspace
  *     sized by the matching *_workspace() query
  *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*), no hidden syncs
- *   - no global mutable state except the thread-local error string
+ *   - no global mutable state that a result depends on: the error string and the opt-in profile ring (knn_profile_*)
+ *     are thread-local, the launch counter (knn_launch_count) is a process-wide atomic, experiment knobs are read from
+ *     the environment once; entry points may be called from several threads on different streams / devices
  */
 #ifndef B200KNN_H_
 #define B200KNN_H_

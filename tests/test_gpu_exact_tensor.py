@@ -181,3 +181,43 @@ def test_c3_full_size_tensor_engine_equals_ffma_engine(knn, monkeypatch):
     monkeypatch.setenv("KNN_EXACT_ENGINE", "ffma")
     fv, fi = knn.search(q, g, 50, "cosine", precision="fp32")
     assert torch.equal(i, fi) and torch.equal(v, fv)
+
+
+def test_c3_sized_gallery_tensor_engine_against_the_oracle(knn, tensor_engine):
+    """The tensor-core engine FORCED at BASELINE config 3's gallery size (112 000 x 1024, top-50) against the CPU oracle
+    directly -- not through the FFMA engine: 128 queries, indices and distances bit for bit, cosine and L2."""
+    S = importlib.import_module("b200knn.search")
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    g = knn.normalize(torch.randn((112_000, 1024), generator=gen, device="cuda"))
+    q = knn.normalize(torch.randn((128, 1024), generator=gen, device="cuda"))
+    gh, qh = host(g), host(q)
+    for metric in ("cosine", "l2"):
+        assert S.exact_engine(128, 112_000, 1024, 50) == "tensor"
+        v, i = knn.search(q, g, 50, metric, precision="fp32")
+        ov, oi = oracle.search(qh, gh, 50, metric, "keep", 0)
+        assert np.array_equal(host(i), oi) and np.array_equal(host(v), ov), metric
+        assert S._search_exact_tensor.last_unverified < 8
+
+
+@pytest.mark.parametrize("d", [4096, 1024])
+def test_all_positive_rows_stress_the_accumulation_bound(knn, tensor_engine, d):
+    """The proof's one hardware assumption is the accumulation error of the tensor cores.  All-positive rows are the
+    adversarial case: every product has the same sign, the fp32 accumulator grows monotonically to ~d/4 and every
+    truncation goes the same way.  The result must still be the oracle's, bit for bit -- through the proof or, for a
+    query whose candidates contradict the error model (the run-time check of knn_rescore_exact), through the FFMA re-run."""
+    S = importlib.import_module("b200knn.search")
+    rs = np.random.RandomState(d)
+    g = rs.rand(24_000, d).astype(np.float32)                 # uniform [0, 1): un-normalised, inner product
+    q = rs.rand(128, d).astype(np.float32)
+    g[77] = g[19_000]                                          # an exact tie
+    v, i = knn.search(dev(q), dev(g), 50, "ip", precision="fp32")
+    ov, oi = oracle.search(q, g, 50, "ip", "keep", 0)
+    assert np.array_equal(host(i), oi) and np.array_equal(host(v), ov)
+    # the observed filter error stays inside the bound on this data too (the bound scales with |q| |g| ~ d / 3)
+    eps = host(S.filter_error_bound(knn.row_sqnorm(dev(q)), S.ExactFilterRows.build(dev(g), None).max_sqnorm, d, "ip"))
+    fv, fi = S._search_prepared(S.split_bf16x3(dev(q), "queries"), None, S.split_bf16x3(dev(g), "gallery"), None, 64,
+                                "ip", "keep", 0, 0, split_rows=True)
+    exact = (q.astype(np.float64)[:, None, :] * g.astype(np.float64)[host(fi)]).sum(-1)
+    err = np.abs(host(fv).astype(np.float64) - exact).max(axis=1)
+    print(f"\nd={d}: max |filter - exact| / eps = {(err / eps).max():.3f}")
+    assert (err <= eps).all()
