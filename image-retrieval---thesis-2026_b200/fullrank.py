@@ -143,6 +143,30 @@ def chunk_rows(ng: int, ties: bool, budget: int = _CHUNK_BYTES, device=None) -> 
     return rows - rows % wave if rows >= wave else rows
 
 
+def query_slice(nq: int, world: int, rank: int):
+    """Contiguous query range ``[s, e)`` of a rank (the same split as ``sharded.shard_rows``)."""
+    return (rank * nq) // world, ((rank + 1) * nq) // world
+
+
+def gather_query_sharded(local: Dict[str, torch.Tensor], nq: int, group=None) -> Dict[str, torch.Tensor]:
+    """All-gather per-query tensors that every rank computed for ITS query slice (``query_slice``) into the full
+    ``[Q, ...]`` tensors, identical on every rank and in the original query order.  Slices are padded to the longest one
+    for the collective (one all-gather per output)."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [query_slice(nq, world, r)[1] - query_slice(nq, world, r)[0] for r in range(world)]
+    longest = max(sizes)
+    out = {}
+    for key, val in local.items():
+        pad = torch.zeros((longest,) + tuple(val.shape[1:]), dtype=val.dtype, device=val.device)
+        pad[: val.shape[0]] = val
+        full = torch.empty((world * longest,) + tuple(val.shape[1:]), dtype=val.dtype, device=val.device)
+        dist.all_gather_into_tensor(full, pad.contiguous(), group=group)
+        out[key] = torch.cat([full[r * longest: r * longest + sizes[r]] for r in range(world)], 0)
+    return out
+
+
 def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: int, q_rel: torch.Tensor,
                        g_rel: torch.Tensor, *, metric: str = "cosine", normalize: bool = False,
                        self_mode: str = "keep", drop_self: bool = False, query_offset: int = 0,
@@ -150,7 +174,8 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
                        jaccard_threshold: float = 0.0, kappas: Sequence[int] = (), sklearn_ap: bool = False,
                        self_last_positive: bool = False, outputs: Optional[Sequence[str]] = None,
                        eps: float = 1e-12, eps_mode: str = "clamp",
-                       rows_per_chunk: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                       rows_per_chunk: Optional[int] = None, distributed: bool = False,
+                       group=None) -> Dict[str, torch.Tensor]:
     """Per-query full-ranking statistics of ``queries`` against the whole ``gallery`` (exact fp32 scores), chunked over
     the queries.  ``self_mode`` is the score the query's own gallery row gets (``fill_diagonal_``: "exclude" = -inf,
     "minus1" = -1, "keep"); ``drop_self`` removes that row from the ranking and from the relevant set.
@@ -158,7 +183,12 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     "npos", each ``[Q]`` / ``[Q, k]``.
 
     The AP kernels of a chunk are chains of dependent double additions in rank order (latency bound, a fraction of the
-    SMs): they run on a side stream while the distance and rank kernels of the next chunk fill the machine."""
+    SMs): they run on a side stream while the distance and rank kernels of the next chunk fill the machine.
+
+    ``distributed=True`` (inside an initialised ``torch.distributed`` job, every rank holding the same inputs): the
+    QUERIES are sharded -- rank r ranks the rows of ``query_slice(Q, W, r)`` against the whole gallery, the per-query
+    statistics are all-gathered (a few bytes per query) and every rank returns the full, identical result.  The
+    reference all-gathers the EMBEDDINGS and recomputes everything on every rank (train.py:604-609)."""
     _require_cuda(queries, gallery)
     if metric not in _METRICS:
         raise ValueError(f"metric must be one of {sorted(_METRICS)}")
@@ -170,6 +200,27 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     nq, ng = q.shape[0], g.shape[0]
     if nq == 0:
         raise ValueError("no queries")
+    if distributed:
+        import torch.distributed as dist
+
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            distributed = False
+    if distributed:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        s0, e0 = query_slice(nq, world, rank)
+        local = full_ranking_stats(q[s0:e0], g, rel_mode, q_rel[s0:e0], g_rel, metric=metric, normalize=False,
+                                   self_mode=self_mode, drop_self=drop_self, query_offset=query_offset + s0,
+                                   q_group=None if q_group is None else q_group[s0:e0], g_group=g_group,
+                                   jaccard_threshold=jaccard_threshold, kappas=kappas, sklearn_ap=sklearn_ap,
+                                   self_last_positive=self_last_positive, outputs=outputs,
+                                   rows_per_chunk=rows_per_chunk) if e0 > s0 else None
+        if local is None:   # a rank without queries still takes part in the collectives: build empty outputs
+            probe = full_ranking_stats(q[:1], g, rel_mode, q_rel[:1], g_rel, metric=metric, self_mode=self_mode,
+                                       drop_self=drop_self, query_offset=query_offset, jaccard_threshold=jaccard_threshold,
+                                       kappas=kappas, sklearn_ap=sklearn_ap, self_last_positive=self_last_positive,
+                                       outputs=outputs, q_group=None if q_group is None else q_group[:1], g_group=g_group)
+            local = {k: v[:0] for k, v in probe.items()}
+        return gather_query_sharded(local, nq, group)
     dev = q.device
     step = int(rows_per_chunk) if rows_per_chunk else chunk_rows(ng, sklearn_ap, device=dev)
     main = torch.cuda.current_stream(dev)

@@ -58,6 +58,22 @@ def _worker(rank, world, port, out_dir):
             prof = sh.profile_read()
             if len(prof) != 1 or min(prof[0]) < 0.0:
                 failures.append((precision, exchange, "profile", prof))
+    # full-ranking metrics with the QUERIES sharded over the ranks: same value as one process, on every rank
+    os.environ.pop("KNN_EXACT_ENGINE", None)
+    from oracle import synth
+    M = b200knn.metrics
+    n = 2001                                             # uneven query slices
+    ml = torch.from_numpy(synth.multihot(n, seed=8)).to(dev)
+    emb = torch.from_numpy(synth.labelset_clustered(synth.multihot(n, seed=8), 64, 9, 1.0)).to(dev)
+    lab = torch.from_numpy(synth.clustered(n, 8, 4, seed=10)[1]).to(dev)
+    for name, fn in (("evaluate_map", lambda d: M.evaluate_map_embeddings(emb, ml, 0.4, distributed=d)),
+                     ("map_multilabel", lambda d: M.compute_map_multilabel_from_embeddings(emb, ml, 0.5, distributed=d)),
+                     ("single_label", lambda d: M._compute_single_label_retrieval_metrics(emb, lab, distributed=d)),
+                     ("multilabel", lambda d: M._compute_multilabel_retrieval_metrics(emb, ml, distributed=d)),
+                     ("compute_map", lambda d: M.compute_map_from_embeddings(emb, lab, [1, 5, 10], "cosine",
+                                                                             distributed=d)[0])):
+        if fn(True) != fn(False):
+            failures.append(("distributed", name))
     torch.cuda.synchronize()
     with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as fh:
         fh.write(repr(failures))

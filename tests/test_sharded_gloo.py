@@ -110,3 +110,30 @@ def test_two_rank_search_equals_single_shard(tmp_path):
         z = np.load(tmp_path / f"r{r}.npz")
         assert np.array_equal(z["i"], i1) and np.array_equal(z["v"], v1)
         assert np.array_equal(z["ih"], i2) and np.array_equal(z["vh"], v2)      # search_host == one-shard search
+
+
+def _gather_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from b200knn.fullrank import gather_query_sharded, query_slice
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nq = 11                                            # uneven slices: 5 + 6
+    full = {"ap": torch.arange(nq, dtype=torch.float64) * 0.5, "hits": torch.arange(nq * 3, dtype=torch.int32).view(nq, 3)}
+    s, e = query_slice(nq, world, rank)
+    out = gather_query_sharded({k: v[s:e].clone() for k, v in full.items()}, nq)
+    ok = all(torch.equal(out[k], full[k]) for k in full)
+    with open(os.path.join(out_dir, f"g{rank}.txt"), "w") as fh:
+        fh.write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_query_sharded_statistics_gather_in_query_order(tmp_path):
+    """The multi-GPU form of the full-ranking metrics shards the QUERIES; the per-query statistics of uneven slices must
+    come back in the original order on every rank (gloo, CPU tensors)."""
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"g{r}.txt").read() == "ok"
