@@ -125,6 +125,27 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Gallery splits of the dense / statistics modes of the FFMA kernel (units = 128-row query block x split, all equally
+// long, `slots` of them resident): the count that wastes the least of the last wave -- 10 query blocks on 296 slots:
+// 29 splits = 290 CTAs = 0.98 of ONE wave, where "2 waves' worth" (30 splits = 300 CTAs) ran a second wave for 4 CTAs.
+static void dense_splits(int64_t qblocks, int64_t ntiles, int64_t slots, int64_t* tiles_per_split, int* splits) {
+  int64_t hi = (4 * slots + qblocks - 1) / qblocks;   // up to ~4 waves
+  if (hi > ntiles) hi = ntiles;
+  if (hi < 1) hi = 1;
+  int64_t best = 1;
+  double best_eff = -1.0;
+  for (int64_t s = 1; s <= hi; ++s) {
+    const int64_t tps = (ntiles + s - 1) / s;
+    const int64_t real = (ntiles + tps - 1) / tps;
+    const int64_t waves = (real * qblocks + slots - 1) / slots;
+    double eff = (double)ntiles * (double)qblocks / ((double)waves * (double)slots * (double)tps);
+    if (real * qblocks < slots) eff *= 0.999;   // prefer filling the machine among (near) ties
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  *tiles_per_split = (ntiles + best - 1) / best;
+  *splits = (int)((ntiles + *tiles_per_split - 1) / *tiles_per_split);
+}
+
 // fp32 problems whose 128 x 128 tiling would occupy less than half of the SMs (and whose score rows fit the shared-memory
 // sort): dense scores on 32 x 32 tiles + one sort per row (csrc/small.cu).  Same scores, same order, same bits.
 static bool small_problem(int64_t nq, int64_t ng, int dtype) {
@@ -572,11 +593,9 @@ extern "C" size_t knn_score_stats_workspace(int64_t nq, int64_t ng) {
   if (nq <= 0 || ng <= 0) return 0;
   const int64_t qblocks = (nq + kRowsPerUnit - 1) / kRowsPerUnit;
   const int64_t ntiles = (ng + 127) / 128;
-  int64_t want = ((int64_t)2 * 2 * sm_count() + qblocks - 1) / qblocks;
-  if (want > ntiles) want = ntiles;
-  if (want < 1) want = 1;
-  const int64_t tps = (ntiles + want - 1) / want;
-  const int64_t splits = (ntiles + tps - 1) / tps;
+  int64_t tps;
+  int splits;
+  dense_splits(qblocks, ntiles, (int64_t)2 * sm_count(), &tps, &splits);
   return (size_t)splits * qblocks * kRowsPerUnit * 4 * sizeof(double);
 }
 
@@ -605,12 +624,9 @@ extern "C" int knn_score_stats(const void* q, const void* g, const float* q_sqno
   p.groups = 1;
   p.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   const int64_t ntiles = (ng + 127) / 128;
-  int64_t want = ((int64_t)2 * 2 * sm_count() + p.qblocks - 1) / p.qblocks;
-  if (want > ntiles) want = ntiles;
-  if (want < 1) want = 1;
-  const int64_t tps = (ntiles + want - 1) / want;
+  int64_t tps;
+  dense_splits(p.qblocks, ntiles, (int64_t)2 * sm_count(), &tps, &p.splits);
   p.split_len = tps * 128;
-  p.splits = (int)((ntiles + tps - 1) / tps);
   p.stats_out = reinterpret_cast<double*>(workspace);
   rc = launch_search_f32(p, false, (cudaStream_t)stream);
   if (rc != KNN_OK) return rc;
@@ -654,12 +670,9 @@ extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqn
   p.groups = 1;
   p.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
   const int64_t ntiles = (ng + 127) / 128;
-  int64_t want = ((int64_t)2 * sm_count() + p.qblocks - 1) / p.qblocks;
-  if (want > ntiles) want = ntiles;
-  if (want < 1) want = 1;
-  const int64_t tps = (ntiles + want - 1) / want;
+  int64_t tps;
+  dense_splits(p.qblocks, ntiles, (int64_t)2 * sm_count(), &tps, &p.splits);   // two resident CTAs per SM
   p.split_len = tps * 128;
-  p.splits = (int)((ntiles + tps - 1) / tps);
   p.dense_out = out;
   if (((nq + 127) / 128) * ((ng + 127) / 128) * 2 < sm_count()) return launch_dense_small(p, (cudaStream_t)stream);
   return launch_search_f32(p, true, (cudaStream_t)stream);

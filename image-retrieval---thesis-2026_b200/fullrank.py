@@ -135,12 +135,11 @@ def ap_sklearn_from_ranks(rp: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 def chunk_rows(ng: int, ties: bool, budget: int = _CHUNK_BYTES, device=None) -> int:
     """Queries per chunk so that the [chunk, N] transients (scores + ranks, + tie outputs and the sklearn workspace) of
-    the two chunks in flight stay inside ``budget`` bytes; a multiple of the rank kernel's persistent grid (two CTAs per
-    SM) so that its last wave is full."""
+    the two chunks in flight stay inside ``budget`` bytes; a multiple of 128 (whole query blocks of the distance kernel --
+    the rank kernel claims rows dynamically and does not care)."""
     per_row = 2 * ng * (4 + 4 + (8 + 12 if ties else 0))
     rows = int(max(1, min(8192, budget // max(per_row, 1))))
-    wave = 2 * torch.cuda.get_device_properties(device).multi_processor_count if torch.cuda.is_available() else 296
-    return rows - rows % wave if rows >= wave else rows
+    return rows - rows % 128 if rows >= 128 else rows
 
 
 def query_slice(nq: int, world: int, rank: int):
