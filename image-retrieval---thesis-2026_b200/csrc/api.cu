@@ -654,14 +654,35 @@ extern "C" int knn_sort_topk(const float* vals, const int64_t* idx, int64_t nq, 
 extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
                                 int64_t nq, int64_t ng, int d, int dtype, int metric, int self_mode,
                                 int64_t self_offset, float* out, void* stream) {
+  const bool split3 = dtype == KNN_BF16X3;
+  if (split3) {
+    KNN_REQUIRE(d % 24 == 0, "KNN_BF16X3 rows are 3 parts of a multiple of 8 columns, got d=%d", d);
+    dtype = KNN_BF16;
+  }
   int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
   if (rc != KNN_OK) return rc;
-  if (dtype != KNN_F32) {
-    set_error("knn_scores_dense: fp32 inputs only (upcast bf16 rows first; the cast is exact)");
-    return KNN_E_UNSUPPORTED;
-  }
   if (nq == 0 || ng == 0) return KNN_OK;
   KNN_REQUIRE(out, "null output pointer");
+  if (dtype == KNN_BF16) {
+    // tensor-core dense mode: the CTA-pair tcgen05 kernel with a store epilogue (bf16 rows, or bf16x3 split rows whose
+    // three products reproduce the fp32 inner product to ~1e-5 |q||g|)
+    KNN_REQUIRE(d % 8 == 0, "bf16 rows must be padded to a multiple of 8 columns, got d=%d", d);
+    SearchParams pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.q = q; pb.g = g; pb.qsq = q_sqnorm; pb.gsq = g_sqnorm;
+    pb.nq = nq; pb.ng = ng; pb.d = d; pb.k = 1; pb.kp = 32;
+    pb.metric = metric; pb.self_mode = self_mode; pb.self_offset = self_offset;
+    pb.groups = 2; pb.split3 = split3 ? 1 : 0;
+    pb.qblocks = (int)((nq + kRowsPerUnit - 1) / kRowsPerUnit);
+    if (pb.qblocks & 1) pb.qblocks += 1;                       // CTA pairs own 256 query rows
+    const int tile = bf16_tile_cols();
+    const int64_t ntiles_b = (ng + tile - 1) / tile;
+    int64_t tps_b;
+    dense_splits(pb.qblocks, ntiles_b, sm_count(), &tps_b, &pb.splits);   // one CTA per SM
+    pb.split_len = tps_b * tile;
+    pb.dense_out = out;
+    return launch_search_bf16_pair(pb, (cudaStream_t)stream);
+  }
   SearchParams p;
   memset(&p, 0, sizeof(p));
   p.q = q; p.g = g; p.qsq = q_sqnorm; p.gsq = g_sqnorm;

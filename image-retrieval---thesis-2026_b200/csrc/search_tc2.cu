@@ -287,8 +287,9 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int rloc = quarter * 32 + lane;
     const bool row_valid = row0 + rloc < p.nq;
     const int64_t vunit = ((int64_t)sp * 2 + grp) * p.qblocks + qb;
+    const bool dense = p.dense_out != nullptr;   // dense mode: the scores are written out instead of selected
     RowState st;
-    rowstate_init(st, p.lists + ((vunit * TM + rloc) * (int64_t)L));
+    rowstate_init(st, dense ? nullptr : p.lists + ((vunit * TM + rloc) * (int64_t)L));
     uint32_t self_row = 0xFFFFFFFFu;
     float qn = 0.f;
     uint32_t* tau_row = nullptr;
@@ -296,8 +297,10 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const int64_t sr = p.self_offset + row0 + rloc;
       if (p.self_mode != KNN_SELF_KEEP && sr >= 0 && sr < p.ng) self_row = (uint32_t)sr;
       if (kL2) qn = __ldg(p.qsq + row0 + rloc);
-      tau_row = p.tau_global + row0 + rloc;
+      if (!dense) tau_row = p.tau_global + row0 + rloc;
     }
+    const int64_t dense_row = (dense && row_valid) ? row0 + rloc : -1;
+    const int64_t dense_self = (p.self_mode != KNN_SELF_KEEP && dense_row >= 0) ? p.self_offset + dense_row : -1;
     const int et = threadIdx.x - 64;
     long long e_wait = 0, e_slow = 0;
     unsigned long long n_slow = 0;
@@ -323,7 +326,10 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TN);
       PendingHits pend;
       pend.n = 0;
-      if (debug != 1)
+      if (dense)
+        dense_store_tile_tmem<kL2>(taddr, grp, 2, TN / 32, col0, c_end, gst, qn, dense_row, dense_self, p.self_mode,
+                                   p.dense_out, p.ng);
+      else if (debug != 1)
         select_tile_tmem<E, kL2>(st, pend, taddr, grp, 2, TN / 32, col0, c_end, gst, qn, self_row, p.self_mode, p.k,
                                  lane, tau_row, row_valid && debug != 2, stats_on, e_slow, n_slow);
       ptx::tc_fence_before();
@@ -332,7 +338,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (leader) ptx::mbar_arrive(&bars->tmem_empty[as]);
         else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
       }
-      flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
+      if (!dense) flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
     if (stats_on && lane == 0) {
       atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));
@@ -343,7 +349,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       atomicAdd(cfg.stats + 10, (unsigned long long)ntiles * (TN / 64));
     }
     // end of unit: the list stays unordered; the unit merge reads `cnt` keys from it
-    p.counts[vunit * TM + rloc] = row_valid ? st.cnt : 0;
+    if (!dense) p.counts[vunit * TM + rloc] = row_valid ? st.cnt : 0;
   }
 
   ptx::tc_fence_before();

@@ -461,4 +461,47 @@ __device__ __forceinline__ void flush_pending_hits(RowState& st, PendingHits& pe
   }
 }
 
+// Dense mode of the tcgen05 kernels: instead of selecting, the owners of a query row write its scores of this tile to the
+// dense [nq, ld] block (similarity, or the positive L2 distance; the query's own column masked as knn_scores_dense does).
+// Every lane executes the (warp-collective) tensor-memory loads; a lane without a valid row just does not store.
+template <bool kL2>
+__device__ __forceinline__ void dense_store_tile_tmem(uint32_t taddr, int first, int step, int nchunks, int64_t col0,
+                                                      int64_t c_end, const float* gst, float qn, int64_t row,
+                                                      int64_t self_col, int self_mode, float* __restrict__ out,
+                                                      int64_t ld) {
+#pragma unroll 1
+  for (int ch = first; ch < nchunks; ch += step) {
+    const int cb = ch * 32;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
+    ptx::tmem_ld_fence(v);
+    if (row < 0) continue;
+    const int64_t cg = col0 + cb;
+    if (cg >= c_end) continue;
+    float* dst = out + row * ld + cg;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]);
+      if (kL2) x = __fsqrt_rn(fmaxf(-fmaf(2.0f, x, -(qn + gst[cb + j])), 0.0f));
+      f[j] = x;
+    }
+    if (self_col >= cg && self_col < cg + 32) {
+      const float m = self_mode == KNN_SELF_EXCLUDE ? (kL2 ? INFINITY : -INFINITY) : (kL2 ? 1.0f : -1.0f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cg + j == self_col) f[j] = m;
+    }
+    if (cg + 32 <= c_end && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        __stcs(reinterpret_cast<float4*>(dst + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cg + j < c_end) __stcs(dst + j, f[j]);
+    }
+  }
+}
+
 }  // namespace knn

@@ -21,7 +21,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import _lib as L
-from .search import _METRICS, _SELF, _prepare, _ptr, _require_cuda, _scores_dense_prepared, _stream
+from .search import _METRICS, _SELF, _prepare, _ptr, _require_cuda, _scores_dense_prepared, _stream, split_bf16x3
 
 REL_SINGLE, REL_JACCARD_F32, REL_JACCARD_F64, REL_ANY = 0, 1, 2, 3
 _CHUNK_BYTES = 8 << 30   # transient memory budget of the query chunks in flight
@@ -174,7 +174,7 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
                        self_last_positive: bool = False, outputs: Optional[Sequence[str]] = None,
                        eps: float = 1e-12, eps_mode: str = "clamp",
                        rows_per_chunk: Optional[int] = None, distributed: bool = False,
-                       group=None) -> Dict[str, torch.Tensor]:
+                       group=None, precision: str = "fp32") -> Dict[str, torch.Tensor]:
     """Per-query full-ranking statistics of ``queries`` against the whole ``gallery`` (exact fp32 scores), chunked over
     the queries.  ``self_mode`` is the score the query's own gallery row gets (``fill_diagonal_``: "exclude" = -inf,
     "minus1" = -1, "keep"); ``drop_self`` removes that row from the ranking and from the relevant set.
@@ -187,15 +187,22 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     ``distributed=True`` (inside an initialised ``torch.distributed`` job, every rank holding the same inputs): the
     QUERIES are sharded -- rank r ranks the rows of ``query_slice(Q, W, r)`` against the whole gallery, the per-query
     statistics are all-gathered (a few bytes per query) and every rank returns the full, identical result.  The
-    reference all-gathers the EMBEDDINGS and recomputes everything on every rank (train.py:604-609)."""
+    reference all-gathers the EMBEDDINGS and recomputes everything on every rank (train.py:604-609).
+
+    ``precision``: "fp32" (default) ranks the exact fp32 scores -- bit-equal to the dense path and the oracle, bound by
+    the FP32 pipe; "bf16x3" computes the score block on the tensor cores from the error-free bf16 split of the fp32
+    rows (|score error| <~ 1e-5 |q||g|: only scores that close may swap ranks); "bf16" ranks bf16-rounded rows."""
     _require_cuda(queries, gallery)
+    if precision not in ("fp32", "bf16", "bf16x3"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
     if metric not in _METRICS:
         raise ValueError(f"metric must be one of {sorted(_METRICS)}")
     if self_mode not in _SELF:
         raise ValueError(f"self_mode must be one of {sorted(_SELF)}")
     want_sq = metric == "l2"
-    q, qsq = _prepare(queries, normalize, "fp32", eps, eps_mode, want_sq)
-    g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, "fp32", eps, eps_mode, want_sq)
+    prep = "bf16" if precision == "bf16" else "fp32"
+    q, qsq = _prepare(queries, normalize, prep, eps, eps_mode, want_sq)
+    g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, prep, eps, eps_mode, want_sq)
     nq, ng = q.shape[0], g.shape[0]
     if nq == 0:
         raise ValueError("no queries")
@@ -212,15 +219,17 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
                                    q_group=None if q_group is None else q_group[s0:e0], g_group=g_group,
                                    jaccard_threshold=jaccard_threshold, kappas=kappas, sklearn_ap=sklearn_ap,
                                    self_last_positive=self_last_positive, outputs=outputs,
-                                   rows_per_chunk=rows_per_chunk) if e0 > s0 else None
+                                   rows_per_chunk=rows_per_chunk, precision=precision) if e0 > s0 else None
         if local is None:   # a rank without queries still takes part in the collectives: build empty outputs
             probe = full_ranking_stats(q[:1], g, rel_mode, q_rel[:1], g_rel, metric=metric, self_mode=self_mode,
                                        drop_self=drop_self, query_offset=query_offset, jaccard_threshold=jaccard_threshold,
                                        kappas=kappas, sklearn_ap=sklearn_ap, self_last_positive=self_last_positive,
-                                       outputs=outputs, q_group=None if q_group is None else q_group[:1], g_group=g_group)
+                                       outputs=outputs, q_group=None if q_group is None else q_group[:1], g_group=g_group,
+                                       precision=precision)
             local = {k: v[:0] for k, v in probe.items()}
         return gather_query_sharded(local, nq, group)
     dev = q.device
+    g3 = split_bf16x3(g, "gallery") if precision == "bf16x3" else None   # once; the query chunks are split on the fly
     step = int(rows_per_chunk) if rows_per_chunk else chunk_rows(ng, sklearn_ap, device=dev)
     main = torch.cuda.current_stream(dev)
     nchunks = (nq + step - 1) // step
@@ -233,8 +242,12 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
             old_rp, old_done = pending.pop(0)
             main.wait_event(old_done)
             del old_rp
-        sc = _scores_dense_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, metric, self_mode,
-                                    query_offset + s)
+        if g3 is not None:
+            sc = _scores_dense_prepared(split_bf16x3(q[s:e], "queries"), None if qsq is None else qsq[s:e], g3, gsq,
+                                        metric, self_mode, query_offset + s, split_rows=True)
+        else:
+            sc = _scores_dense_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, metric, self_mode,
+                                        query_offset + s)
         rp = rank_of_positives(sc, rel_mode, q_rel[s:e], g_rel, largest_first=(metric != "l2"),
                                jaccard_threshold=jaccard_threshold, self_offset=query_offset + s, drop_self=drop_self,
                                q_group=None if q_group is None else q_group[s:e], g_group=g_group, ties=sklearn_ap)

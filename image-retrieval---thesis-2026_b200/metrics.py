@@ -263,7 +263,7 @@ def compute_map(ranks, gnd, kappas=[]):
 
 
 def compute_map_from_embeddings(embeds: torch.Tensor, labels, kappas=(), metric: str = "l2", normalize: bool = False,
-                                distributed: bool = False):
+                                distributed: bool = False, precision: str = "fp32"):
     """``compute_map(argsort(dists, dim=0), labels, kappas)`` (test.py:1090-1091) straight from the embeddings, without
     the N x N ``dists`` / ``ranks`` matrices: ``dists = -cdist(e, e)`` (``metric="l2"``) or ``e @ e.T`` with the
     diagonal at -inf, the trapezoidal AP and mP@k of test.py:58-146 over the full ranking.  The query counts among its
@@ -272,7 +272,7 @@ def compute_map_from_embeddings(embeds: torch.Tensor, labels, kappas=(), metric:
     lab = _dev_i64(labels, embeds.device).view(-1)
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, lab, lab, metric=metric, normalize=normalize,
                                self_mode="exclude", drop_self=True, kappas=kappas, self_last_positive=True,
-                               outputs=("ap_trapz", "prs", "nres"), distributed=distributed)
+                               outputs=("ap_trapz", "prs", "nres"), distributed=distributed, precision=precision)
     aps = st["ap_trapz"].cpu().numpy()
     prs_np = st["prs"].cpu().numpy().reshape(len(aps), len(kappas))
     valid = st["nres"].cpu().numpy() > 0
@@ -429,7 +429,7 @@ def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch
 # D6 / D11 / D13: embeddings-in single-label evaluation (train.py:399-441; fusion_eval/metrics.py:41-94)
 # --------------------------------------------------------------------------------------------------
 def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10),
-                                            distributed: bool = False):
+                                            distributed: bool = False, precision: str = "fp32"):
     """train.py:399-441: cosine self-retrieval, standard AP over the full ranking / (#same-label - 1), R@K."""
     if len(labels) <= 1:
         return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
@@ -437,7 +437,7 @@ def _compute_single_label_retrieval_metrics(embeds: torch.Tensor, labels: torch.
     labels = _dev_i64(labels, embeds.device).view(-1)
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_SINGLE, labels, labels, metric="cosine", normalize=True,
                                self_mode="exclude", drop_self=True, outputs=("prec_sum", "first"),
-                               distributed=distributed)
+                               distributed=distributed, precision=precision)
     hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
     aps = np.where(hits_np > 0, ps / np.maximum(hits_np, 1), 0.0)   # relevant_counts == hits over the full ranking
     metrics = {"mAP": float(np.mean(aps) * 100.0)}
@@ -526,14 +526,14 @@ def is_retrieval_correct(query_label, results, config=None) -> bool:
 # D4 / D7 / D8: multilabel AP over the full ranking
 # --------------------------------------------------------------------------------------------------
 def compute_map_multilabel_from_embeddings(embeds: torch.Tensor, labels_multihot: torch.Tensor,
-                                           threshold: float = 0.5, distributed: bool = False) -> float:
+                                           threshold: float = 0.5, distributed: bool = False, precision: str = "fp32") -> float:
     """test.py:941-985 on cosine self-retrieval: rank-by-rank AP, relevance = Jaccard > threshold, self removed,
     queries without relevant items skipped."""
     _require_cuda(embeds)
     m = pack_multihot(labels_multihot.to(embeds.device))
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
                                self_mode="exclude", drop_self=True, jaccard_threshold=float(threshold),
-                               outputs=("prec_sum",), distributed=distributed)
+                               outputs=("prec_sum",), distributed=distributed, precision=precision)
     hits_np, ps = st["npos"].cpu().numpy(), st["prec_sum"].cpu().numpy()
     aps = (ps / np.maximum(hits_np, 1))[hits_np > 0]
     return float(np.mean(aps)) if len(aps) else 0
@@ -556,7 +556,8 @@ def compute_map_multilabel(dists: torch.Tensor, labels: torch.Tensor, threshold:
 
 
 def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Tensor, topk=(1, 5, 10),
-                                          relevance_threshold: float = 0.4, distributed: bool = False):
+                                          relevance_threshold: float = 0.4, distributed: bool = False,
+                                          precision: str = "fp32"):
     """train.py:444-487: sklearn AP (tied scores grouped) with self masked out, R@K = any relevant in top-k."""
     if len(labels) <= 1:
         return {"mAP": 0.0, **{f"R@{k}": 0.0 for k in topk}}
@@ -564,7 +565,7 @@ def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Te
     m = pack_multihot(labels.to(embeds.device))
     st = FR.full_ranking_stats(embeds, embeds, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
                                self_mode="exclude", drop_self=True, jaccard_threshold=float(relevance_threshold),
-                               sklearn_ap=True, outputs=("first",), distributed=distributed)
+                               sklearn_ap=True, outputs=("first",), distributed=distributed, precision=precision)
     hits_np, first_np = st["npos"].cpu().numpy(), st["first"].cpu().numpy()
     aps = st["ap_sklearn"].cpu().numpy()[hits_np > 0]
     metrics = {"mAP": float(np.mean(aps) * 100.0) if len(aps) > 0 else 0.0}
@@ -575,7 +576,7 @@ def _compute_multilabel_retrieval_metrics(embeds: torch.Tensor, labels: torch.Te
 
 
 def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jaccard_threshold: float = 0.4,
-                            distributed: bool = False) -> float:
+                            distributed: bool = False, precision: str = "fp32") -> float:
     """nih_multilabel_training.py:66-99 on given embeddings: self is KEPT with similarity -1 and counts as a
     relevant item (J(self, self) = 1 > threshold) ranked wherever -1 falls.  ``distributed=True`` inside a
     ``torch.distributed`` job shards the QUERIES over the ranks (every rank passes the same embeddings, as after the
@@ -584,7 +585,7 @@ def evaluate_map_embeddings(embeddings: torch.Tensor, labels: torch.Tensor, jacc
     m = pack_multihot(labels.to(embeddings.device))
     st = FR.full_ranking_stats(embeddings, embeddings, FR.REL_JACCARD_F32, m, m, metric="cosine", normalize=True,
                                self_mode="minus1", drop_self=False, jaccard_threshold=float(jaccard_threshold),
-                               sklearn_ap=True, outputs=(), distributed=distributed)
+                               sklearn_ap=True, outputs=(), distributed=distributed, precision=precision)
     hits = st["npos"].cpu().numpy()
     aps = st["ap_sklearn"].cpu().numpy()[hits > 0]
     if len(aps) == 0:

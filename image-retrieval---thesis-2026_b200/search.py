@@ -396,12 +396,14 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     return out_val, out_idx
 
 
-def _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, self_offset_local):
+def _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, self_offset_local, split_rows=False):
+    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3); bf16 rows run the tcgen05 kernel, fp32 rows the exact one."""
     nq, d = q.shape
     ng = g.shape[0]
     out = torch.empty((nq, ng), dtype=torch.float32, device=q.device)
+    dt = L.KNN_BF16X3 if split_rows else _DT[q.dtype]
     with torch.cuda.device(q.device):
-        rc = L.load().knn_scores_dense(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _DT[q.dtype],
+        rc = L.load().knn_scores_dense(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, dt,
                                        _METRICS[metric], _SELF[self_mode], self_offset_local, _ptr(out), _stream(q))
     L.check(rc, "knn_scores_dense")
     return out
@@ -457,13 +459,22 @@ def search(
 
 def scores_dense(queries: torch.Tensor, gallery: torch.Tensor, metric: str = "cosine", *, normalize: bool = False,
                  self_mode: str = "keep", query_offset: int = 0, eps: float = 1e-12,
-                 eps_mode: str = "clamp") -> torch.Tensor:
-    """The dense ``dists`` matrix of test.py:1080 / fusion_eval/metrics.py:15 for SMALL problems (callers that
-    save or post-process the full matrix).  Similarities for cosine/ip, positive distances for l2."""
+                 eps_mode: str = "clamp", precision: str = "fp32") -> torch.Tensor:
+    """The dense ``dists`` matrix of test.py:1080 / fusion_eval/metrics.py:15 (callers that save or post-process the
+    full matrix).  Similarities for cosine/ip, positive distances for l2.  precision: "fp32" = the exact fp32 chain
+    (bit-equal to the search), "bf16" = bf16 rows on the tensor cores, "bf16x3" = fp32 rows through the error-free
+    three-product split on the tensor cores (|error| <~ 1e-5 |q||g|)."""
     _require_cuda(queries, gallery)
+    if precision not in ("fp32", "bf16", "bf16x3"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'bf16x3'")
     want_sq = metric == "l2"
-    q, qsq = _prepare(queries, normalize, "fp32", eps, eps_mode, want_sq)
-    g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, "fp32", eps, eps_mode, want_sq)
+    prep = "bf16" if precision == "bf16" else "fp32"
+    q, qsq = _prepare(queries, normalize, prep, eps, eps_mode, want_sq)
+    g, gsq = (q, qsq) if gallery is queries else _prepare(gallery, normalize, prep, eps, eps_mode, want_sq)
+    if precision == "bf16x3":
+        q3 = split_bf16x3(q, "queries")
+        g3 = split_bf16x3(g, "gallery")
+        return _scores_dense_prepared(q3, qsq, g3, gsq, metric, self_mode, int(query_offset), split_rows=True)
     return _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, int(query_offset))
 
 

@@ -199,9 +199,12 @@ KNN_API int knn_lesion_rerank(const float* cand_val, const int64_t* cand_idx, in
 KNN_API int knn_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest,
                   float* out_vals, int64_t* out_idx, void* stream);
 
-/* Dense score matrix (small problems only; compatibility with callers that want the full `dists`
- * matrix of test.py:1080 / fusion_eval/metrics.py:15).  out [nq,ng] fp32, same score definition and
- * self handling as knn_search (KNN_SELF_EXCLUDE writes -inf for similarity, +inf for L2). */
+/* Dense score block (callers that want the full `dists` matrix of test.py:1080 / fusion_eval/metrics.py:15, and the
+ * per-chunk input of knn_rank_of_positives).  out [nq,ng] fp32, same score definition and self handling as knn_search
+ * (KNN_SELF_EXCLUDE writes -inf for similarity, +inf for L2).  dtype KNN_F32: the exact fp32 chain (FFMA kernel);
+ * KNN_BF16 / KNN_BF16X3 (d a multiple of 8 / rows of knn_split_bf16x3): the tcgen05 CTA-pair kernel with a store
+ * epilogue -- bf16 inputs with fp32 accumulation, or the three-product split that reproduces the fp32 inner product to
+ * ~1e-5 |q||g| (q_sqnorm / g_sqnorm = the norms of the fp32 rows for KNN_L2). */
 KNN_API int knn_scores_dense(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm,
                      int64_t nq, int64_t ng, int d, int dtype, int metric,
                      int self_mode, int64_t self_offset, float* out, void* stream);

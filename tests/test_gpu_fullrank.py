@@ -263,3 +263,52 @@ def test_nih_scale_full_ranking_map_without_an_n_by_n_matrix(knn):
             assert RM.average_precision_ranked(sc[q][order], rel[order]) == got[q], q
         else:
             assert np.isnan(got[q])
+
+
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_tensor_core_dense_scores(knn, metric):
+    """knn_scores_dense on the tcgen05 kernel: bf16 rows = fp32 accumulation of the bf16-rounded inputs; bf16x3 = the
+    error-free split, |error| <= the filter bound of the exact engine (3.02 * 2^-18 + accumulation) |q||g|."""
+    rs = np.random.RandomState(5)
+    nq, ng, d = 300, 5000, 200                                  # odd block count, ragged tile, d not a multiple of 64
+    q = oracle.normalize(rs.standard_normal((nq, d)).astype(np.float32))
+    g = oracle.normalize(rs.standard_normal((ng, d)).astype(np.float32))
+    exact = knn.scores_dense(dev(q), dev(g), metric, self_mode="exclude", query_offset=17).cpu().numpy()
+    assert np.array_equal(exact, oracle.scores(q, g, metric, "exclude", 17))
+    x3 = knn.scores_dense(dev(q), dev(g), metric, self_mode="exclude", query_offset=17, precision="bf16x3").cpu().numpy()
+    fin = np.isfinite(exact)
+    assert np.array_equal(np.isinf(x3), ~fin)                   # the masked self entries
+    tol = 3e-5 if metric == "cosine" else 2e-3                  # d = sqrt(d^2): the error of d^2 (~4e-5) over 2 d
+    assert np.abs(x3[fin] - exact[fin]).max() < tol
+    b = knn.scores_dense(dev(q), dev(g), metric, self_mode="minus1" if metric == "cosine" else "keep",
+                         query_offset=17, precision="bf16").cpu().numpy()
+    qb, gb = oracle.bf16_round(q), oracle.bf16_round(g)
+    want = qb.astype(np.float64) @ gb.astype(np.float64).T
+    if metric == "l2":
+        want = np.sqrt(np.maximum((qb.astype(np.float64) ** 2).sum(1)[:, None] + (gb.astype(np.float64) ** 2).sum(1)[None, :]
+                                  - 2 * want, 0))
+        assert np.abs(b - want).max() < 2e-3
+    else:
+        r = np.arange(nq)
+        assert np.all(b[r, r + 17] == -1.0)
+        b[r, r + 17] = want[r, r + 17]
+        assert np.abs(b - want).max() < 1e-5
+
+
+def test_full_ranking_metrics_on_the_tensor_cores_track_the_exact_ones(knn):
+    """precision="bf16x3": the score block comes from the tensor cores; only scores closer than ~1e-5 may swap ranks, so
+    the metrics agree with the exact mode to ~1e-6."""
+    M = knn.metrics
+    n, d = 6000, 128
+    ml = synth.multihot(n, seed=12)
+    emb = dev(synth.labelset_clustered(ml, d, 13, 1.0))
+    mld = dev(ml)
+    a = M.evaluate_map_embeddings(emb, mld, 0.4)
+    b = M.evaluate_map_embeddings(emb, mld, 0.4, precision="bf16x3")
+    c = M.evaluate_map_embeddings(emb, mld, 0.4, precision="bf16")
+    assert abs(a - b) < 1e-4 and abs(a - c) < 0.05, (a, b, c)
+    x, lab = synth.clustered(n, d, 5, seed=14, noise=3.0)
+    ea = M._compute_single_label_retrieval_metrics(dev(x), dev(lab))
+    eb = M._compute_single_label_retrieval_metrics(dev(x), dev(lab), precision="bf16x3")
+    for k in ea:
+        assert abs(ea[k] - eb[k]) < 1e-3, (k, ea[k], eb[k])

@@ -32,3 +32,6 @@ for _ in range(2):
     sc = _scores_dense_prepared(q, None, emb, None, "cosine", "exclude", 0); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 print(f"dense 1184 x {n}: {dt*1e3:.2f} ms -> {2*1184*n*d/dt/1e12:.1f} TFLOP/s; all rows {dt*n/1184:.3f} s")
+for prec in ("bf16x3", "bf16"):
+    t(f"evaluate_map_embeddings precision={prec}", lambda: M.evaluate_map_embeddings(emb, mld, 0.4, precision=prec))
+    t(f"compute_map_multilabel precision={prec}", lambda: M.compute_map_multilabel_from_embeddings(emb, mld, 0.5, precision=prec))
