@@ -24,6 +24,7 @@
 // Order: best score first (largest, or smallest with largest_first = 0), ties by ascending gallery row -- the order of
 // knn_search / knn_rank_rows, so the ranks equal the positions a full knn_rank_rows ranking would give.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace knn {
@@ -214,6 +215,74 @@ __device__ uint32_t smem_exclusive_scan(uint32_t* arr, int n, unsigned long long
   return total;
 }
 
+// Runs of equal scores over the fully sorted row `sorted` (nr keys): per positive its rank, the end of its run (ge = items
+// with a score >= its own) and the number of distinct score values above it (tgroup); npos / ngroups of the row.
+__device__ void ties_pass(const RankParams& p, const uint64_t* tmp, int64_t nr, int64_t row, unsigned long long* red) {
+  const int tid = threadIdx.x;
+  int32_t* out_rank = p.pos_ranks + row * p.ld_out;
+  struct { unsigned long long* red; } sh{red};
+  // ---- 5. runs of equal scores over the sorted row: per positive its rank, the end of its run (ge = items with a
+  // score >= its own) and the number of distinct score values above it (tgroup)
+  int32_t* out_ge = p.pos_ge + row * p.ld_out;
+  int32_t* out_tg = p.pos_tgroup + row * p.ld_out;
+  unsigned long long carry_add = 0, carry_max = 0;   // (positives << 32 | run starts) so far; last run start so far
+  for (int64_t base = 0; base < nr; base += kChunk) {
+    uint32_t rl[kItems], st[kItems];
+    unsigned long long loc = 0;
+    const int64_t i0 = base + tid * kItems;
+    uint32_t prev_ord = (i0 > 0 && i0 - 1 < nr) ? (uint32_t)(tmp[i0 - 1] >> 32) : 0u;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      const int64_t i = i0 + u;
+      rl[u] = 0; st[u] = 0;
+      if (i < nr) {
+        const unsigned long long ki = tmp[i];
+        rl[u] = (uint32_t)(ki & 1ull);
+        st[u] = (i == 0) || (prev_ord != (uint32_t)(ki >> 32));
+        prev_ord = (uint32_t)(ki >> 32);
+      }
+      loc += ((unsigned long long)rl[u] << 32) | st[u];
+    }
+    unsigned long long tot_add, tot_max;
+    unsigned long long run = carry_add + block_excl_add(loc, sh.red, tot_add);   // before this thread's items
+    // this thread's last run start as ((position + 1) << 32 | positives before it): the later start wins the max
+    unsigned long long mine = 0, r2 = run;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      if (st[u]) mine = ((unsigned long long)(i0 + u + 1) << 32) | (uint32_t)(r2 >> 32);
+      r2 += ((unsigned long long)rl[u] << 32) | st[u];
+    }
+    unsigned long long last = block_excl_max(mine, sh.red, tot_max);
+    if (carry_max > last) last = carry_max;
+#pragma unroll
+    for (int u = 0; u < kItems; ++u) {
+      const int64_t i = i0 + u;
+      if (i < nr) {
+        const uint32_t pidx = (uint32_t)(run >> 32);   // positives before position i
+        if (st[u]) {
+          // a run starting at i > 0 closes the previous run: its positives P(start) .. pidx - 1 get ge = i
+          if (i > 0)
+            for (uint32_t t = (uint32_t)last; t < pidx; ++t) out_ge[t] = (int32_t)i;
+          last = ((unsigned long long)(i + 1) << 32) | pidx;
+        }
+        if (rl[u]) {
+          out_rank[pidx] = (int32_t)i;
+          out_tg[pidx] = (int32_t)((uint32_t)run + st[u] - 1);   // run starts in [0, i] minus one
+        }
+      }
+      run += ((unsigned long long)rl[u] << 32) | st[u];
+    }
+    carry_add += tot_add;
+    if (tot_max > carry_max) carry_max = tot_max;
+  }
+  if (tid == 0) {
+    const uint32_t total_pos = (uint32_t)(carry_add >> 32);
+    for (uint32_t t = (uint32_t)carry_max; t < total_pos; ++t) out_ge[t] = (int32_t)nr;   // the last run
+    p.npos[row] = (int32_t)total_pos;
+    if (p.ngroups) p.ngroups[row] = (int32_t)(uint32_t)carry_add;
+  }
+}
+
 #ifdef RP_TIMING
 __device__ unsigned long long rp_timing[8];
 #define RP_TICK(slot)                                                        \
@@ -256,10 +325,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) rank_positives_kernel(Ra
   __syncthreads();
 
   while (true) {
-    if (tid == 0) sh.row_claim = atomicAdd(p.next_row, 1u);
+    if (tid == 0) {
+      const unsigned int c = atomicAdd(p.next_row, 1u);
+      sh.row_claim = c < p.nq ? c : 0xFFFFFFFFu;
+    }
     __syncthreads();
+    if (sh.row_claim == 0xFFFFFFFFu) break;
     const int64_t row = sh.row_claim;
-    if (row >= p.nq) break;
     const float* srow = p.scores + row * p.ld_scores;
     const int64_t self = p.drop_self ? p.self_offset + row : -1;
     const int64_t ql = p.qlab[row];
@@ -508,7 +580,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) rank_positives_kernel(Ra
         }
         if (ls >= w0 && le <= w0 + kStage) {
           const int o0 = (int)(ls - w0), o1 = (int)(le - w0), oi = kHalo + off;
-          for (int o = o0; o < o1; ++o) {
+          int o = o0;
+          for (; o + 4 <= o1; o += 4) {   // four independent shared-memory loads in flight (the walk is latency bound)
+            const unsigned long long k0 = sh.u.stage[o], k1 = sh.u.stage[o + 1], k2 = sh.u.stage[o + 2], k3 = sh.u.stage[o + 3];
+            const uint32_t g0 = (k0 >> 2) > mine, g1 = (k1 >> 2) > mine, g2 = (k2 >> 2) > mine, g3 = (k3 >> 2) > mine;
+            gt += g0 + g1 + g2 + g3;
+            pos_gt += ((uint32_t)k0 & g0) + ((uint32_t)k1 & g1) + ((uint32_t)k2 & g2) + ((uint32_t)k3 & g3);
+            pos_before += ((uint32_t)k0 & (uint32_t)(o < oi)) + ((uint32_t)k1 & (uint32_t)(o + 1 < oi)) +
+                          ((uint32_t)k2 & (uint32_t)(o + 2 < oi)) + ((uint32_t)k3 & (uint32_t)(o + 3 < oi));
+          }
+          for (; o < o1; ++o) {
             const unsigned long long kj = sh.u.stage[o];
             const uint32_t g = (kj >> 2) > mine;
             gt += g;
@@ -565,66 +646,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) rank_positives_kernel(Ra
     }   // slabs
 
     if (p.ties) {
-      // ---- 5. runs of equal scores over the sorted row: per positive its rank, the end of its run (ge = items with a
-      // score >= its own) and the number of distinct score values above it (tgroup)
-      int32_t* out_ge = p.pos_ge + row * p.ld_out;
-      int32_t* out_tg = p.pos_tgroup + row * p.ld_out;
-      unsigned long long carry_add = 0, carry_max = 0;   // (positives << 32 | run starts) so far; last run start so far
-      for (int64_t base = 0; base < nr; base += kChunk) {
-        uint32_t rl[kItems], st[kItems];
-        unsigned long long loc = 0;
-        const int64_t i0 = base + tid * kItems;
-        uint32_t prev_ord = (i0 > 0 && i0 - 1 < nr) ? (uint32_t)(tmp[i0 - 1] >> 32) : 0u;
-#pragma unroll
-        for (int u = 0; u < kItems; ++u) {
-          const int64_t i = i0 + u;
-          rl[u] = 0; st[u] = 0;
-          if (i < nr) {
-            const unsigned long long ki = tmp[i];
-            rl[u] = (uint32_t)(ki & 1ull);
-            st[u] = (i == 0) || (prev_ord != (uint32_t)(ki >> 32));
-            prev_ord = (uint32_t)(ki >> 32);
-          }
-          loc += ((unsigned long long)rl[u] << 32) | st[u];
-        }
-        unsigned long long tot_add, tot_max;
-        unsigned long long run = carry_add + block_excl_add(loc, sh.red, tot_add);   // before this thread's items
-        // this thread's last run start as ((position + 1) << 32 | positives before it): the later start wins the max
-        unsigned long long mine = 0, r2 = run;
-#pragma unroll
-        for (int u = 0; u < kItems; ++u) {
-          if (st[u]) mine = ((unsigned long long)(i0 + u + 1) << 32) | (uint32_t)(r2 >> 32);
-          r2 += ((unsigned long long)rl[u] << 32) | st[u];
-        }
-        unsigned long long last = block_excl_max(mine, sh.red, tot_max);
-        if (carry_max > last) last = carry_max;
-#pragma unroll
-        for (int u = 0; u < kItems; ++u) {
-          const int64_t i = i0 + u;
-          if (i < nr) {
-            const uint32_t pidx = (uint32_t)(run >> 32);   // positives before position i
-            if (st[u]) {
-              // a run starting at i > 0 closes the previous run: its positives P(start) .. pidx - 1 get ge = i
-              if (i > 0)
-                for (uint32_t t = (uint32_t)last; t < pidx; ++t) out_ge[t] = (int32_t)i;
-              last = ((unsigned long long)(i + 1) << 32) | pidx;
-            }
-            if (rl[u]) {
-              out_rank[pidx] = (int32_t)i;
-              out_tg[pidx] = (int32_t)((uint32_t)run + st[u] - 1);   // run starts in [0, i] minus one
-            }
-          }
-          run += ((unsigned long long)rl[u] << 32) | st[u];
-        }
-        carry_add += tot_add;
-        if (tot_max > carry_max) carry_max = tot_max;
-      }
-      if (tid == 0) {
-        const uint32_t total_pos = (uint32_t)(carry_add >> 32);
-        for (uint32_t t = (uint32_t)carry_max; t < total_pos; ++t) out_ge[t] = (int32_t)nr;   // the last run
-        p.npos[row] = (int32_t)total_pos;
-        if (p.ngroups) p.ngroups[row] = (int32_t)(uint32_t)carry_add;
-      }
+      ties_pass(p, tmp, nr, row, sh.red);
     } else if (tid == 0) {
       p.npos[row] = (int32_t)carry;
     }
@@ -891,7 +913,7 @@ extern "C" __attribute__((visibility("default"))) int knn_rank_timing(unsigned l
 
 extern "C" size_t knn_rank_of_positives_workspace(int64_t nq, int64_t ng) {
   if (nq <= 0 || ng <= 0) return 0;
-  return (size_t)rank_grid(nq) * (size_t)ng * 2 * sizeof(uint64_t) + 256;   // key rows + the row counter
+  return (size_t)rank_grid(nq) * (size_t)ng * 2 * sizeof(uint64_t) + 256;   // key rows (two per resident CTA) + the row counter
 }
 
 extern "C" int knn_rank_of_positives(const float* scores, int64_t ld_scores, int64_t nq, int64_t ng, int largest_first,
@@ -914,7 +936,9 @@ extern "C" int knn_rank_of_positives(const float* scores, int64_t ld_scores, int
     set_error("knn_rank_of_positives: workspace too small (%zu < %zu)", workspace_bytes, need);
     return KNN_E_WORKSPACE;
   }
+  cudaStream_t st = (cudaStream_t)stream;
   RankParams p;
+  memset(&p, 0, sizeof(p));
   p.scores = scores; p.ld_scores = ld_scores; p.nq = nq; p.ng = ng; p.largest = largest_first ? 1 : 0;
   p.rel_mode = rel_mode;
   p.qlab = reinterpret_cast<const int64_t*>(q_rel);
@@ -940,12 +964,12 @@ extern "C" int knn_rank_of_positives(const float* scores, int64_t ld_scores, int
   p.scratch = reinterpret_cast<uint64_t*>(workspace);
   p.tmp = p.scratch + (size_t)grid * (size_t)ng;
   p.next_row = reinterpret_cast<unsigned int*>(p.tmp + (size_t)grid * (size_t)ng);
-  KNN_CHECK_CUDA(cudaMemsetAsync(p.next_row, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  KNN_CHECK_CUDA(cudaMemsetAsync(p.next_row, 0, sizeof(unsigned int), st));
   p.pos_ranks = pos_ranks; p.ld_out = ld_out; p.pos_ge = pos_ge; p.pos_tgroup = pos_tgroup;
   p.npos = npos; p.nranked = nranked; p.ngroups = ngroups;
   const size_t smem = rank_smem_bytes(p.nbins);
   KNN_CHECK_CUDA(cudaFuncSetAttribute(rank_positives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rank_positives_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  rank_positives_kernel<<<(unsigned)grid, kThreads, smem, st>>>(p);
   KNN_LAUNCHED();
   return KNN_OK;
 }

@@ -13,7 +13,7 @@ lib.knn_rank_timing(buf, 1)
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record(); FR.rank_of_positives(sd, 0, lab[:nq], lab, drop_self=True, ties=ties); t1.record()
 lib.knn_rank_timing(buf, 0)
-names = ["sample+map", "histogram", "bin scan", "scatter", "refine", "resolve", "ties/outputs"]
+names = ["sample+map", "histogram", "bin scan", "scatter/partition", "refine", "resolve/buckets", "ties/outputs"]
 tot = sum(buf[:7])
 print(f"{nq} x {ng} ties={ties}: {t0.elapsed_time(t1):.2f} ms (incl. host); per row cycles:")
 for n, c in zip(names, buf[:7]):
