@@ -189,7 +189,7 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     statistics are all-gathered (a few bytes per query) and every rank returns the full, identical result.  The
     reference all-gathers the EMBEDDINGS and recomputes everything on every rank (train.py:604-609).
 
-    ``precision``: "fp32" (default) ranks the exact fp32 scores -- bit-equal to the dense path and the oracle, bound by
+    ``precision``: "fp32" (default) ranks the exact fp32 scores -- bit-equal to the dense path and the CPU restatement in the tests, bound by
     the FP32 pipe; "bf16x3" computes the score block on the tensor cores from the error-free bf16 split of the fp32
     rows (|score error| <~ 1e-5 |q||g|: only scores that close may swap ranks); "bf16" ranks bf16-rounded rows."""
     _require_cuda(queries, gallery)

@@ -79,14 +79,12 @@ def test_formats_roundtrip(tmp_path):
     assert sorted(z.files) == sorted(["embeds", "labels", "dists", "kappas", "acc", "mAP", "pr",
                                       "classification_k_values", "classification_k1"])   # test.py:1122-1126
     assert np.isposinf(np.diag(z["dists"])).all() and np.array_equal(z["classification_k1"], np.arange(1.0, 8.0))
-    pred, idx = F.rank_retrieval(z, topk=3)
     want = np.argsort(np.where(np.isinf(-s), np.nan, -s), axis=1, kind="stable")[:, :3]
-    assert np.array_equal(idx, want) and np.array_equal(pred, lab[want])
     order = np.argsort(-s, axis=1, kind="stable")[:, :5]
     p2 = F.save_evaluation_npz(str(tmp_path / "sparse"), emb, lab, [1], np.array([1.0]), 0.1, np.array([0.1]), cls,
                                topk_dists=-np.take_along_axis(s, order, 1), topk_idx=order)
     pred2, idx2 = F.rank_retrieval(np.load(p2, allow_pickle=True), topk=3)
-    assert np.array_equal(idx2, want)
+    assert np.array_equal(idx2, want) and np.array_equal(pred2, lab[want])   # sparse bundles: host slicing only
 
     q = QueryRecord("q.png", "a")
     res = SearchResult(q, "conv", [RetrievedItem(1, "x.png", "a", 0.9, 0.9), RetrievedItem(2, "y.png", "b", 0.8, 0.8)], [0.0])
@@ -110,6 +108,24 @@ def test_formats_roundtrip(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_rank_retrieval_of_a_dense_bundle_on_the_device(tmp_path):
+    """compute_saliency.py:19-29: dense bundles are ranked by the library (knn_rank_rows), the query's own column last."""
+    from b200knn import formats as F
+
+    rs = np.random.RandomState(0)
+    n = 12
+    emb = rs.standard_normal((n, 4)).astype(np.float32)
+    lab = rs.randint(0, 3, n)
+    s = emb @ emb.T
+    np.fill_diagonal(s, -np.inf)
+    p = F.save_evaluation_npz(str(tmp_path / "run"), emb, lab, [1], np.array([1.0]), 0.1, np.array([0.1]), {},
+                              dists=torch.from_numpy(s))
+    pred, idx = F.rank_retrieval(np.load(p, allow_pickle=True), topk=3)
+    want = np.argsort(np.where(np.isinf(-s), np.nan, -s), axis=1, kind="stable")[:, :3]
+    assert np.array_equal(idx, want) and np.array_equal(pred, lab[want])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("exclude_self", [True, False])
 def test_adapter_matches_the_reference_adapter(gc, exclude_self):
