@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KNN_LIB") or os.path.join(_HERE, "libb200knn.so")
 
 # constants mirrored from include/b200knn.h
-KNN_F32, KNN_BF16, KNN_BF16X3 = 0, 1, 2
+KNN_F32, KNN_BF16, KNN_BF16X3, KNN_F32_PACKED = 0, 1, 2, 3
 KNN_COSINE, KNN_IP, KNN_L2 = 0, 1, 2
 KNN_EPS_CLAMP, KNN_EPS_NONE, KNN_EPS_ADD, KNN_CAST_ONLY = 0, 1, 2, 3
 KNN_SELF_KEEP, KNN_SELF_EXCLUDE, KNN_SELF_MINUS1 = 0, 1, 2
@@ -50,6 +50,8 @@ SIGNATURES = {
     "knn_rescore_topk": (_i, [_p, _p, _i64, _i, _p, _i64, _i, _p, _f, _f, _i, _i64, _i, _p, _p]),
     "knn_lesion_rerank": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p, _p, _i64, _i, _i, _d, _p, _p, _p, _p]),
     "knn_sort_topk": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
+    "knn_pack_f32_bytes": (_sz, [_i64, _i]),
+    "knn_pack_f32": (_i, [_p, _i64, _i, _p, _p]),
     "knn_scores_dense": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i64, _p, _p]),
     "knn_rank_rows": (_i, [_p, _i64, _i64, _i, _p, _p, _sz, _p]),
     "knn_rank_rows_workspace": (_sz, [_i64, _i64]),

@@ -302,9 +302,11 @@ static WsLayout ws_layout(const SearchGeom& g, int k) {
 extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
   if (dtype == KNN_BF16X3) dtype = KNN_BF16;  // same geometry: the split rows are bf16 rows of 3 * dpad columns
+  const bool packed = dtype == KNN_F32_PACKED;  // same geometry as KNN_F32; never the small-problem path
+  if (packed) dtype = KNN_F32;
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
   size_t need = ws_layout(g, k).total();
-  if (small_problem(nq, ng, dtype) && (size_t)nq * (size_t)ng * sizeof(float) > need)
+  if (!packed && small_problem(nq, ng, dtype) && (size_t)nq * (size_t)ng * sizeof(float) > need)
     need = (size_t)nq * (size_t)ng * sizeof(float);   // the dense score block of the small path
   return need;
 }
@@ -336,8 +338,12 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
     KNN_REQUIRE(d % 24 == 0, "KNN_BF16X3 rows are 3 parts of a multiple of 8 columns, got d=%d", d);
     dtype = KNN_BF16;
   }
+  const bool packed = dtype == KNN_F32_PACKED;
+  if (packed) dtype = KNN_F32;
   int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
   if (rc != KNN_OK) return rc;
+  if (packed) KNN_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) & 15) == 0,
+                          "KNN_F32_PACKED rows must be 16-byte aligned");
   KNN_REQUIRE(k >= 1, "k must be >= 1, got %d", k);
   if (k > kMaxFusedK) {
     set_error("knn_search: k=%d exceeds the fused limit %d; use knn_scores_dense + knn_rank_rows", k, kMaxFusedK);
@@ -345,14 +351,14 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   }
   if (nq == 0) return KNN_OK;
   KNN_REQUIRE(out_val && out_idx, "null output pointer");
-  const size_t need = knn_search_workspace(nq, ng, d, dtype, k);
+  const size_t need = knn_search_workspace(nq, ng, d, packed ? KNN_F32_PACKED : dtype, k);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("knn_search: workspace too small (%zu < %zu)", workspace_bytes, need);
     return KNN_E_WORKSPACE;
   }
   KNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  if (!split3 && small_problem(nq, ng, dtype)) {
+  if (!split3 && !packed && small_problem(nq, ng, dtype)) {
     SearchParams ps;
     memset(&ps, 0, sizeof(ps));
     ps.q = q; ps.g = g; ps.qsq = q_sqnorm; ps.gsq = g_sqnorm;
@@ -374,6 +380,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
   p.split3 = split3 ? 1 : 0;
+  p.f32_packed = packed ? 1 : 0;
   const WsLayout wl = ws_layout(geo, k);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
   p.tau_global = reinterpret_cast<uint32_t*>(wsb);
@@ -602,12 +609,16 @@ extern "C" size_t knn_score_stats_workspace(int64_t nq, int64_t ng) {
 extern "C" int knn_score_stats(const void* q, const void* g, const float* q_sqnorm, const float* g_sqnorm, int64_t nq,
                                int64_t ng, int d, int dtype, int metric, int self_mode, int64_t self_offset,
                                double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  const bool packed = dtype == KNN_F32_PACKED;
+  if (packed) dtype = KNN_F32;
   int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
   if (rc != KNN_OK) return rc;
   if (dtype != KNN_F32) {
     set_error("knn_score_stats: fp32 inputs only");
     return KNN_E_UNSUPPORTED;
   }
+  if (packed) KNN_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) & 15) == 0,
+                          "KNN_F32_PACKED rows must be 16-byte aligned");
   if (nq == 0) return KNN_OK;
   KNN_REQUIRE(out, "null output pointer");
   KNN_REQUIRE(ng > 0, "knn_score_stats: empty gallery");
@@ -628,6 +639,7 @@ extern "C" int knn_score_stats(const void* q, const void* g, const float* q_sqno
   dense_splits(p.qblocks, ntiles, (int64_t)2 * sm_count(), &tps, &p.splits);
   p.split_len = tps * 128;
   p.stats_out = reinterpret_cast<double*>(workspace);
+  p.f32_packed = packed ? 1 : 0;
   rc = launch_search_f32(p, false, (cudaStream_t)stream);
   if (rc != KNN_OK) return rc;
   return launch_stats_reduce(p.stats_out, p.splits, p.qblocks, nq, out, (cudaStream_t)stream);
@@ -659,10 +671,14 @@ extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqn
     KNN_REQUIRE(d % 24 == 0, "KNN_BF16X3 rows are 3 parts of a multiple of 8 columns, got d=%d", d);
     dtype = KNN_BF16;
   }
+  const bool packed = dtype == KNN_F32_PACKED;
+  if (packed) dtype = KNN_F32;
   int rc = check_common(q, g, q_sqnorm, g_sqnorm, nq, ng, d, dtype, metric, self_mode);
   if (rc != KNN_OK) return rc;
   if (nq == 0 || ng == 0) return KNN_OK;
   KNN_REQUIRE(out, "null output pointer");
+  if (packed) KNN_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) & 15) == 0,
+                          "KNN_F32_PACKED rows must be 16-byte aligned");
   if (dtype == KNN_BF16) {
     // tensor-core dense mode: the CTA-pair tcgen05 kernel with a store epilogue (bf16 rows, or bf16x3 split rows whose
     // three products reproduce the fp32 inner product to ~1e-5 |q||g|)
@@ -695,6 +711,21 @@ extern "C" int knn_scores_dense(const void* q, const void* g, const float* q_sqn
   dense_splits(p.qblocks, ntiles, (int64_t)2 * sm_count(), &tps, &p.splits);   // two resident CTAs per SM
   p.split_len = tps * 128;
   p.dense_out = out;
-  if (((nq + 127) / 128) * ((ng + 127) / 128) * 2 < sm_count()) return launch_dense_small(p, (cudaStream_t)stream);
+  p.f32_packed = packed ? 1 : 0;
+  if (!packed && ((nq + 127) / 128) * ((ng + 127) / 128) * 2 < sm_count())
+    return launch_dense_small(p, (cudaStream_t)stream);
   return launch_search_f32(p, true, (cudaStream_t)stream);
+}
+
+extern "C" size_t knn_pack_f32_bytes(int64_t n, int d) {
+  if (n <= 0 || d < 1) return 0;
+  return pack_f32_bytes(n, d);
+}
+
+extern "C" int knn_pack_f32(const float* x, int64_t n, int d, float* out, void* stream) {
+  KNN_REQUIRE(n >= 0 && d >= 1, "knn_pack_f32: bad shape n=%lld d=%d", (long long)n, d);
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(x && out, "knn_pack_f32: null pointer");
+  KNN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "knn_pack_f32: out must be 16-byte aligned");
+  return launch_pack_f32(x, n, d, out, (cudaStream_t)stream);
 }

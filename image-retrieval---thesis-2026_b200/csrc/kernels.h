@@ -22,6 +22,7 @@ struct SearchParams {
   int groups;            // candidate lists per (split, row): 2 for the TMEM-resident kernel, else 1
   int qblocks;
   int split3;            // rows are knn_split_bf16x3 output (3 parts of d/3 columns): q [hi|lo|hi], g [hi|hi|lo]
+  int f32_packed;        // fp32 rows are knn_pack_f32 output (128-row tiles [tile][dpad][128]); d is the original width
   uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys (unordered)
   int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished
   uint32_t* tau_global;  // [qblocks*128] shared thresholds (order-preserving encoding, 0 = none)
@@ -37,6 +38,10 @@ struct SearchParams {
 };
 
 int launch_search_f32(const SearchParams& p, bool dense, cudaStream_t stream);
+// fp32 rows [n, d] -> 128-row tiles [ceil(n/128)][dpad][128] (dpad = d rounded up to 16, zero padded): the operand
+// layout of the bulk-copy pipeline of the FFMA kernel (KNN_F32_PACKED)
+size_t pack_f32_bytes(int64_t n, int d);
+int launch_pack_f32(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
 int launch_search_bf16(const SearchParams& p, cudaStream_t stream);       // dispatch (pair kernel by default)
 int launch_search_bf16_pair(const SearchParams& p, cudaStream_t stream);  // cta_group::2, csrc/search_tc2.cu
 int bf16_tile_cols();  // gallery rows per tile of the shared-memory-A tcgen05 kernels

@@ -21,7 +21,8 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import _lib as L
-from .search import _METRICS, _SELF, _prepare, _ptr, _require_cuda, _scores_dense_prepared, _stream, split_bf16x3
+from .search import (PackedRows, _METRICS, _SELF, _prepare, _ptr, _require_cuda, _scores_dense_prepared, _stream,
+                     split_bf16x3, use_packed)
 
 REL_SINGLE, REL_JACCARD_F32, REL_JACCARD_F64, REL_ANY = 0, 1, 2, 3
 _CHUNK_BYTES = 8 << 30   # transient memory budget of the query chunks in flight
@@ -231,6 +232,9 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
     dev = q.device
     g3 = split_bf16x3(g, "gallery") if precision == "bf16x3" else None   # once; the query chunks are split on the fly
     step = int(rows_per_chunk) if rows_per_chunk else chunk_rows(ng, sklearn_ap, device=dev)
+    # exact mode: the gallery goes into the FFMA kernel's packed operand layout once for all query chunks
+    gp = PackedRows.build(g) if g3 is None and g.dtype == torch.float32 and use_packed(min(nq, step), ng, g.shape[1], dev) \
+        else None
     main = torch.cuda.current_stream(dev)
     nchunks = (nq + step - 1) // step
     side = torch.cuda.Stream(dev) if nchunks > 1 else main
@@ -247,7 +251,7 @@ def full_ranking_stats(queries: torch.Tensor, gallery: torch.Tensor, rel_mode: i
                                         metric, self_mode, query_offset + s, split_rows=True)
         else:
             sc = _scores_dense_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, metric, self_mode,
-                                        query_offset + s)
+                                        query_offset + s, g_packed=gp)
         rp = rank_of_positives(sc, rel_mode, q_rel[s:e], g_rel, largest_first=(metric != "l2"),
                                jaccard_threshold=jaccard_threshold, self_offset=query_offset + s, drop_self=drop_self,
                                q_group=None if q_group is None else q_group[s:e], g_group=g_group, ties=sklearn_ap)

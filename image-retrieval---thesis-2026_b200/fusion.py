@@ -72,7 +72,7 @@ def score_stats(queries: torch.Tensor, gallery: torch.Tensor, metric: str = "ip"
                 query_offset: int = 0) -> Dict[str, torch.Tensor]:
     """Row statistics of ``score(q, g)`` over the whole gallery: ``{"mean","std","min","max"}`` (float64, [Q]).
     ``std`` is the population standard deviation (``np.std``).  fp32 inputs, exact-fp32 scores."""
-    from .search import _METRICS, _SELF, row_sqnorm
+    from .search import _METRICS, _SELF, _packed_operands, row_sqnorm
 
     _require_cuda(queries, gallery)
     q, g = _as2d(queries.float().contiguous(), "queries"), _as2d(gallery.float().contiguous(), "gallery")
@@ -82,10 +82,14 @@ def score_stats(queries: torch.Tensor, gallery: torch.Tensor, metric: str = "ip"
         qsq, gsq = row_sqnorm(q), row_sqnorm(g)
     out = torch.empty((nq, 4), dtype=torch.float64, device=q.device)
     lib = L.load()
-    with torch.cuda.device(q.device):
+    d = q.shape[1]
+    dt = L.KNN_F32
+    if nq > 0 and ng > 0:
+        q, g, dt = _packed_operands(q, g, None)
+    with torch.cuda.device(out.device):
         nbytes = lib.knn_score_stats_workspace(nq, ng)
-        ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=q.device)
-        rc = lib.knn_score_stats(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, q.shape[1], L.KNN_F32, _METRICS[metric],
+        ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=out.device)
+        rc = lib.knn_score_stats(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, dt, _METRICS[metric],
                                  _SELF[self_mode], query_offset, _ptr(out), _ptr(ws), ws.numel(), _stream(q))
     L.check(rc, "knn_score_stats")
     n = float(ng - (1 if self_mode == "exclude" else 0))

@@ -137,6 +137,7 @@ class FlatIndex:
         self.rows: Optional[torch.Tensor] = None
         self.sqnorm: Optional[torch.Tensor] = None
         self._filter: Optional[ExactFilterRows] = None   # bf16 split of fp32 rows (tensor-core exact engine), lazy
+        self._packed: Optional["PackedRows"] = None      # fp32 rows in the FFMA kernel's packed operand layout, lazy
 
     @property
     def ntotal(self) -> int:
@@ -153,6 +154,7 @@ class FlatIndex:
         if sq is not None:
             self.sqnorm = sq if self.sqnorm is None else torch.cat([self.sqnorm, sq], 0)
         self._filter = None
+        self._packed = None
         return self
 
     def adopt(self, rows: torch.Tensor, sqnorm: Optional[torch.Tensor] = None) -> "FlatIndex":
@@ -164,6 +166,7 @@ class FlatIndex:
         self.rows = rows
         self.sqnorm = sqnorm if sqnorm is not None else (row_sqnorm(rows) if self.metric == "l2" else None)
         self._filter = None
+        self._packed = None
         return self
 
     def search(self, queries: torch.Tensor, k: int, *, exclude_self: bool = False, self_mode: Optional[str] = None,
@@ -198,8 +201,11 @@ class FlatIndex:
                 self._filter = ExactFilterRows.build(self.rows, self.sqnorm)
             return _search_exact_tensor(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
                                         self.index_base, self._filter, out=out)
+        if (self.precision == "fp32" and self._packed is None and int(k) <= L.MAX_FUSED_K
+                and use_packed(q.shape[0], self.ntotal, self.dim, self.device)):
+            self._packed = PackedRows.build(self.rows)
         return _search_prepared(q, qsq, self.rows, self.sqnorm, int(k), self.metric, mode, int(query_offset),
-                                self.index_base, out=out)
+                                self.index_base, out=out, g_packed=self._packed)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -274,6 +280,59 @@ def split_bf16x3(x: torch.Tensor, role: str) -> torch.Tensor:
     return out
 
 
+class PackedRows:
+    """fp32 rows in the KNN_F32_PACKED operand layout of the exact FFMA kernel (``knn_pack_f32``: 128-row tiles
+    ``[tile][dpad][128]``): pack a gallery once, search it with many query batches."""
+
+    def __init__(self, data: torch.Tensor, n: int, d: int):
+        self.data, self.n, self.d = data, n, d
+
+    @staticmethod
+    def build(rows: torch.Tensor) -> "PackedRows":
+        _require_cuda(rows)
+        rows = _as2d(rows, "rows")
+        if rows.dtype != torch.float32 or not rows.is_contiguous():
+            raise ValueError("PackedRows takes contiguous fp32 rows")
+        n, d = rows.shape
+        lib = L.load()
+        out = torch.empty((max(lib.knn_pack_f32_bytes(n, d) // 4, 4),), dtype=torch.float32, device=rows.device)
+        with torch.cuda.device(rows.device):
+            rc = lib.knn_pack_f32(_ptr(rows), n, d, _ptr(out), _stream(rows))
+        L.check(rc, "knn_pack_f32")
+        return PackedRows(out, n, d)
+
+
+_PACK_MIN_FLOP = 4.0e9     # below ~0.1 ms of FFMA work the two pack launches do not pay
+
+
+def use_packed(nq: int, ng: int, d: int, device=None) -> bool:
+    """Whether an exact-fp32 FFMA call packs its operands first (KNN_F32_PACK=0|1 forces it off / on): enough work to
+    pay for the pack launches, and the packed copy (the size of the rows) fits the device's free memory."""
+    forced = os.environ.get("KNN_F32_PACK", "")
+    if forced in ("0", "1"):
+        return forced == "1" and nq > 0 and ng > 0
+    if 2.0 * nq * ng * d < _PACK_MIN_FLOP:
+        return False
+    if device is not None and torch.cuda.is_available():
+        need = 4 * (ng + nq + 256) * ((d + 15) // 16 * 16) + (1 << 28)
+        if need > torch.cuda.get_device_properties(device).total_memory // 16:
+            free, _ = torch.cuda.mem_get_info(device)
+            if need >= 0.5 * free:
+                return False
+    return True
+
+
+def _packed_operands(q, g, g_packed):
+    """(q pointer tensor, g pointer tensor, dtype code) of an fp32 FFMA call."""
+    if g_packed is None and not use_packed(q.shape[0], g.shape[0], q.shape[1], q.device):
+        return q, g, L.KNN_F32
+    gp = g_packed if g_packed is not None else PackedRows.build(g)
+    if gp.n != g.shape[0] or gp.d != g.shape[1]:
+        raise ValueError("packed gallery does not match the gallery rows")
+    qp = PackedRows.build(q if q.is_contiguous() else q.contiguous())
+    return qp.data, gp.data, L.KNN_F32_PACKED
+
+
 class ExactFilterRows:
     """What the tensor-core exact engine keeps per gallery besides the fp32 rows: the bf16 split rows, the squared
     norms and their maximum (a device scalar; enters the error bound of the filter)."""
@@ -327,9 +386,11 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
     # queries whose candidate set could not be proven complete (ties / near-duplicates wider than the slack):
     # re-run their 128-row blocks through the FFMA engine (contiguous runs keep the self-row arithmetic)
     bad = torch.nonzero(flags).flatten()
-    for s, e in rerun_ranges(bad.tolist(), nq):
+    runs = rerun_ranges(bad.tolist(), nq)
+    gp = PackedRows.build(g) if len(runs) > 1 and use_packed(runs[0][1] - runs[0][0], ng, d, dev) else None
+    for s, e in runs:
         v, i = _search_prepared(q[s:e], None if qsq is None else qsq[s:e], g, gsq, k, metric, self_mode,
-                                query_offset + s, index_base)
+                                query_offset + s, index_base, g_packed=gp)
         out_val[s:e] = v
         out_idx[s:e] = i
     _search_exact_tensor.last_unverified = int(bad.numel())
@@ -351,8 +412,10 @@ def _out_buffers(out, nq, k, dev):
     return ov, oi
 
 
-def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base, split_rows=False, out=None):
-    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3: same scores, each part loaded once per tile)."""
+def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base, split_rows=False, out=None,
+                     g_packed: Optional["PackedRows"] = None):
+    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3: same scores, each part loaded once per tile).
+    g_packed: the fp32 gallery already in the packed operand layout (else packed here when the call is large enough)."""
     nq, d = q.shape
     ng = g.shape[0]
     if g.shape[1] != d or g.dtype != q.dtype:
@@ -367,9 +430,12 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     with torch.cuda.device(dev):
         if k <= L.MAX_FUSED_K:
             dt = L.KNN_BF16X3 if split_rows else _DT[q.dtype]
+            qd, gd = q, g
+            if dt == L.KNN_F32:
+                qd, gd, dt = _packed_operands(q, g, g_packed)
             nbytes = lib.knn_search_workspace(nq, ng, d, dt, k)
             ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
-            rc = lib.knn_search(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, dt, k, _METRICS[metric],
+            rc = lib.knn_search(_ptr(qd), _ptr(gd), _ptr(qsq), _ptr(gsq), nq, ng, d, dt, k, _METRICS[metric],
                                 _SELF[self_mode], query_offset, index_base, _ptr(out_val), _ptr(out_idx),
                                 _ptr(ws), ws.numel(), _stream(q))
             L.check(rc, "knn_search")
@@ -383,10 +449,12 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     out_idx.fill_(-1)
     qf = q if q.dtype == torch.float32 else normalize(q, eps_mode="cast", out_dtype=torch.float32)
     gf = g if g.dtype == torch.float32 else normalize(g, eps_mode="cast", out_dtype=torch.float32)
+    if g_packed is None and use_packed(min(nq, chunk), ng, d, dev):
+        g_packed = PackedRows.build(gf)
     for s in range(0, nq, chunk):
         e = min(nq, s + chunk)
         sc = _scores_dense_prepared(qf[s:e], None if qsq is None else qsq[s:e], gf, gsq, metric, self_mode,
-                                    query_offset - index_base + s)
+                                    query_offset - index_base + s, g_packed=g_packed)
         rk = rank_rows(sc, largest_first=largest)[:, :kk]
         out_idx[s:e, :kk] = rk + index_base
         out_val[s:e, :kk] = torch.gather(sc, 1, rk)
@@ -396,12 +464,16 @@ def _search_prepared(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_b
     return out_val, out_idx
 
 
-def _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, self_offset_local, split_rows=False):
-    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3); bf16 rows run the tcgen05 kernel, fp32 rows the exact one."""
+def _scores_dense_prepared(q, qsq, g, gsq, metric, self_mode, self_offset_local, split_rows=False,
+                           g_packed: Optional["PackedRows"] = None):
+    """split_rows: q / g are split_bf16x3 rows (KNN_BF16X3); bf16 rows run the tcgen05 kernel, fp32 rows the exact one
+    (g_packed: the gallery already in the packed operand layout)."""
     nq, d = q.shape
     ng = g.shape[0]
     out = torch.empty((nq, ng), dtype=torch.float32, device=q.device)
     dt = L.KNN_BF16X3 if split_rows else _DT[q.dtype]
+    if dt == L.KNN_F32 and nq > 0 and ng > 0:
+        q, g, dt = _packed_operands(q, g, g_packed)
     with torch.cuda.device(q.device):
         rc = L.load().knn_scores_dense(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, dt,
                                        _METRICS[metric], _SELF[self_mode], self_offset_local, _ptr(out), _stream(q))

@@ -46,6 +46,10 @@ extern "C" {
 #define KNN_BF16  1
 #define KNN_BF16X3 2  /* knn_search only: bf16 rows written by knn_split_bf16x3 (d = 3 * dpad); same result as KNN_BF16
                          over those rows, but the kernels may load each hi / lo part once for the three products */
+#define KNN_F32_PACKED 3  /* knn_search / knn_scores_dense / knn_score_stats: q and g are knn_pack_f32 output (fp32 rows
+                         transposed into 128-row tiles); d stays the ORIGINAL row width.  Same scores, same bits as
+                         KNN_F32 -- the FFMA kernel fills its operand ring with bulk copies instead of transposing every
+                         tile through registers (~1.3x the throughput); never takes the small-problem path */
 
 /* metrics: score ordering is always "best first" in the outputs */
 #define KNN_COSINE 0   /* inner product of (already normalised) rows, larger = better (test.py:1006, train.py:405) */
@@ -198,6 +202,12 @@ KNN_API int knn_lesion_rerank(const float* cand_val, const int64_t* cand_idx, in
  * follows a re-scoring (test.py:633). */
 KNN_API int knn_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest,
                   float* out_vals, int64_t* out_idx, void* stream);
+
+/* fp32 rows [n,d] row-major -> the KNN_F32_PACKED operand layout: 128-row tiles [ceil(n/128)][dpad][128] fp32 with
+ * dpad = d rounded up to 16, zeros beyond n and d (what `torch.mm(q, g.t())`, test.py:1006, would read as g.t() tile by
+ * tile).  out: knn_pack_f32_bytes(n, d) bytes, 16-byte aligned.  Pack a gallery once, search it with many batches. */
+KNN_API size_t knn_pack_f32_bytes(int64_t n, int d);
+KNN_API int knn_pack_f32(const float* x, int64_t n, int d, float* out, void* stream);
 
 /* Dense score block (callers that want the full `dists` matrix of test.py:1080 / fusion_eval/metrics.py:15, and the
  * per-chunk input of knn_rank_of_positives).  out [nq,ng] fp32, same score definition and self handling as knn_search
