@@ -62,6 +62,10 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
                     help="N > 1: candidate exchange -- merge kernel reading the peers' symmetric-memory buffers over "
                          "NVLink (falls back to the all-gather if symmetric memory is unavailable), or NCCL all-gather")
+    ap.add_argument("--pipeline", default="on", choices=["on", "off"],
+                    help="N > 1, peer exchange: run the exchange of step i (wait for the slowest shard + merge over NVLink) "
+                         "on a side stream under the local search of step i + 1 (ShardedFlatIndex.search_async); every "
+                         "step's result is still taken -- one step later -- inside the timed region")
     return ap.parse_args()
 
 
@@ -272,6 +276,16 @@ def parity_check(b200knn, dist, world, rank, dev, rows, start, count, d, k, q_sr
     return out
 
 
+class PendingNow:
+    """A result that is already complete in stream order (same interface as sharded.PendingSearch)."""
+
+    def __init__(self, vals, idx):
+        self.vals, self.idx = vals, idx
+
+    def result(self):
+        return self.vals, self.idx
+
+
 def _pad(res, k):
     import torch
 
@@ -307,7 +321,8 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         e = min(count, s + GEN_CHUNK)
         rows[s:e] = b200knn.normalize(_source_rows(gen, start, s, e, d, dev), out_dtype=store_dtype)
     index = b200knn.FlatIndex(d, "cosine", precision, normalize=True, index_base=start, device=dev).adopt(rows)
-    sharded = ShardedFlatIndex(index, exchange=exchange)
+    pipeline = bool(ctx.get("pipeline")) and world > 1 and exchange == "peer"
+    sharded = ShardedFlatIndex(index, exchange=exchange, pipeline=pipeline)
 
     # ---- queries: i.i.d. Gaussian rows (a flat score distribution is the worst case for the fused selection),
     # replicated on every rank -------------------------------------------------------------------------------
@@ -316,22 +331,42 @@ def run_workload(name, args, ctx, steps, warmup, primary):
     q_host = qsrc.cpu().pin_memory()                      # the user's host buffer (fp32)
     q_dev = b200knn.normalize(qsrc, out_dtype=store_dtype)
     index_prepared = b200knn.FlatIndex(d, "cosine", precision, normalize=False, index_base=start, device=dev).adopt(rows)
-    sharded_prepared = ShardedFlatIndex(index_prepared, exchange=exchange)
+    sharded_prepared = ShardedFlatIndex(index_prepared, exchange=exchange, pipeline=pipeline)
     out_val_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
     out_idx_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+
+    # Pipelined exchange (N > 1): a step enqueues its search and TAKES the result of the previous step (the consumer
+    # runs one step behind); `drain` takes the last one, inside the timed region.
+    pending = []
+
+    def take(p, to_host):
+        v, i = p.result()
+        if to_host:
+            out_val_host.copy_(v, non_blocking=True)
+            out_idx_host.copy_(i, non_blocking=True)
+        return v, i
 
     def step_resident():
         # queries already normalised / cast in HBM: the index over the same rows with normalize=False skips the
         # normalisation FlatIndex.search would otherwise repeat; N > 1 adds the candidate exchange + shard merge
-        return sharded_prepared.search(q_dev, k)
+        if not pipeline:
+            return sharded_prepared.search(q_dev, k)
+        pending.append((sharded_prepared.search_async(q_dev, k), False))
+        return take(*pending.pop(0)) if len(pending) > 1 else None
 
     def step_e2e():
         # public API on a HOST batch: this rank copies its 1/N slice, normalises + casts it, the prepared slices are
         # all-gathered over NVLink; then search, candidate exchange, shard merge, results back to the host
-        v, i = sharded.search_host(q_host, k)
-        out_val_host.copy_(v, non_blocking=True)
-        out_idx_host.copy_(i, non_blocking=True)
-        return v, i
+        if not pipeline:
+            return take(PendingNow(*sharded.search_host(q_host, k)), True)
+        pending.append((sharded.search_host_async(q_host, k), True))
+        return take(*pending.pop(0)) if len(pending) > 1 else None
+
+    def drain():
+        res = None
+        while pending:
+            res = take(*pending.pop(0))
+        return res
 
     def barrier():
         if world > 1:
@@ -345,6 +380,7 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         t0.record()
         for _ in range(n):
             fn()
+        drain()
         t1.record()
         barrier()
         ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
@@ -354,8 +390,10 @@ def run_workload(name, args, ctx, steps, warmup, primary):
 
     for _ in range(max(warmup, 3)):
         step_resident()
+    drain()
     for _ in range(2):
         step_e2e()
+    drain()
 
     # ---- timed region: device-resident, clocks sampled; the library records CUDA events around its kernels on the
     # launching stream during these very steps (no synchronisation), read back after the region has ended ----------
@@ -405,7 +443,9 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         "config": {
             "workload": f"{name}: {nq} queries x {ng} gallery x {d}-d {precision}, top-{k}, cosine",
             "gallery_rows_per_gpu": count, "sharding": f"rows/{world}",
-            "exchange": "none" if world == 1 else exchange, "l2_flush": "inputs larger than L2 "
+            "exchange": "none" if world == 1 else exchange,
+            "pipeline": ("exchange of step i on a side stream under the local search of step i+1; results taken one step "
+                         "later, the last one before the closing event") if pipeline else "off", "l2_flush": "inputs larger than L2 "
             f"({count * d * esize / 1e9:.1f} GB gallery shard streamed per step)",
         },
         "roofline": ({
@@ -461,7 +501,7 @@ def run_workload(name, args, ctx, steps, warmup, primary):
                             "exchange_wait_plus_merge_ms": [round(x, 3) for x in allr[:, 6].tolist()]}
     # ---- correctness of this very configuration (after the timed regions) ------------------------------------
     try:
-        result = step_resident()
+        result = sharded_prepared.search(q_dev, k)
         line["parity_check"] = parity_check(b200knn, dist, world, rank, dev, rows, start, count, d, k, qsrc, q_dev,
                                             result, exact)
     except Exception as exc:  # noqa: BLE001 - reported, never hidden
@@ -518,7 +558,7 @@ def main():
         if ok.item() == 0:
             exchange = "allgather"
     ctx = {"dist": dist, "world": world, "rank": rank, "local_rank": local_rank, "dev": dev, "lib": lib,
-           "exchange": exchange}
+           "exchange": exchange, "pipeline": args.pipeline == "on"}
 
     line = run_workload(args.workload, args, ctx, args.steps, args.warmup, primary=True)
     # the other two regimes the metric names, measured in the same driver-run process: HBM-bound small batch (c4) and

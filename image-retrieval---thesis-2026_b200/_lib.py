@@ -58,6 +58,8 @@ SIGNATURES = {
     "knn_merge_topk": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
     "knn_merge_topk_parts": (_i, [_p, _p, _i, _i64, _i, _i, _p, _p, _p]),
     "knn_merge_topk_parts_sync": (_i, [_p, _p, _i, _i64, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "knn_merge_topk_parts_wait": (_i, [_p, _p, _i, _i64, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "knn_peer_publish": (_i, [_p, _i, _i, _i, _p]),
     "knn_relevance_single": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p]),
     "knn_relevance_multilabel": (_i, [_p, _i64, _i, _p, _p, _i64, _d, _i, _p, _p, _p]),
     "knn_ranked_stats": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),

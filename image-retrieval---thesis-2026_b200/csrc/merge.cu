@@ -353,6 +353,26 @@ __global__ void peer_signal_kernel(PeerFlags pf, int parts, int rank, int epoch)
   }
 }
 
+// Pipelined exchange: ONE warp waits for the peers' flags on the side stream, the merge kernel is launched behind it.
+// (8192 merge CTAs spinning would hold every SM while a peer is late and keep the next local search out; one 32-thread
+// CTA costs nothing.)  Bounded: a peer that never publishes surfaces as a launch failure, not as a hung GPU.
+__global__ void peer_wait_kernel(const int32_t* __restrict__ my_flags, int parts, int epoch) {
+  if ((int)threadIdx.x < parts) {
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(my_flags + threadIdx.x) : "memory");
+      if (v < epoch) {
+        __nanosleep(256);
+        if (clock64() - t0 > 60000000000ll) {   // ~30 s
+          printf("b200knn: peer %d never published search %d\n", (int)threadIdx.x, epoch);
+          __trap();
+        }
+      }
+    } while (v < epoch);
+  }
+}
+
 __global__ void __launch_bounds__(256) merge_topk_kernel(MergeParts mp, int parts, int64_t nq, int k, int l2,
                                                         float* __restrict__ out_val,
                                                         int64_t* __restrict__ out_idx,
@@ -405,11 +425,15 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(MergeParts mp, int part
 
 static int launch_merge_parts(const MergeParts& mp, int parts, int64_t nq, int k, int metric, float* out_val,
                               int64_t* out_idx, cudaStream_t stream, const PeerFlags* pf = nullptr, int rank = 0,
-                              int epoch = 0) {
+                              int epoch = 0, bool publish = true) {
   const size_t smem = (size_t)parts * k * 16;
   KNN_REQUIRE(smem <= 200 * 1024, "knn_merge_topk: parts*k=%d too large (max %d)", parts * k, 200 * 1024 / 16);
-  if (pf != nullptr) {   // published even for an empty batch: the peers wait for it
+  if (pf != nullptr && publish) {   // published even for an empty batch: the peers wait for it
     peer_signal_kernel<<<1, 32, 0, stream>>>(*pf, parts, rank, epoch);
+    KNN_LAUNCHED();
+  }
+  if (pf != nullptr && !publish) {   // pipelined exchange: one warp waits, the merge CTAs find the flags set
+    peer_wait_kernel<<<1, 32, 0, stream>>>(pf->flags[rank], parts, epoch);
     KNN_LAUNCHED();
   }
   if (nq == 0) return KNN_OK;
@@ -682,6 +706,41 @@ extern "C" int knn_merge_topk_parts_sync(const float* const* val_parts_host, con
     pf.flags[p] = flags_host[p];
   }
   return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream, &pf, rank, epoch);
+}
+
+// The two halves of knn_merge_topk_parts_sync as separate calls, for a PIPELINED exchange: the publish runs on the search
+// stream right behind the local search, the wait + merge on a side stream, so the next local search does not wait for the
+// slowest shard (sharded.py).
+extern "C" int knn_peer_publish(int32_t* const* flags_host, int parts, int rank, int epoch, void* stream) {
+  KNN_REQUIRE(flags_host && parts >= 1 && parts <= kMaxMergeParts && parts <= 32 && rank >= 0 && rank < parts,
+              "knn_peer_publish: bad arguments parts=%d rank=%d", parts, rank);
+  PeerFlags pf;
+  for (int p = 0; p < parts; ++p) {
+    KNN_REQUIRE(flags_host[p], "knn_peer_publish: null flag array %d", p);
+    pf.flags[p] = flags_host[p];
+  }
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, parts, rank, epoch);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+extern "C" int knn_merge_topk_parts_wait(const float* const* val_parts_host, const int64_t* const* idx_parts_host,
+                                         int parts, int64_t nq, int k, int metric, int32_t* const* flags_host, int rank,
+                                         int epoch, float* out_val, int64_t* out_idx, void* stream) {
+  KNN_REQUIRE(val_parts_host && idx_parts_host && flags_host && (nq == 0 || (out_val && out_idx)),
+              "knn_merge_topk_parts_wait: null pointer");
+  KNN_REQUIRE(parts >= 1 && parts <= kMaxMergeParts && parts <= 32 && k >= 1 && nq >= 0 && rank >= 0 && rank < parts,
+              "knn_merge_topk_parts_wait: bad sizes parts=%d (max %d) rank=%d k=%d nq=%lld", parts, kMaxMergeParts, rank, k,
+              (long long)nq);
+  MergeParts mp;
+  PeerFlags pf;
+  for (int p = 0; p < parts; ++p) {
+    KNN_REQUIRE(val_parts_host[p] && idx_parts_host[p] && flags_host[p], "knn_merge_topk_parts_wait: null part %d", p);
+    mp.idx[p] = idx_parts_host[p];
+    mp.val[p] = val_parts_host[p];
+    pf.flags[p] = flags_host[p];
+  }
+  return launch_merge_parts(mp, parts, nq, k, metric, out_val, out_idx, (cudaStream_t)stream, &pf, rank, epoch, false);
 }
 
 static int64_t rank_npad(int64_t ng) {

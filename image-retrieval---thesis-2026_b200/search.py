@@ -665,11 +665,12 @@ def rank_rows(scores: torch.Tensor, largest_first: bool = True) -> torch.Tensor:
 
 
 def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device, flag_ptrs=None, rank: int = 0,
-                     epoch: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                     epoch: int = 0, publish: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """k-way merge of separately placed per-shard lists given as raw DEVICE addresses (``knn_merge_topk_parts``):
     slices of an all-gathered buffer, or the peers' symmetric-memory buffers (fused exchange + merge).  With
     ``flag_ptrs`` (every rank's flag array as mapped here) the synchronisation of the exchange runs inside
-    (``knn_merge_topk_parts_sync``): this rank publishes ``epoch``, the merge waits for every peer's."""
+    (``knn_merge_topk_parts_sync``): this rank publishes ``epoch``, the merge waits for every peer's;
+    ``publish=False`` only waits and merges (``knn_merge_topk_parts_wait``: the publish ran elsewhere)."""
     import ctypes
 
     parts = len(val_ptrs)
@@ -683,8 +684,8 @@ def merge_topk_parts(val_ptrs, idx_ptrs, nq: int, k: int, metric: str, device, f
             rc = L.load().knn_merge_topk_parts(vp, ip, parts, nq, k, _METRICS[metric], _ptr(out_val), _ptr(out_idx), stream)
         else:
             fp = (ctypes.c_void_p * parts)(*[int(p) for p in flag_ptrs])
-            rc = L.load().knn_merge_topk_parts_sync(vp, ip, parts, nq, k, _METRICS[metric], fp, int(rank), int(epoch),
-                                                    _ptr(out_val), _ptr(out_idx), stream)
+            fn = L.load().knn_merge_topk_parts_sync if publish else L.load().knn_merge_topk_parts_wait
+            rc = fn(vp, ip, parts, nq, k, _METRICS[metric], fp, int(rank), int(epoch), _ptr(out_val), _ptr(out_idx), stream)
     L.check(rc, "knn_merge_topk_parts")
     return out_val, out_idx
 

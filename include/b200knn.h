@@ -248,6 +248,16 @@ KNN_API int knn_merge_topk_parts(const float* const* val_parts_host, const int64
 KNN_API int knn_merge_topk_parts_sync(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
                               int64_t nq, int k, int metric, int32_t* const* flags_host, int rank, int epoch,
                               float* out_val, int64_t* out_idx, void* stream);
+/* The two halves of knn_merge_topk_parts_sync as separate calls, for a PIPELINED exchange (sharded.py,
+ * `ShardedFlatIndex(exchange="peer", pipeline=True)`): knn_peer_publish runs on the search stream right behind the local
+ * search; knn_merge_topk_parts_wait (wait for every peer's `epoch`, then merge over NVLink -- no publish) runs on a side
+ * stream, so the NEXT local search neither waits for the slowest shard nor for the merge.  Buffer reuse is then the
+ * caller's protocol: with the publish on the search stream and "search j starts behind this rank's own merge j-2", a
+ * candidate buffer may be rewritten FOUR searches later (proof in DESIGN section 6). */
+KNN_API int knn_peer_publish(int32_t* const* flags_host, int parts, int rank, int epoch, void* stream);
+KNN_API int knn_merge_topk_parts_wait(const float* const* val_parts_host, const int64_t* const* idx_parts_host, int parts,
+                              int64_t nq, int k, int metric, int32_t* const* flags_host, int rank, int epoch,
+                              float* out_val, int64_t* out_idx, void* stream);
 
 /* Single-label relevance of retrieved lists: rel[i,j] = (glab[idx[i,j]] == qlab[i]), 0 for idx < 0.
  * Building block of retrieval_accuracy (test.py:38-54), compute_metrics (test_ath.py:90-172),

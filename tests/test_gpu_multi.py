@@ -58,6 +58,36 @@ def _worker(rank, world, port, out_dir):
             prof = sh.profile_read()
             if len(prof) != 1 or min(prof[0]) < 0.0:
                 failures.append((precision, exchange, "profile", prof))
+    # pipelined peer exchange: searches enqueued back to back, the exchange of each on a side stream; alternating query
+    # batches (a stale or early-rewritten slot would return the other batch's answer) and a rank that lags by a random
+    # amount before every search (exercises the four-slot protocol)
+    os.environ.pop("KNN_EXACT_ENGINE", None)
+    g = b200knn.normalize(torch.randn((60_001, 128), generator=gen, device=dev))
+    qa = b200knn.normalize(torch.randn((300, 128), generator=gen, device=dev))
+    qb = b200knn.normalize(torch.randn((300, 128), generator=gen, device=dev))
+    want = [b200knn.search(x, g, 100, "cosine", precision="bf16") for x in (qa, qb)]
+    sh = ShardedFlatIndex.from_full(g, "cosine", "bf16", exchange="peer", pipeline=True)
+    import random
+    lag = random.Random(100 + rank)
+    pend = []
+    for step in range(24):
+        if lag.random() < 0.5:
+            torch.cuda._sleep(int(lag.random() * 3e6))      # up to ~1.5 ms of skew on this rank's search stream
+        pend.append((step & 1, sh.search_async(qa if step & 1 == 0 else qb, 100)))
+        if step % 5 == 4:                                     # take results late and in bursts
+            while pend:
+                which, p = pend.pop(0)
+                v, i = p.result()
+                if not (torch.equal(i, want[which][1]) and torch.equal(v, want[which][0])):
+                    failures.append(("pipelined", step, which, int((i != want[which][1]).sum())))
+    while pend:
+        which, p = pend.pop(0)
+        v, i = p.result()
+        if not (torch.equal(i, want[which][1]) and torch.equal(v, want[which][0])):
+            failures.append(("pipelined-tail", which, int((i != want[which][1]).sum())))
+    v, i = sh.search_host(qb.cpu().pin_memory(), 100)         # the synchronous entry points on a pipelined index
+    if not (torch.equal(i, want[1][1]) and torch.equal(v, want[1][0])):
+        failures.append(("pipelined", "search_host"))
     # full-ranking metrics with the QUERIES sharded over the ranks: same value as one process, on every rank
     os.environ.pop("KNN_EXACT_ENGINE", None)
     from oracle import synth
