@@ -433,7 +433,7 @@ def run_workload(name, args, ctx, steps, warmup, primary):
     # several query blocks -> CTA-pair kernel
     kernel_name = ("search_bf16_ts_kernel" if d <= 768 else "search_bf16_kernel") if nq <= 128 else "search_bf16_pair_kernel"
     if exact:
-        kernel_name = "search_bf16_pair_kernel<kSplit> (bf16x3 filter of the exact mode)" if nq > 128 else kernel_name
+        kernel_name = "search_bf16_pair_kernel<kSplit> (bf16 split filter of the exact mode)" if nq > 128 else kernel_name
 
     line = {
         "metric": "queries/sec @top-100", "value": value, "unit": "queries/s", "n_gpus": world,
@@ -475,13 +475,17 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         import importlib
 
         S = importlib.import_module("b200knn.search")
+        nprod = 2 if (S._two_product_filter(nq, count, "keep") and k * 2 + 16 <= 256) else 3
         line["roofline"]["note"] = (
-            "exact fp32 mode on the tensor cores: the dominant kernel is the bf16x3 split filter (3 MMAs per product, "
-            "csrc/search_tc2.cu kSplit); 'achieved' counts every product ONCE (SURVEY 8d), mma_TFLOPs is the bf16 "
-            "tensor work actually issued; the exact fp32 re-scoring + proof kernel runs after it; kernel_ms averages the "
-            "profiled knn_search calls of the timed steps (FFMA re-runs of unproven queries, if any, included)")
-        line["roofline"]["mma_TFLOPs"] = 3.0 * achieved
-        line["roofline"]["mma_frac_of_peak"] = 3.0 * achieved / peaks["tflops"]
+            f"exact fp32 mode on the tensor cores: the dominant kernel is the bf16 split filter ({nprod} MMAs per product, "
+            "csrc/search_tc2.cu kSplit; two products = q_hi.g_hi + q_lo.g_hi under the wide bound |q| max|g_lo|, queries "
+            "it cannot prove are re-run with three); 'achieved' counts every product ONCE (SURVEY 8d), mma_TFLOPs is the "
+            "bf16 tensor work actually issued; the exact fp32 re-scoring + proof kernel runs after it; kernel_ms averages "
+            "the profiled knn_search calls of the timed steps (re-runs of unproven queries, if any, included)")
+        line["roofline"]["mma_TFLOPs"] = nprod * achieved
+        line["roofline"]["mma_frac_of_peak"] = nprod * achieved / peaks["tflops"]
+        line["config"]["filter_products"] = nprod
+        line["config"]["two_product_queries_rerun_with_three"] = S._search_exact_tensor.last_two_product_rerun
         line["config"]["unverified_queries_rerun_on_ffma"] = S._search_exact_tensor.last_unverified
     if world > 1:  # per-rank view of the same timed region: which rank the max-over-ranks step time waits for
         n = max(len(xprof), 1)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KNN_LIB") or os.path.join(_HERE, "libb200knn.so")
 
 # constants mirrored from include/b200knn.h
-KNN_F32, KNN_BF16, KNN_BF16X3, KNN_F32_PACKED = 0, 1, 2, 3
+KNN_F32, KNN_BF16, KNN_BF16X3, KNN_F32_PACKED, KNN_BF16X2 = 0, 1, 2, 3, 4
 KNN_COSINE, KNN_IP, KNN_L2 = 0, 1, 2
 KNN_EPS_CLAMP, KNN_EPS_NONE, KNN_EPS_ADD, KNN_CAST_ONLY = 0, 1, 2, 3
 KNN_SELF_KEEP, KNN_SELF_EXCLUDE, KNN_SELF_MINUS1 = 0, 1, 2
@@ -33,6 +33,8 @@ SIGNATURES = {
     "knn_split_bf16x3": (_i, [_p, _i64, _i, _i, _p, _p]),
     "knn_max_sqnorm": (_i, [_p, _i64, _p, _p]),
     "knn_filter_error_bound": (_i, [_p, _i64, _p, _i, _i, _p, _p]),
+    "knn_filter_error_bound2": (_i, [_p, _i64, _p, _p, _i, _i, _p, _p]),
+    "knn_split_lo_max_sqnorm": (_i, [_p, _i64, _i, _p, _p]),
     "knn_rescore_exact": (_i, [_p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i64, _i64, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "knn_launch_count": (C.c_longlong, []),
     "knn_profile_enable": (_i, [_i]),

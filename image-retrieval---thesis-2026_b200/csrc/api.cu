@@ -301,7 +301,7 @@ static WsLayout ws_layout(const SearchGeom& g, int k) {
 
 extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, int k) {
   if (nq <= 0 || k < 1 || k > kMaxFusedK) return 0;
-  if (dtype == KNN_BF16X3) dtype = KNN_BF16;  // same geometry: the split rows are bf16 rows of 3 * dpad columns
+  if (dtype == KNN_BF16X3 || dtype == KNN_BF16X2) dtype = KNN_BF16;  // same geometry: bf16 rows of 3 * dpad columns
   const bool packed = dtype == KNN_F32_PACKED;  // same geometry as KNN_F32; never the small-problem path
   if (packed) dtype = KNN_F32;
   const SearchGeom g = make_geom(nq, ng < 0 ? 0 : ng, d, dtype, k);
@@ -333,7 +333,8 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
                           int64_t ng, int d, int dtype, int k, int metric, int self_mode, int64_t self_offset,
                           int64_t index_base, float* out_val, int64_t* out_idx, void* workspace,
                           size_t workspace_bytes, void* stream) {
-  const bool split3 = dtype == KNN_BF16X3;
+  const bool two = dtype == KNN_BF16X2;
+  const bool split3 = dtype == KNN_BF16X3 || two;
   if (split3) {
     KNN_REQUIRE(d % 24 == 0, "KNN_BF16X3 rows are 3 parts of a multiple of 8 columns, got d=%d", d);
     dtype = KNN_BF16;
@@ -379,7 +380,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
   p.metric = metric; p.self_mode = self_mode;
   p.self_offset = self_offset - index_base;
   p.split_len = geo.split_len; p.splits = geo.splits; p.qblocks = geo.qblocks; p.groups = geo.groups;
-  p.split3 = split3 ? 1 : 0;
+  p.split3 = split3 ? (two ? 2 : 1) : 0;
   p.f32_packed = packed ? 1 : 0;
   const WsLayout wl = ws_layout(geo, k);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);

@@ -5,8 +5,11 @@
 // ever returned, so the chain has to run for a handful of candidates per query only -- if a cheap, *bounded-error*
 // score can name those candidates.  The bf16 tcgen05 kernels provide exactly that through an error-free split:
 //
-//   x = hi + lo + e,   hi = bf16_rn(x),  lo = bf16_rn(x - hi)  (x - hi is exact in fp32),  |e| <= 2^-18 |x|
-//   q.g ~= qhi.ghi + qlo.ghi + qhi.glo     (dropped: qlo.glo, qe.g, q.ge  <=  3.02 * 2^-18 * |q||g|)
+//   x = hi + lo + e,   hi = bf16_rn(x),  lo = bf16_rn(x - hi)  (x - hi is exact in fp32)
+//   bf16 keeps 8 significant bits: |x - hi| <= 2^-8 |x|, and lo sits at least one binade lower: |e| <= 2^-17 |x|
+//   q.g ~= qhi.ghi + qlo.ghi + qhi.glo     (dropped: qlo.glo <= 2^-16, qe.g <= 2^-17, (qhi+qlo).ge <= 2^-17 (1 + 2^-7)
+//                                           -- together <= 8.04 * 2^-18 * |q||g|; round 1 used u = 2^-9 and got 3.02,
+//                                           which rows sitting just below the bf16 rounding midpoints exceed)
 //
 // and the three partial products are ONE inner product of the concatenated rows
 //   queries  [ hi | lo | hi ]      gallery  [ hi | hi | lo ]      (3 * dpad wide, dpad = d rounded up to 8)
@@ -156,6 +159,17 @@ __device__ __forceinline__ void emit_and_verify(uint64_t* keys, int npad, int nv
   }
 }
 
+// Pruning inside the candidate set (similarity metrics): the filter's values are sorted best first, and each of its k best
+// has an exact score >= f_k - eps (f_k = the k-th best filter value).  A candidate whose filter value lies below
+// f_k - 2 eps has an exact score < f_k - eps: at least k rows beat it strictly, it cannot be in the answer and need not
+// be re-scored.  With the narrow bound of the three-product filter this never fires; under the wide bound of the
+// two-product filter (kc = 2k + slack candidates) it removes ~45 % of the gathered rows.  Rounded down: prunes less.
+template <bool kL2>
+__device__ __forceinline__ float prune_threshold(const float* __restrict__ vals, int kc, int k, float eps) {
+  if (kL2 || k > kc) return -INFINITY;
+  return __fmaf_rd(-2.0f, eps, __ldg(vals + (k - 1)));
+}
+
 // Generic form: one CTA per query, thread t re-scores candidates t, t + 128, ... reading its rows straight from
 // global memory.  Any d, any kc <= 4096.  The exact chain (search_f32.cu's definition):
 //   dot = fmaf(q[0], g[0], +0) ... fmaf(q[d-1], g[d-1], dot)
@@ -180,12 +194,14 @@ rescore_exact_kernel(const float* __restrict__ q, const float* __restrict__ g, c
   int nvalid = 0;
   int off = 0;
   const float e_r = __ldg(eps + r);
+  const float thr = prune_threshold<kL2>(cand_val + r * kc, kc, k, e_r);
   for (int j = threadIdx.x; j < npad; j += blockDim.x) {
     uint64_t key = 0ull;
     if (j < kc) {
       const int64_t row = cand_idx[r * kc + j] - index_base;
       if (cand_idx[r * kc + j] >= 0 && row >= 0 && row < ng) {
         ++nvalid;
+        if (j >= k && __ldg(cand_val + r * kc + j) < thr) { keys[j] = 0ull; continue; }   // provably outside the top k
         const float* grow = g + row * (int64_t)d;
         float dot = 0.0f;
         for (int e = 0; e < d; ++e) dot = fmaf(qs[e], __ldg(grow + e), dot);
@@ -230,16 +246,22 @@ rescore_exact_stream_kernel(const float* __restrict__ q, const float* __restrict
     ptx::fence_barrier_init();
   }
   int64_t row = -1;
+  bool listed = false;                                                // a row of the gallery (counts for "set = gallery")
   if (c < kc) {
     const int64_t gi = cand_idx[r * kc + c];
-    if (gi >= 0 && gi - index_base >= 0 && gi - index_base < ng) row = gi - index_base;
+    if (gi >= 0 && gi - index_base >= 0 && gi - index_base < ng) {
+      listed = true;
+      // candidates that provably cannot reach the top k are not re-scored (see prune_threshold)
+      if (c < k || !(__ldg(cand_val + r * kc + c) < prune_threshold<kL2>(cand_val + r * kc, kc, k, __ldg(eps + r))))
+        row = gi - index_base;
+    }
   }
   const bool active = row >= 0;
   const float* grow = g + (active ? row : 0) * (int64_t)d;
   const float* qrow = q + r * (int64_t)d;
   for (int e = c * 4; e < d; e += npad * 4)
     *reinterpret_cast<float4*>(qs + e) = __ldg(reinterpret_cast<const float4*>(qrow + e));
-  const int nvalid = __syncthreads_count(active ? 1 : 0);            // also: barriers initialised, qs complete
+  const int nvalid = __syncthreads_count(listed ? 1 : 0);            // also: barriers initialised, qs complete
 
   const int nchunks = (d + cf - 1) / cf;
   const uint32_t bar0 = ptx::smem_u32(&bars[0]);
@@ -311,7 +333,7 @@ __global__ void __launch_bounds__(256) error_bound_kernel(const float* __restric
   const double steps = (double)(3 * dpad / 16 + 1);
   // split error + tensor-core accumulation + rounding of the exact fp32 chain + rounding of the fp32 squared norms the
   // bound itself is built from ((d/32 + 6) * 2^-24: the per-lane chains and the butterfly of normalize.cu)
-  const double u = 3.02 * 3.814697265625e-06 /*2^-18*/ + steps * 4.76837158203125e-07 /*2^-21*/ * 1.012 +
+  const double u = 8.04 * 3.814697265625e-06 /*2^-18*/ + steps * 4.76837158203125e-07 /*2^-21*/ * 1.012 +
                    (double)d * 5.9604644775390625e-08 /*2^-24*/ * 1.001 +
                    ((double)d / 32.0 + 6.0) * 5.9604644775390625e-08;
   const double qn2 = (double)__ldg(qsq + i), gn2 = (double)__ldg(gmax);
@@ -320,10 +342,73 @@ __global__ void __launch_bounds__(256) error_bound_kernel(const float* __restric
   eps[i] = __double2float_ru(e);
 }
 
+// Two-product filter (q_hi.g_hi + q_lo.g_hi): the dropped product is q.(g - g_hi), bounded by |q| * |g - g_hi|.  The lo
+// part of a gallery split row is bf16(g - g_hi): max over the rows of its squared norm (one warp per row, fp32).
+__global__ void __launch_bounds__(256) lo_max_sqnorm_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n, int dpad,
+                                                            uint32_t* out) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float acc = 0.0f;
+  if (r < n) {
+    const __nv_bfloat16* lo = rows + r * (int64_t)(3 * dpad) + 2 * dpad;   // gallery rows are [hi | hi | lo]
+    for (int c = lane; c < dpad; c += 32) {
+      const float v = __bfloat162float(lo[c]);
+      acc = fmaf(v, v, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  if (lane == 0 && acc > 0.0f) atomicMax(out, __float_as_uint(acc));
+}
+
+// eps of the two-product filter: |q| * (max|g_lo| + 2^-16 max|g|)  [dropped product: g - g_hi = g_lo + e, |e| <= 2^-17|g|;
+// residual of the query split: |q - q_hi - q_lo| <= 2^-17 |q|] + accumulation of 2 * dpad / 16 + 1 MMA steps + the chain
+// and norm roundings of error_bound_kernel.  max|g_lo|^2 is an fp32 sum: (1 + 1e-4) covers its rounding.
+__global__ void __launch_bounds__(256) error_bound2_kernel(const float* __restrict__ qsq, const float* __restrict__ gmax,
+                                                           const float* __restrict__ glomax, int64_t nq, int d, int l2,
+                                                           float* __restrict__ eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const int dpad = (d + 7) & ~7;
+  const double steps = (double)(2 * dpad / 16 + 1);
+  const double u = 4.04 * 3.814697265625e-06 /*2^-18*/ + steps * 4.76837158203125e-07 /*2^-21*/ * 1.012 +
+                   (double)d * 5.9604644775390625e-08 /*2^-24*/ * 1.001 +
+                   ((double)d / 32.0 + 6.0) * 5.9604644775390625e-08;
+  const double qn2 = (double)__ldg(qsq + i), gn2 = (double)__ldg(gmax), lo2 = (double)__ldg(glomax);
+  double e = (u * sqrt(qn2 * gn2) + sqrt(qn2 * lo2) * (1.0 + 1e-4)) * (1.0 + 1e-6) + 1e-30;
+  if (l2) e = 2.0 * e + 4.76837158203125e-07 * 1.01 * (qn2 + gn2);
+  eps[i] = __double2float_ru(e);
+}
+
 }  // namespace
 }  // namespace knn
 
 using namespace knn;
+
+extern "C" int knn_split_lo_max_sqnorm(const void* gallery_split_rows, int64_t n, int d, float* out, void* stream) {
+  KNN_REQUIRE(n >= 0 && d >= 1 && out, "knn_split_lo_max_sqnorm: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  KNN_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  if (n == 0) return KNN_OK;
+  KNN_REQUIRE(gallery_split_rows, "knn_split_lo_max_sqnorm: null pointer");
+  const int dpad = (d + 7) & ~7;
+  lo_max_sqnorm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gallery_split_rows), n, dpad, reinterpret_cast<uint32_t*>(out));
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
+
+extern "C" int knn_filter_error_bound2(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max,
+                                       const float* g_lo_sqnorm_max, int d, int metric, float* eps, void* stream) {
+  KNN_REQUIRE(nq >= 0 && d >= 1, "bad shape nq=%lld d=%d", (long long)nq, d);
+  KNN_REQUIRE(metric == KNN_COSINE || metric == KNN_IP || metric == KNN_L2, "bad metric %d", metric);
+  if (nq == 0) return KNN_OK;
+  KNN_REQUIRE(q_sqnorm && g_sqnorm_max && g_lo_sqnorm_max && eps, "null pointer");
+  error_bound2_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      q_sqnorm, g_sqnorm_max, g_lo_sqnorm_max, nq, d, metric == KNN_L2 ? 1 : 0, eps);
+  KNN_LAUNCHED();
+  return KNN_OK;
+}
 
 extern "C" int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* out, void* stream) {
   KNN_REQUIRE(n >= 0 && d >= 1, "bad shape n=%lld d=%d", (long long)n, d);

@@ -21,7 +21,8 @@ struct SearchParams {
   int splits;
   int groups;            // candidate lists per (split, row): 2 for the TMEM-resident kernel, else 1
   int qblocks;
-  int split3;            // rows are knn_split_bf16x3 output (3 parts of d/3 columns): q [hi|lo|hi], g [hi|hi|lo]
+  int split3;            // rows are knn_split_bf16x3 output (3 parts of d/3 columns): q [hi|lo|hi], g [hi|hi|lo];
+                         // 2 = the same rows, TWO products only (q_hi.g_hi + q_lo.g_hi: KNN_BF16X2)
   int f32_packed;        // fp32 rows are knn_pack_f32 output (128-row tiles [tile][dpad][128]); d is the original width
   uint64_t* lists;       // [splits * groups][qblocks][128][2*kp] candidate keys (unordered)
   int32_t* counts;       // [splits * groups][qblocks][128] keys in each list when its unit finished

@@ -55,6 +55,8 @@ struct PairCfg {
   int prefetch;          // L2 prefetch distance of the gallery stream in k-blocks (0 = off)
   int lockstep;          // soft lock-step window in tiles (0 = off), see SearchParams::progress
   int lock_ignore;       // peers further behind than this many tiles are late starters: not waited for
+  int two;               // split mode with TWO products (q_hi.g_hi + q_lo.g_hi): the gallery lo part is neither loaded nor
+                         // multiplied, a stage holds {G hi, Q hi, Q lo} (3 x 16 KB)
   unsigned long long* stats;  // diagnostics (KNN_PAIR_STATS=1): stall-cycle counters, see knn_debug_stats()
 };
 
@@ -173,7 +175,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (pf_t < ntiles) {
               ptx::tma_prefetch_2d(&tmap_g, pf_kb * (kSplit ? kSplit : BKE),
                                    (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
-              if (kSplit)
+              if (kSplit && !cfg.two)
                 ptx::tma_prefetch_2d(&tmap_g2, pf_kb * kSplit, (int32_t)(c_begin + (int64_t)pf_t * TN + (int64_t)rank * TNH));
             }
             if (++pf_kb == nkb) { pf_kb = 0; ++pf_t; }
@@ -186,10 +188,11 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           constexpr int kBk = kSplit ? kSplit : BKE;                 // elements per k-block
           constexpr uint32_t kKb = (uint32_t)(TM * kBk * 2);         // bytes of one 128-row k-block
           ptx::tma_load_2d_2sm_u32(dst, &tmap_g, full_bar, kb * kBk, col0, ptx::kEvictNormal);
-          if (kSplit) {  // stage = {G hi, G lo, Q hi, Q lo}
-            ptx::tma_load_2d_2sm_u32(dst + kKb, &tmap_g2, full_bar, kb * kBk, col0, ptx::kEvictNormal);
-            ptx::tma_load_2d_2sm_u32(dst + 2 * kKb, &tmap_q, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
-            ptx::tma_load_2d_2sm_u32(dst + 3 * kKb, &tmap_q2, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
+          if (kSplit) {  // stage = {G hi, G lo, Q hi, Q lo}; two products: {G hi, Q hi, Q lo}
+            const uint32_t qh = cfg.two ? kKb : 2 * kKb;
+            if (!cfg.two) ptx::tma_load_2d_2sm_u32(dst + kKb, &tmap_g2, full_bar, kb * kBk, col0, ptx::kEvictNormal);
+            ptx::tma_load_2d_2sm_u32(dst + qh, &tmap_q, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
+            ptx::tma_load_2d_2sm_u32(dst + qh + kKb, &tmap_q2, full_bar, kb * kBk, (int32_t)row0, ptx::kEvictLast);
           } else if (!cfg.resident)
             ptx::tma_load_2d_2sm_u32(dst + KB_BYTES, &tmap_q, full_bar, kb * BKE, (int32_t)row0, ptx::kEvictLast);
           if (leader) ptx::mbar_arrive_expect_tx_u32(full_bar, tx_bytes);
@@ -237,21 +240,23 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
               constexpr int kBk = kSplit ? kSplit : BKE;
               constexpr uint32_t kPart = (uint32_t)(TM * kBk * 2) >> 4;  // descriptor units between the parts of a stage
               auto desc = [](uint32_t lo) { return kSplit == 32 ? ptx::sw64_desc(lo) : ptx::sw128_desc(lo); };
+              const uint32_t qh = b_lo + (cfg.two ? kPart : 2 * kPart);   // query hi part; the lo part follows it
 #pragma unroll
               for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_hi . g_hi
                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 2 * kPart + ko), desc(b_lo + ko), idesc,
-                                     (k != 0 || kb != 0) ? 1u : 0u);
+                ptx::mma_bf16_ss_2sm(tmem_d, desc(qh + ko), desc(b_lo + ko), idesc, (k != 0 || kb != 0) ? 1u : 0u);
               }
 #pragma unroll
               for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_lo . g_hi
                 const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 3 * kPart + ko), desc(b_lo + ko), idesc, 1u);
+                ptx::mma_bf16_ss_2sm(tmem_d, desc(qh + kPart + ko), desc(b_lo + ko), idesc, 1u);
               }
+              if (!cfg.two) {
 #pragma unroll
-              for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_hi . g_lo
-                const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
-                ptx::mma_bf16_ss_2sm(tmem_d, desc(b_lo + 2 * kPart + ko), desc(b_lo + kPart + ko), idesc, 1u);
+                for (int k = 0; k < kBk / UMMA_K; ++k) {   // q_hi . g_lo
+                  const uint32_t ko = (uint32_t)(k * UMMA_K * 2 / 16);
+                  ptx::mma_bf16_ss_2sm(tmem_d, desc(qh + ko), desc(b_lo + kPart + ko), idesc, 1u);
+                }
               }
             } else {
               const uint32_t a_lo = cfg.resident ? a_res : b_lo + (KB_BYTES >> 4);
@@ -387,7 +392,8 @@ int launch_e(const SearchParams& p, cudaStream_t stream) {
   const size_t fixed = sizeof(float) * kAccStages * TN + sizeof(PairBarriers);
   cfg.resident = (!kSplit && (size_t)cfg.nkb * KB_BYTES + 4 * (size_t)KB_BYTES + fixed <= kSmemBudget) ? 1 : 0;
   cfg.a_bytes = cfg.resident ? (uint32_t)cfg.nkb * KB_BYTES : 0u;
-  cfg.stage_bytes = kSplit ? 4 * kKb : (cfg.resident ? KB_BYTES : 2 * KB_BYTES);
+  cfg.two = (kSplit && p.split3 == 2) ? 1 : 0;
+  cfg.stage_bytes = kSplit ? (cfg.two ? 3 : 4) * kKb : (cfg.resident ? KB_BYTES : 2 * KB_BYTES);
   int stages = (int)((kSmemBudget - fixed - cfg.a_bytes) / cfg.stage_bytes);
   cfg.stages = stages > kMaxStages ? kMaxStages : stages;
   cfg.debug = 0;

@@ -337,55 +337,120 @@ class ExactFilterRows:
     """What the tensor-core exact engine keeps per gallery besides the fp32 rows: the bf16 split rows, the squared
     norms and their maximum (a device scalar; enters the error bound of the filter)."""
 
-    def __init__(self, split: torch.Tensor, sqnorm: torch.Tensor, max_sqnorm: torch.Tensor):
+    def __init__(self, split: torch.Tensor, sqnorm: torch.Tensor, max_sqnorm: torch.Tensor,
+                 lo_max_sqnorm: Optional[torch.Tensor] = None):
         self.split, self.sqnorm, self.max_sqnorm = split, sqnorm, max_sqnorm
+        self.lo_max_sqnorm = lo_max_sqnorm     # max |g - bf16(g)|^2 over the rows: the bound of the two-product filter
 
     @staticmethod
     def build(rows: torch.Tensor, sqnorm: Optional[torch.Tensor]) -> "ExactFilterRows":
         sq = sqnorm if sqnorm is not None else row_sqnorm(rows)
         mx = torch.empty((1,), dtype=torch.float32, device=rows.device)
+        lo = torch.empty((1,), dtype=torch.float32, device=rows.device)
+        split = split_bf16x3(rows, "gallery")
         with torch.cuda.device(rows.device):
             rc = L.load().knn_max_sqnorm(_ptr(sq), sq.numel(), _ptr(mx), _stream(rows))
-        L.check(rc, "knn_max_sqnorm")
-        return ExactFilterRows(split_bf16x3(rows, "gallery"), sq, mx)
+            L.check(rc, "knn_max_sqnorm")
+            rc = L.load().knn_split_lo_max_sqnorm(_ptr(split), rows.shape[0], rows.shape[1], _ptr(lo), _stream(rows))
+            L.check(rc, "knn_split_lo_max_sqnorm")
+        return ExactFilterRows(split, sq, mx, lo)
 
 
-def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric: str) -> torch.Tensor:
+def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric: str,
+                       lo_max_gsq: Optional[torch.Tensor] = None) -> torch.Tensor:
     """eps[q] >= |filter value - exact-mode value| for every gallery row (fp32 [Q], rounded up): split error +
     tensor-core accumulation + the exact fp32 chain's own rounding, times |q| * max|g| (``knn_filter_error_bound``,
-    formula in include/b200knn.h)."""
+    formula in include/b200knn.h).  With ``lo_max_gsq`` (max squared norm of the gallery's lo parts): the bound of the
+    TWO-product filter, whose dropped product adds |q| * max|g_lo| (``knn_filter_error_bound2``)."""
     _require_cuda(qsq, max_gsq)
     eps = torch.empty_like(qsq)
     with torch.cuda.device(qsq.device):
-        rc = L.load().knn_filter_error_bound(_ptr(qsq), qsq.numel(), _ptr(max_gsq), int(d), _METRICS[metric],
-                                             _ptr(eps), _stream(qsq))
+        if lo_max_gsq is None:
+            rc = L.load().knn_filter_error_bound(_ptr(qsq), qsq.numel(), _ptr(max_gsq), int(d), _METRICS[metric],
+                                                 _ptr(eps), _stream(qsq))
+        else:
+            rc = L.load().knn_filter_error_bound2(_ptr(qsq), qsq.numel(), _ptr(max_gsq), _ptr(lo_max_gsq), int(d),
+                                                  _METRICS[metric], _ptr(eps), _stream(qsq))
     L.check(rc, "knn_filter_error_bound")
     return eps
 
 
+def _two_product_filter(nq: int, ng: int, self_mode: str) -> bool:
+    """Whether the tensor-core exact engine tries the two-product filter first (KNN_EXACT_PRODUCTS=2|3 forces it):
+    queries it cannot prove are GATHERED and re-run through the three-product filter, which needs self_mode "keep" (a
+    gathered batch has no ``query_offset + i`` self rows), and several 256-row query blocks to be worth a second pass."""
+    forced = os.environ.get("KNN_EXACT_PRODUCTS", "")
+    if self_mode != "keep" or forced == "3":
+        return False
+    return forced == "2" or nq >= 1024
+
+
 def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base,
-                         filt: Optional[ExactFilterRows] = None, out=None):
-    """precision="fp32" through the tensor cores; same contract and same bits as _search_prepared on fp32 rows."""
+                         filt: Optional[ExactFilterRows] = None, out=None, products: Optional[int] = None):
+    """precision="fp32" through the tensor cores; same contract and same bits as _search_prepared on fp32 rows.
+    products: 3 = the three-product split filter; 2 = the two-product filter first (2/3 of the tensor work, ~65 x the
+    error bound), its unproven queries gathered and re-run with three products; None = by :func:`_two_product_filter`."""
     nq, d = q.shape
     ng = g.shape[0]
     dev = q.device
     kc = _filter_k(k)
     if filt is None:
         filt = ExactFilterRows.build(g, gsq)
+    if products is None:
+        products = 2 if (_two_product_filter(nq, ng, self_mode) and filt.lo_max_sqnorm is not None) else 3
+    if products == 2:
+        # the wide bound needs a wider candidate set: with kc = 64 for k = 50 the proof failed for 41 % of the queries
+        # of BASELINE config 3 (the 14 ranks of slack span ~0.003 of score, the bound is ~0.002), with 128 for none;
+        # knn_rescore_exact prunes the candidates that provably cannot reach the top k, so the re-scoring grows by
+        # ~10 %, not 2 x
+        kc2 = 32
+        while kc2 < 2 * k + 16:
+            kc2 <<= 1
+        if kc2 > L.MAX_FUSED_K:
+            products = 3
+        else:
+            kc = kc2
     q_sq = qsq if qsq is not None else row_sqnorm(q)
-    eps = filter_error_bound(q_sq, filt.max_sqnorm, d, metric)
-    cand_val, cand_idx = _search_prepared(split_bf16x3(q, "queries"), qsq, filt.split, gsq if metric == "l2" else None,
-                                          kc, metric, self_mode, query_offset, index_base, split_rows=True)
+    eps = filter_error_bound(q_sq, filt.max_sqnorm, d, metric, filt.lo_max_sqnorm if products == 2 else None)
+    lib = L.load()
+    q3 = split_bf16x3(q, "queries")
+    if products == 2:
+        cand_val = torch.empty((nq, kc), dtype=torch.float32, device=dev)
+        cand_idx = torch.empty((nq, kc), dtype=torch.int64, device=dev)
+        d3 = q3.shape[1]
+        with torch.cuda.device(dev):
+            nbytes = lib.knn_search_workspace(nq, ng, d3, L.KNN_BF16X2, kc)
+            ws = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=dev)
+            rc = lib.knn_search(_ptr(q3), _ptr(filt.split), _ptr(qsq), _ptr(gsq if metric == "l2" else None), nq, ng, d3,
+                                L.KNN_BF16X2, kc, _METRICS[metric], _SELF[self_mode], query_offset, index_base,
+                                _ptr(cand_val), _ptr(cand_idx), _ptr(ws), ws.numel(), _stream(q))
+        L.check(rc, "knn_search")
+    else:
+        cand_val, cand_idx = _search_prepared(q3, qsq, filt.split, gsq if metric == "l2" else None,
+                                              kc, metric, self_mode, query_offset, index_base, split_rows=True)
     out_val, out_idx = _out_buffers(out, nq, k, dev)
     flags = torch.empty((nq,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = L.load().knn_rescore_exact(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _METRICS[metric],
-                                        _SELF[self_mode], query_offset, index_base, _ptr(cand_val), _ptr(cand_idx),
-                                        kc, k, _ptr(eps), _ptr(out_val), _ptr(out_idx), _ptr(flags), _stream(q))
+        rc = lib.knn_rescore_exact(_ptr(q), _ptr(g), _ptr(qsq), _ptr(gsq), nq, ng, d, _METRICS[metric],
+                                   _SELF[self_mode], query_offset, index_base, _ptr(cand_val), _ptr(cand_idx),
+                                   kc, k, _ptr(eps), _ptr(out_val), _ptr(out_idx), _ptr(flags), _stream(q))
     L.check(rc, "knn_rescore_exact")
+    bad = torch.nonzero(flags).flatten()
+    if products == 2:
+        # unproven under the wide bound: gather those queries and run them through the three-product filter (which
+        # falls back to the FFMA engine for what IT cannot prove)
+        _search_exact_tensor.last_two_product_rerun = int(bad.numel())
+        if bad.numel() > 0:
+            qb = q.index_select(0, bad)
+            v, i = _search_exact_tensor(qb, None if qsq is None else qsq.index_select(0, bad), g, gsq, k, metric,
+                                        self_mode, 0, index_base, filt=filt, products=3)
+            out_val.index_copy_(0, bad, v)
+            out_idx.index_copy_(0, bad, i)
+        else:
+            _search_exact_tensor.last_unverified = 0
+        return out_val, out_idx
     # queries whose candidate set could not be proven complete (ties / near-duplicates wider than the slack):
     # re-run their 128-row blocks through the FFMA engine (contiguous runs keep the self-row arithmetic)
-    bad = torch.nonzero(flags).flatten()
     runs = rerun_ranges(bad.tolist(), nq)
     gp = PackedRows.build(g) if len(runs) > 1 and use_packed(runs[0][1] - runs[0][0], ng, d, dev) else None
     for s, e in runs:
@@ -397,6 +462,7 @@ def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, ind
     return out_val, out_idx
 
 
+_search_exact_tensor.last_two_product_rerun = 0
 _search_exact_tensor.last_unverified = 0
 
 

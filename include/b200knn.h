@@ -46,6 +46,9 @@ extern "C" {
 #define KNN_BF16  1
 #define KNN_BF16X3 2  /* knn_search only: bf16 rows written by knn_split_bf16x3 (d = 3 * dpad); same result as KNN_BF16
                          over those rows, but the kernels may load each hi / lo part once for the three products */
+#define KNN_BF16X2 4  /* knn_search only: the SAME rows as KNN_BF16X3, but the CTA-pair kernel computes only the two products
+                         q_hi.g_hi + q_lo.g_hi (the gallery lo part is neither loaded nor multiplied: 2/3 of the work).
+                         The dropped product is bounded by |q| * max|g - g_hi|: knn_filter_error_bound2 */
 #define KNN_F32_PACKED 3  /* knn_search / knn_scores_dense / knn_score_stats: q and g are knn_pack_f32 output (fp32 rows
                          transposed into 128-row tiles); d stays the ORIGINAL row width.  Same scores, same bits as
                          KNN_F32 -- the FFMA kernel fills its operand ring with bulk copies instead of transposing every
@@ -105,7 +108,9 @@ KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, in
  * knn_split_bf16x3: error-free split of fp32 rows x [n,d] into bf16 parts hi = bf16(x), lo = bf16(x - hi), written
  *   as ONE row of 3*dpad bf16 (dpad = d rounded up to 8, zero padded): role 0 (queries) [hi|lo|hi], role 1 (gallery)
  *   [hi|hi|lo], so that knn_search(KNN_BF16) over the split rows computes qhi.ghi + qlo.ghi + qhi.glo, which differs
- *   from q.g by at most 3.02 * 2^-18 * |q||g| plus the accumulation error of the tensor cores.
+ *   from q.g by at most 8.04 * 2^-18 * |q||g| (bf16 keeps 8 significant bits: |x - hi| <= 2^-8 |x|,
+ *   |x - hi - lo| <= 2^-17 |x|; dropped: qlo.glo, (q - qhi - qlo).g, (qhi + qlo).(g - ghi - glo)) plus the accumulation
+ *   error of the tensor cores.
  * knn_rescore_exact: cand_val / cand_idx [nq,kc] = the filter's top-kc (kc > k, best first, global rows, -1 = empty).
  *   Every candidate is re-scored with the exact fp32 chain of the KNN_F32 path, the best k are written to
  *   out_val / out_idx exactly as knn_search(KNN_F32) would, and unverified[q] = 0 iff the result is PROVEN to be the
@@ -116,7 +121,7 @@ KNN_API size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype, in
 KNN_API int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* out, void* stream);
 /* The error bound knn_rescore_exact needs.  knn_max_sqnorm: out[0] = max of the gallery's squared row norms (device
  * scalar).  knn_filter_error_bound: eps[q] (rounded up) = u * |q| * max|g|  with
- *   u = 3.02 * 2^-18 (dropped terms of the split) + (3 * dpad / 16 + 1) * 2^-21 * 1.012 (tensor-core accumulation:
+ *   u = 8.04 * 2^-18 (dropped terms of the split) + (3 * dpad / 16 + 1) * 2^-21 * 1.012 (tensor-core accumulation:
  *   at most 2^-21 of the magnitude sum per K = 16 MMA step -- the one hardware assumption, checked against observed
  *   errors by tests/test_gpu_exact_tensor.py AND at run time: knn_rescore_exact flags a query whose candidates show
  *   |filter value - exact value| > eps / 2) + d * 2^-24 * 1.001 (rounding of the exact fp32 chain itself)
@@ -125,6 +130,15 @@ KNN_API int knn_split_bf16x3(const float* x, int64_t n, int d, int role, void* o
 KNN_API int knn_max_sqnorm(const float* sqnorm, int64_t n, float* out, void* stream);
 KNN_API int knn_filter_error_bound(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max, int d, int metric,
                            float* eps, void* stream);
+/* The bound of the TWO-product filter (KNN_BF16X2).  knn_split_lo_max_sqnorm: out[0] = max over the rows of a gallery
+ * split (role 1 of knn_split_bf16x3, n rows of 3 * dpad bf16) of the squared norm of the lo part.
+ * knn_filter_error_bound2: eps[q] = |q| * (1.0001 * max|g_lo| + u2 * max|g|), u2 = 4.04 * 2^-18 (g - g_hi - g_lo and
+ * q - q_hi - q_lo) + (2 * dpad / 16 + 1) * 2^-21 * 1.012 + the chain / norm roundings of knn_filter_error_bound;
+ * ~10 x the three-product bound at d = 1024 on typical rows (|g_lo| ~ 0.38 * 2^-8 |g|): the caller re-runs the queries it cannot
+ * prove through the three-product filter (search._search_exact_tensor). */
+KNN_API int knn_split_lo_max_sqnorm(const void* gallery_split_rows, int64_t n, int d, float* out, void* stream);
+KNN_API int knn_filter_error_bound2(const float* q_sqnorm, int64_t nq, const float* g_sqnorm_max,
+                            const float* g_lo_sqnorm_max, int d, int metric, float* eps, void* stream);
 KNN_API int knn_rescore_exact(const float* q, const float* g, const float* q_sqnorm, const float* g_sqnorm,
                       int64_t nq, int64_t ng, int d, int metric, int self_mode, int64_t self_offset,
                       int64_t index_base, const float* cand_val, const int64_t* cand_idx, int kc, int k,

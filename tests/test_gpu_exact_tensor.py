@@ -221,3 +221,78 @@ def test_all_positive_rows_stress_the_accumulation_bound(knn, tensor_engine, d):
     err = np.abs(host(fv).astype(np.float64) - exact).max(axis=1)
     print(f"\nd={d}: max |filter - exact| / eps = {(err / eps).max():.3f}")
     assert (err <= eps).all()
+
+
+# ------------------------------------------------------------------------------------------ two-product filter
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+def test_two_product_filter_is_bit_identical_and_reruns_what_it_cannot_prove(knn, monkeypatch, metric):
+    """KNN_BF16X2 (q_hi.g_hi + q_lo.g_hi, bound |q| max|g_lo|): same bits as the three-product filter and the FFMA
+    engine.  Gaussian rows verify almost everywhere; rows with tight clusters (score gaps below the wide bound) must
+    come back through the gathered three-product re-run."""
+    S = importlib.import_module("b200knn.search")
+
+    monkeypatch.setenv("KNN_EXACT_ENGINE", "tensor")
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    g = knn.normalize(torch.randn((50_000, 256), generator=gen, device="cuda"))
+    q = knn.normalize(torch.randn((2100, 256), generator=gen, device="cuda"))
+    # 300 queries sit inside tight clusters of 200 gallery rows (more than the kc = 128 candidates of k = 50): the proof
+    # cannot separate the cluster's members under the wide bound
+    centre = g[:12].repeat_interleave(200, 0)
+    g[10_000:12_400] = knn.normalize(centre + 2e-3 * torch.randn(centre.shape, generator=gen, device="cuda"))
+    q[500:800] = knn.normalize(g[10_000:10_300] + 1e-3 * torch.randn((300, 256), generator=gen, device="cuda"))
+    res = {}
+    for products in ("2", "3", "ffma"):
+        if products == "ffma":
+            monkeypatch.setenv("KNN_EXACT_ENGINE", "ffma")
+        else:
+            monkeypatch.setenv("KNN_EXACT_PRODUCTS", products)
+        S._search_exact_tensor.last_two_product_rerun = -1
+        res[products] = knn.search(q, g, 50, metric, precision="fp32")
+        if products == "2":
+            rerun = S._search_exact_tensor.last_two_product_rerun
+            assert 100 <= rerun < 1500, rerun          # the clustered queries, not everything
+        if products == "3":
+            assert S._search_exact_tensor.last_two_product_rerun == -1
+    for products in ("2", "3"):
+        assert torch.equal(res[products][1], res["ffma"][1]) and torch.equal(res[products][0], res["ffma"][0])
+    ov, oi = oracle.search(host(q[490:510]), host(g), 50, metric, "keep", 0)
+    assert np.array_equal(host(res["2"][1][490:510]), oi) and np.array_equal(host(res["2"][0][490:510]), ov)
+
+
+def test_two_product_bound_holds_and_is_about_the_lo_norm(knn):
+    """|two-product filter value - exact value| must stay below the bound knn_filter_error_bound2 on Gaussian, all-positive
+    and wide-dynamic-range rows; the bound is dominated by |q| max|g_lo| (a row's |g_lo| is 0.3 - 0.6 of 2^-8 |g|)."""
+    S = importlib.import_module("b200knn.search")
+    L = importlib.import_module("b200knn._lib")
+
+    rs = np.random.RandomState(5)
+    for d, kind in ((1024, "gauss"), (1024, "positive"), (96, "range"), (2048, "positive")):
+        g = rs.standard_normal((20000, d)).astype(np.float32)
+        q = rs.standard_normal((1024, d)).astype(np.float32)
+        if kind == "positive":
+            g, q = np.abs(g), np.abs(q)
+        if kind == "range":
+            g *= np.exp(rs.uniform(-4, 4, g.shape)).astype(np.float32)
+        gd, qd = dev(g), dev(q)
+        filt = S.ExactFilterRows.build(gd, None)
+        q3 = S.split_bf16x3(qd, "queries")
+        kc = 64
+        lib = L.load()
+        av = torch.empty((1024, kc), dtype=torch.float32, device="cuda")
+        ai = torch.empty((1024, kc), dtype=torch.int64, device="cuda")
+        nbytes = lib.knn_search_workspace(1024, 20000, q3.shape[1], L.KNN_BF16X2, kc)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+        rc = lib.knn_search(q3.data_ptr(), filt.split.data_ptr(), None, None, 1024, 20000, q3.shape[1], L.KNN_BF16X2, kc,
+                            1, 0, 0, 0, av.data_ptr(), ai.data_ptr(), ws.data_ptr(), ws.numel(),
+                            torch.cuda.current_stream().cuda_stream)
+        L.check(rc, "knn_search")
+        exact = knn.scores_dense(qd, gd, "ip")
+        ev = torch.gather(exact, 1, ai)
+        eps2 = S.filter_error_bound(S.row_sqnorm(qd), filt.max_sqnorm, d, "ip", filt.lo_max_sqnorm)
+        eps3 = S.filter_error_bound(S.row_sqnorm(qd), filt.max_sqnorm, d, "ip")
+        ratio = ((av - ev).abs() / eps2[:, None]).max().item()
+        assert ratio < 0.5, (d, kind, ratio)
+        if kind == "gauss":   # the dropped product is really there: outside the three-product bound somewhere
+            assert ((av - ev).abs() > eps3[:, None]).any(), (d, kind)
+        lo = float(filt.lo_max_sqnorm.item()) ** 0.5 / float(filt.max_sqnorm.item()) ** 0.5
+        assert 2.0 ** -10 < lo < 2.0 ** -8, lo

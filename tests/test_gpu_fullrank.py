@@ -268,7 +268,7 @@ def test_nih_scale_full_ranking_map_without_an_n_by_n_matrix(knn):
 @pytest.mark.parametrize("metric", ["cosine", "l2"])
 def test_tensor_core_dense_scores(knn, metric):
     """knn_scores_dense on the tcgen05 kernel: bf16 rows = fp32 accumulation of the bf16-rounded inputs; bf16x3 = the
-    error-free split, |error| <= the filter bound of the exact engine (3.02 * 2^-18 + accumulation) |q||g|."""
+    error-free split, |error| <= the filter bound of the exact engine (8.04 * 2^-18 + accumulation) |q||g|."""
     rs = np.random.RandomState(5)
     nq, ng, d = 300, 5000, 200                                  # odd block count, ragged tile, d not a multiple of 64
     q = oracle.normalize(rs.standard_normal((nq, d)).astype(np.float32))
