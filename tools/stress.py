@@ -39,7 +39,7 @@ def main():
     while time.time() - t0 < args.seconds:
         precision = rs.choice(["bf16", "bf16", "fp32", "fp32-tensor"])
         metric = rs.choice(["cosine", "l2", "ip"])
-        nq = rs.choice([1, 7, 64, 128, 129, 300, 1000, 2500])
+        nq = rs.choice([1, 7, 64, 128, 129, 300, 1000, 1500, 2500])
         ng = rs.choice([500, 5000, 40_000, 200_000, 700_001])
         d = rs.choice([8, 36, 64, 100, 256, 512, 768, 1024])
         k = rs.choice([1, 10, 31, 32, 33, 50, 64, 100, 128, 200, 256])
