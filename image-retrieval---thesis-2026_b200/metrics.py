@@ -26,6 +26,21 @@ _NAN = float("nan")
 # --------------------------------------------------------------------------------------------------
 # thin wrappers over the C ABI
 # --------------------------------------------------------------------------------------------------
+_CUTOFFS: Dict[Tuple[Tuple[int, ...], str], torch.Tensor] = {}
+
+
+def _cutoffs_dev(cutoffs: Iterable[int], device) -> torch.Tensor:
+    """int32 device tensor of cut-offs, cached per (values, device): the same few tuples ((1, 5, 10), 1..20) come back on
+    every metric call and a pageable host->device copy costs more than the small-problem kernels themselves."""
+    key = (tuple(int(c) for c in cutoffs), str(device))
+    t = _CUTOFFS.get(key)
+    if t is None:
+        if len(_CUTOFFS) > 256:
+            _CUTOFFS.clear()
+        t = _CUTOFFS[key] = torch.as_tensor(list(key[0]), dtype=torch.int32, device=device)
+    return t
+
+
 def _dev_i64(x, device) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.int64).contiguous()
@@ -106,7 +121,7 @@ def ranked_stats_multi(rel: torch.Tensor, cutoffs: Sequence[int], want: Sequence
     for c0 in range(0, len(cuts), 16):
         part = cuts[c0:c0 + 16]
         nk = len(part)
-        kks = torch.as_tensor(part, dtype=torch.int32, device=dev)
+        kks = _cutoffs_dev(part, dev)
         bufs = {"hits": torch.empty((nq, nk), dtype=torch.int32, device=dev) if "hits" in want else None,
                 "first": torch.empty((nq,), dtype=torch.int32, device=dev) if "first" in want else None,
                 "ap": torch.empty((nq, nk), dtype=torch.float64, device=dev) if "ap" in want else None,
@@ -134,7 +149,7 @@ def majority_vote_multi(retrieved_labels: torch.Tensor, cutoffs: Sequence[int], 
     _require_cuda(retrieved_labels)
     lab = retrieved_labels.contiguous().long()
     nq, k = lab.shape
-    kks = torch.as_tensor([int(c) for c in cutoffs], dtype=torch.int32, device=lab.device)
+    kks = _cutoffs_dev(cutoffs, lab.device)
     vote = torch.empty((nq, len(cutoffs)), dtype=torch.int64, device=lab.device)
     with torch.cuda.device(lab.device):
         rc = L.load().knn_majority_vote_multi(_ptr(lab), nq, k, _ptr(kks), len(cutoffs), 0 if tie == "first" else 1,
@@ -189,7 +204,7 @@ def recall_at_k_from_topk(indices: torch.Tensor, qlabels, glabels, topk: Sequenc
     nq, k = idx.shape
     dev = idx.device
     ql, gl = _dev_i64(qlabels, dev).view(-1), _dev_i64(glabels, dev).view(-1)
-    kks = torch.as_tensor([int(t) for t in topk], dtype=torch.int32, device=dev)
+    kks = _cutoffs_dev(topk, dev)
     counts = torch.empty((len(topk),), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         rc = L.load().knn_recall_counts(_ptr(idx), nq, k, _ptr(ql), _ptr(gl), gl.numel(), _ptr(kks), len(topk),
@@ -235,7 +250,7 @@ def map_full(ranks_rowmajor: torch.Tensor, qlabels, glabels, kappas: Sequence[in
     nq, ng = rk.shape
     dev = rk.device
     ql, gl = _dev_i64(qlabels, dev).view(-1), _dev_i64(glabels, dev).view(-1)
-    kap = torch.as_tensor(list(kappas), dtype=torch.int32, device=dev)
+    kap = _cutoffs_dev(kappas, dev)
     ap = torch.empty((nq,), dtype=torch.float64, device=dev)
     prs = torch.empty((nq, max(len(kappas), 1)), dtype=torch.float64, device=dev)
     npos = torch.empty((nq,), dtype=torch.int32, device=dev)
