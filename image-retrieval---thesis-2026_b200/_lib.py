@@ -42,6 +42,7 @@ SIGNATURES = {
     "knn_profile_read": (_i, [_i, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "knn_profile_last": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "knn_debug_stats": (_i, [C.POINTER(C.c_ulonglong), _i]),
+    "knn_search_geometry": (_i, [_i64, _i64, _i, _i, _i, C.POINTER(C.c_int64)]),
     "knn_pack_bits": (_i, [_p, _i64, _i, _i, _p, _p]),
     "knn_unpack_bits_pm1": (_i, [_p, _i64, _i, _p, _p]),
     "knn_hamming_from_scores": (_i, [_p, _i64, _i, _p, _p]),

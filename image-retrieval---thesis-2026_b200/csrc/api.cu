@@ -61,7 +61,7 @@ static bool use_ts(int dtype, int d, int qblocks) {
 // so the number of splits is chosen to make qblocks * splits fill WHOLE waves of the machine: between one wave
 // and ~4 waves' worth of splits, the count with the best (work / waves) efficiency wins (8192 queries on 148 SMs:
 // 37 splits = 16 full waves instead of 10 splits = 4.32 waves).
-static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots);
+static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots, bool pair, bool ts);
 
 static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   SearchGeom g;
@@ -119,7 +119,7 @@ static SearchGeom make_geom(int64_t nq, int64_t ng, int d, int dtype, int k) {
   const int64_t tiles_per_split = ntiles > 0 ? (ntiles + best - 1) / best : 1;
   g.split_len = tiles_per_split * tile;
   g.splits = ntiles > 0 ? (int)((ntiles + tiles_per_split - 1) / tiles_per_split) : 0;
-  seed_geometry(g, ng, tile, slots);
+  seed_geometry(g, ng, tile, slots, dtype == KNN_BF16 && !ts && g.qblocks > 1, ts);
   return g;
 }
 
@@ -215,14 +215,20 @@ unsigned long long* debug_stats_buffer() {
 //   * spread over ~2 waves of CTAs (a single query block gets 2 * #SM units), but never fewer than kSeedUnitMin rows
 //     per unit: a unit that short fills its candidate lists without a single compaction.  With one query block the
 //     sample therefore grows to 2 * #SM * 224 = 66 k rows -- searched in parallel it costs about one tile time.
+constexpr int64_t kTwoPhaseMaxRowsSeed = 1024;   // = kTwoPhaseMaxRows: small batches keep seeding from list maxima
 constexpr int64_t kSeedUnitMin = 224;  // = list capacity (256 for k <= 128) - one 32-column chunk
-static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
+static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots, bool pair, bool ts) {
   static const int64_t forced = [] {
     const char* e = getenv("KNN_SEED_ROWS");
     return e ? (int64_t)atoll(e) : (int64_t)-1;
   }();
+  static const int maxima_mode = [] {
+    const char* e = getenv("KNN_SEED_MAXIMA");   // 0: the pair kernel's pre-pass selects like the main pass (round-1 form)
+    return e ? atoi(e) : 1;
+  }();
   g.seed_splits = 0;
   g.seed_len = 0;
+  g.seed_stride = 0;
   // the sample's threshold is shared by every list of a row: it pays for itself only when there are many of them
   // (8192 x 50M: 74 lists per row; 25000 x 112k: 6 -- there the pre-pass cost half as much as the main pass)
   if (forced < 0 && g.splits * g.groups < 8) return;
@@ -233,6 +239,44 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
     while (rows * 2 <= 65536 && (double)(rows * 2) <= budget) rows *= 2;
   }
   if (rows <= 0) return;
+  // MAXIMA mode (CTA-pair kernel, large query batches; select.cuh: seed_tile_tmem): the pre-pass appends the best score
+  // of every `stride` chunks per selection thread and the seeding merge takes the k-th largest of those maxima.  Nothing
+  // is selected, so a unit has no warm-up and the pre-pass costs its MMA time: the unit count is free to fit the
+  // machine -- the (units, tiles per unit) pair with the fewest waves x (tiles + fixed cost of a wave) wins
+  // (8192 queries: 2 units of 128 tiles = one wave at 86 %, where 3 units of 86 tiles ran a second wave for 44 CTAs).
+  if (pair && maxima_mode && (int64_t)g.qblocks * kRowsPerUnit > kTwoPhaseMaxRowsSeed) {
+    // Sample size: the pre-pass now costs rows / ng of the main pass and a tighter starting threshold saves the main pass
+    // more than that up to ~1 % of the gallery (8192 x 6.25 M, 16 k / 32 k / 64 k rows: main pass 35.4 / 35.0 / 34.6 ms,
+    // pre-pass 0.32 / 0.34 / 0.56 ms): 1 % of the gallery up to 65536 rows, and at least 128 * kp rows (4 * kp chunks --
+    // with fewer groups than ~2k the k-th largest maximum is a loose bound) where 2 % of the gallery allows it.
+    int64_t mrows = rows;
+    if (forced < 0) {
+      mrows = ng / 100 < 65536 ? ng / 100 : 65536;
+      if (mrows < 128 * (int64_t)g.kp) mrows = 128 * (int64_t)g.kp;
+    }
+    if (mrows > ng / 50) mrows = ng / 50 / tile * tile;
+    const int64_t stiles = (mrows + tile - 1) / tile;
+    int64_t best_u = 0, best_t = 0;
+    double best_cost = 0.0;
+    for (int64_t u = 1; u <= 64 && u <= stiles; ++u) {
+      const int64_t t = (stiles + u - 1) / u;
+      if (u * t * tile > ng / 50) continue;   // the sample stays a small prefix of the gallery (see below)
+      const int64_t waves = (u * g.qblocks + slots - 1) / slots;
+      const double cost = (double)waves * (double)(t + 6);
+      if (best_u == 0 || cost < best_cost - 1e-9) { best_u = u; best_t = t; best_cost = cost; }
+    }
+    if (best_u > 0) {
+      const int64_t per_thread = best_t * (tile / 32) / g.groups;   // chunks a selection thread sees in a unit
+      const int64_t stride = (per_thread + g.L - 1) / g.L;          // ceil(per_thread / stride) <= L keys per list
+      const int64_t maxima = best_u * g.groups * ((per_thread + stride - 1) / stride);
+      if (maxima >= 2 * (int64_t)g.kp) {   // enough groups for the k-th largest maximum to be a useful bound
+        g.seed_splits = (int)best_u;
+        g.seed_len = best_t * tile;
+        g.seed_stride = (int)stride;
+        return;
+      }
+    }
+  }
   static const int64_t forced_units = [] {
     const char* e = getenv("KNN_SEED_UNITS");   // experiment knob
     return e ? (int64_t)atoll(e) : (int64_t)0;
@@ -245,10 +289,22 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots) {
   (void)tile;
   // the sample stays a small prefix of the gallery: at most 2 % of it (the minimum useful sample, 4096 rows, is
   // not worth scanning twice in a gallery of 100 k rows)
+  // (maxima mode below has no list to fill: a small gallery shard keeps its unit count with shorter units instead --
+  // 64 x 1.25 M, the 8-GPU shard of config 4: 296 units of 64 rows rather than 111 of 224)
+  const bool ts_maxima = ts && maxima_mode && (int64_t)g.qblocks * kRowsPerUnit <= kTwoPhaseMaxRowsSeed;
+  if (ts_maxima && units * len > ng / 50) {
+    const int64_t fit = ng / 50 / units / 64 * 64;   // whole chunks for both selection threads of a row
+    if (fit >= 64) len = fit;
+  }
   while (units > 1 && units * len > ng / 50) --units;
   if (units * len > ng / 50) return;
   g.seed_splits = (int)units;
   g.seed_len = len;
+  // Small batches on the TMEM-resident kernel seed from the LIST MAXIMA (ws_layout: seed_maxima; >= 2k lists per row):
+  // only the best score of every (unit, selection thread) is ever read, so the unit keeps just that -- one running
+  // maximum per thread, one key per list, no appends (seed_stride = "the whole unit").
+  if (ts_maxima && units * g.groups >= 2 * (int64_t)g.kp && units * g.groups <= 4096)
+    g.seed_stride = 1 << 30;
 }
 
 }  // namespace knn
@@ -309,6 +365,18 @@ extern "C" size_t knn_search_workspace(int64_t nq, int64_t ng, int d, int dtype,
   if (!packed && small_problem(nq, ng, dtype) && (size_t)nq * (size_t)ng * sizeof(float) > need)
     need = (size_t)nq * (size_t)ng * sizeof(float);   // the dense score block of the small path
   return need;
+}
+
+extern "C" int knn_search_geometry(int64_t nq, int64_t ng, int d, int dtype, int k, int64_t* out8) {
+  KNN_REQUIRE(out8 != nullptr && nq > 0 && ng >= 0 && d >= 1 && k >= 1 && k <= kMaxFusedK,
+              "knn_search_geometry: bad arguments nq=%lld ng=%lld d=%d k=%d", (long long)nq, (long long)ng, d, k);
+  if (dtype == KNN_BF16X3 || dtype == KNN_BF16X2) dtype = KNN_BF16;
+  if (dtype == KNN_F32_PACKED) dtype = KNN_F32;
+  KNN_REQUIRE(dtype == KNN_F32 || dtype == KNN_BF16, "knn_search_geometry: bad dtype %d", dtype);
+  const SearchGeom g = make_geom(nq, ng, d, dtype, k);
+  out8[0] = g.qblocks; out8[1] = g.splits; out8[2] = g.groups; out8[3] = g.split_len; out8[4] = g.L;
+  out8[5] = g.seed_splits; out8[6] = g.seed_len; out8[7] = g.seed_stride;
+  return KNN_OK;
 }
 
 static int check_common(const void* q, const void* g, const float* qs, const float* gs, int64_t nq, int64_t ng,
@@ -423,6 +491,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
       ps.ng = (int64_t)geo.seed_splits * geo.seed_len;
       ps.splits = geo.seed_splits;
       ps.split_len = geo.seed_len;
+      ps.seed_stride = geo.seed_stride;
       const size_t scratch_rows = (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit;
       ps.lists = p.lists + scratch_rows * (size_t)geo.L;
       ps.counts = p.counts + scratch_rows;

@@ -88,6 +88,7 @@ struct SearchGeom {
   int L;              // list capacity per row
   int seed_splits;    // units per query block of the threshold-seeding pre-pass (0 = none)
   int64_t seed_len;   // gallery rows per seeding unit
+  int seed_stride;    // > 0: the pre-pass collects chunk maxima (SearchParams::seed_stride) instead of selecting
 };
 
 }  // namespace knn

@@ -34,6 +34,8 @@ struct SearchParams {
   uint32_t* maxima;      // [qblocks*128][splits*groups] best score of every list (threshold seeding from list maxima)
   int32_t* progress;     // [splits][qblocks/2] tile index every CTA pair last published (soft lock-step of the pairs that
                          // stream the same gallery range, pair kernel only); -1 = not started; nullptr = off
+  int seed_stride;       // > 0: threshold-seeding pass in MAXIMA mode (pair kernel): every selection thread appends the
+                         // best score of each run of `seed_stride` of its 32-column chunks instead of selecting
   float* dense_out;      // dense mode only
   double* stats_out;     // statistics mode only: [splits][qblocks][128][4] = sum, sum of squares, min, max
 };

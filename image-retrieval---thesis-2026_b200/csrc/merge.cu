@@ -1,4 +1,5 @@
 // Final selection over per-unit candidate lists, k-way merge of per-shard results, and full row ranking.
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -651,6 +652,20 @@ int launch_merge_units(const SearchParams& p, int64_t index_base, float* out_val
   const int64_t max_keys = (int64_t)p.splits * p.groups * 2 * p.kp;
   int cap = 2 * p.kp;  // >= k, power of two
   while (cap < max_keys && cap < kSortCap) cap <<= 1;
+  // Many rows, final merge: the shared threshold every unit published leaves k .. ~2k keys per row above it, whatever
+  // the number of lists, so a row rarely needs more than 4 * kp sort slots -- and a 128-thread CTA with an 8 KB buffer
+  // (12 per SM) spends far less time in block barriers than a 512-thread one with 32 KB (3 per SM; ncu: 16.5 barrier
+  // stalls per issue).  Rows with more survivors (mass ties at the cut-off) take the radix-select passes of the kernel.
+  static const int optimistic = [] {
+    const char* e = getenv("KNN_MERGE_SMALL_CTA");   // 0: size the CTA for the worst case (round-1 behaviour)
+    return e ? atoi(e) : 1;
+  }();
+  // (up to 32 lists per row -- 8192 x 6.25 M, 18 lists: 0.57 -> 0.31 ms; with the 74 lists of 8192 x 50 M more rows
+  // overflow the small buffer than the shorter barriers save: 1.19 -> 1.30 ms, so those keep the large CTA)
+  if (optimistic && tau_out == nullptr && p.nq >= 2048 && p.splits * p.groups <= 32) {
+    const int small = 4 * p.kp > 1024 ? 4 * p.kp : 1024;
+    if (cap > small) cap = small;
+  }
   const int threads = cap <= 1024 ? 128 : (cap <= 2048 ? 256 : kSortThreads);
   merge_units_kernel<<<(unsigned)p.nq, threads, (size_t)cap * sizeof(uint64_t), stream>>>(p, index_base, out_val,
                                                                                         out_idx, tau_out, cap);

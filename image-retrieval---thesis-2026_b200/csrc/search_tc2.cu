@@ -307,6 +307,11 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int64_t dense_row = (dense && row_valid) ? row0 + rloc : -1;
     const int64_t dense_self = (p.self_mode != KNN_SELF_KEEP && dense_row >= 0) ? p.self_offset + dense_row : -1;
     const int et = threadIdx.x - 64;
+    const int seed_stride = dense ? 0 : p.seed_stride;   // > 0: maxima mode of the threshold-seeding pass (select.cuh)
+    SeedRun seed_run;
+    seed_run.best = -INFINITY;
+    seed_run.col = 0u;
+    seed_run.since = 0;
     long long e_wait = 0, e_slow = 0;
     unsigned long long n_slow = 0;
     const long long e_begin = stats_on ? clock64() : 0;
@@ -322,7 +327,7 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         gst[et] = __ldg(p.gsq + c);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       }
-      const uint32_t tau_peek = peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
+      const uint32_t tau_peek = seed_stride > 0 ? 0u : peek_tau(tau_row);  // L2 round trip hidden behind the barrier wait
       const long long cw = stats_on ? clock64() : 0;
       ptx::mbar_wait(&bars->tmem_full[as], aphase);
       if (stats_on) e_wait += clock64() - cw;
@@ -334,6 +339,8 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if (dense)
         dense_store_tile_tmem<kL2>(taddr, grp, 2, TN / 32, col0, c_end, gst, qn, dense_row, dense_self, p.self_mode,
                                    p.dense_out, p.ng);
+      else if (seed_stride > 0)
+        seed_tile_tmem<kL2>(st, seed_run, seed_stride, taddr, grp, 2, TN / 32, col0, c_end, gst, qn, self_row, row_valid);
       else if (debug != 1)
         select_tile_tmem<E, kL2>(st, pend, taddr, grp, 2, TN / 32, col0, c_end, gst, qn, self_row, p.self_mode, p.k,
                                  lane, tau_row, row_valid && debug != 2, stats_on, e_slow, n_slow);
@@ -343,8 +350,10 @@ search_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (leader) ptx::mbar_arrive(&bars->tmem_empty[as]);
         else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tmem_empty[as]), 0));
       }
-      if (!dense) flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
+      if (!dense && seed_stride == 0)
+        flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
+    if (seed_stride > 0 && seed_run.since > 0) seed_flush<kL2>(st, seed_run, row_valid);
     if (stats_on && lane == 0) {
       atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));
       atomicAdd(cfg.stats + 4, (unsigned long long)e_wait);

@@ -461,6 +461,57 @@ __device__ __forceinline__ void flush_pending_hits(RowState& st, PendingHits& pe
   }
 }
 
+// Threshold-seeding pass in MAXIMA mode (SearchParams::seed_stride > 0).  The pre-pass only has to produce a valid LOWER
+// BOUND of every query's final k-th best score, not the sample's top-k: the best score of each of n DISJOINT groups of
+// gallery rows belongs to n distinct rows, so the k-th largest of those maxima is reached by at least k rows.  A
+// selection thread therefore keeps ONE running maximum over `stride` consecutive chunks of its own (the chunk maximum
+// is what the fast path of select_tile_tmem computes anyway) and appends it as a key -- no threshold, no compaction,
+// none of the accept-everything warm-up a selecting unit pays (which was 85 % of the pre-pass at 8192 x 50 M).  With
+// 32..64 rows per group the k-th largest maximum sits within a few ranks of the sample's exact k-th best score.
+// Chunks that hold the query's own row (self modes) or padding columns contribute nothing: still a valid bound.
+// The key's row is the first column of the chunk that gave the maximum -- distinct for distinct groups.
+struct SeedRun {
+  float best;
+  uint32_t col;
+  int since;
+};
+template <bool kL2>
+__device__ __forceinline__ void seed_flush(RowState& st, SeedRun& run, bool row_valid) {
+  if (row_valid && run.best > -INFINITY) {
+    __stcg(st.list + st.cnt, make_key(exact_score<kL2>(run.best), run.col));
+    ++st.cnt;
+  }
+  run.best = -INFINITY;
+  run.since = 0;
+}
+template <bool kL2>
+__device__ __forceinline__ void seed_tile_tmem(RowState& st, SeedRun& run, int stride, uint32_t taddr, int first,
+                                               int step, int nchunks, int64_t col0, int64_t c_end, const float* gst,
+                                               float qn, uint32_t self_row, bool row_valid) {
+#pragma unroll 1
+  for (int ch = first; ch < nchunks; ch += step) {
+    const int cb = ch * 32;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + (uint32_t)cb, v);
+    ptx::tmem_ld_fence(v);
+    const int64_t cg = col0 + cb;
+    const float* gn = gst + cb;
+    auto fv = [&](int j) -> float {
+      const float dot = __uint_as_float(v[j]);
+      if (kL2) return fmaf(2.0f, dot, -(qn + gn[j]));
+      return dot;
+    };
+    const float m = chunk_max32(fv);
+    const bool whole = cg + 32 <= c_end;                            // no padding column in this chunk
+    const bool has_self = self_row - (uint32_t)cg < 32u;            // self_row = 0xFFFFFFFF: never
+    if (whole && !has_self && m > run.best) {                       // (a NaN maximum fails the compare: skipped)
+      run.best = m;
+      run.col = (uint32_t)cg;
+    }
+    if (++run.since >= stride) seed_flush<kL2>(st, run, row_valid);
+  }
+}
+
 // Dense mode of the tcgen05 kernels: instead of selecting, the owners of a query row write its scores of this tile to the
 // dense [nq, ld] block (similarity, or the positive L2 distance; the query's own column masked as knn_scores_dense does).
 // Every lane executes the (warp-collective) tensor-memory loads; a lane without a valid row just does not store.

@@ -162,6 +162,12 @@ KNN_API int knn_profile_last(float* distance_ms_host, float* merge_ms_host);
  * their TMA / MMA / selection roles spend waiting on each other to 32 device counters (layout: DESIGN.md
  * "stall counters").  Synchronises the device, copies the counters to out32 (host), optionally clears them. */
 KNN_API int knn_debug_stats(unsigned long long* out32_host, int reset);
+/* Work decomposition knn_search / knn_search_workspace use for this problem (host arithmetic only, no device call):
+ * out8_host = {query blocks of 128 rows, gallery splits, candidate lists per (split, row), gallery rows per split,
+ * list capacity, units per query block of the threshold-seeding pre-pass (0 = none), gallery rows per seeding unit,
+ * chunks per appended maximum of the pre-pass (0 = the pre-pass selects like the main pass)}.  For measurement
+ * harnesses and tests; no reference counterpart (torch.mm + topk has no decomposition, test.py:1006,44). */
+KNN_API int knn_search_geometry(int64_t nq, int64_t ng, int d, int dtype, int k, int64_t* out8_host);
 
 /* Hamming distance over binary codes + fused top-k: the replacement of
  * `(q[:, None, :] != g[None, :, :]).sum(dim=2).float()` + `argsort(dim=1)`, test_ath.py:80-100, train_ath.py:162-175.

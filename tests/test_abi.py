@@ -96,3 +96,37 @@ def test_exact_engine_host_logic():
     assert S.rerun_ranges([5, 130, 131, 600], 2000) == [(0, 256), (512, 640)]
     assert S.rerun_ranges([1999], 2000) == [(1920, 2000)]
     assert S.rerun_ranges(list(range(0, 2000, 128)), 2000) == [(0, 2000)]
+
+
+def test_search_geometry_of_the_seeding_pre_pass():
+    """knn_search_geometry is host arithmetic: the threshold-seeding pre-pass of the large-batch bf16 path collects chunk
+    maxima (seed_stride >= 1), its lists fit their capacity, the sample stays below 2 % of the gallery; small batches
+    and fp32 keep the selecting pre-pass."""
+    from b200knn import _lib
+
+    lib = _lib.load()
+
+    def geo(nq, ng, d, dtype, k):
+        out = (C.c_int64 * 8)()
+        assert lib.knn_search_geometry(nq, ng, d, dtype, k, out) == 0, lib.knn_last_error()
+        return dict(zip(("qblocks", "splits", "groups", "split_len", "L", "seed_units", "seed_len", "seed_stride"), out))
+
+    for nq, ng, d, k in [(8192, 50_000_000, 512, 100), (8192, 6_250_000, 512, 100), (8192, 2_000_000, 512, 100),
+                         (1280, 820_000, 64, 10), (1280, 820_000, 64, 256), (4096, 30_000_000, 768, 32)]:
+        g = geo(nq, ng, d, 1, k)
+        assert g["seed_stride"] >= 1 and g["seed_units"] >= 1, (nq, ng, k, g)
+        assert g["seed_len"] % 256 == 0 and g["seed_units"] * g["seed_len"] <= ng // 50
+        per_thread = g["seed_len"] // 256 * 8 // g["groups"]            # chunks of one selection thread in a unit
+        keys = -(-per_thread // g["seed_stride"])
+        assert keys <= g["L"], g                                          # a list never overflows
+        kp = 32
+        while kp < k:
+            kp *= 2
+        assert g["seed_units"] * g["groups"] * keys >= 2 * kp, g          # enough maxima for a useful bound
+    g = geo(64, 10_000_000, 768, 1, 100)                                  # one query block: TMEM-resident kernel,
+    assert g["seed_stride"] == 1 << 30 and g["seed_units"] * g["groups"] >= 200   # one maximum per (unit, thread)
+    assert geo(64, 8_000_000, 1024, 1, 100)["seed_stride"] == 0           # d > 768: one-CTA shared-memory-A kernel
+    assert geo(1024, 5_000_000, 512, 1, 100)["seed_stride"] == 0          # <= 1024 rows: seeds from list maxima
+    assert geo(8192, 2_000_000, 512, 0, 100)["seed_stride"] == 0          # fp32 FFMA kernel
+    out = (C.c_int64 * 8)()
+    assert lib.knn_search_geometry(0, 10, 8, 0, 1, out) == -1 and lib.knn_search_geometry(4, 10, 8, 9, 1, out) == -1

@@ -275,6 +275,58 @@ def test_bf16_exact_grid_adversarial_and_self(knn):
     assert np.array_equal(host(i)[0], np.arange(64))
 
 
+def _geometry(knn, nq, ng, d, dtype, k):
+    import ctypes as C
+
+    from b200knn import _lib
+
+    out = (C.c_int64 * 8)()
+    assert _lib.load().knn_search_geometry(nq, ng, d, dtype, k, out) == 0
+    return dict(zip(("qblocks", "splits", "groups", "split_len", "L", "seed_units", "seed_len", "seed_stride"), out))
+
+
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_threshold_seeding_from_chunk_maxima_is_exact(knn, metric):
+    """Large query batches on the CTA-pair kernel seed their thresholds from the chunk maxima of a gallery sample
+    (select.cuh: seed_tile_tmem): the k-th largest maximum must be a LOWER bound of every query's final k-th best
+    score, or neighbours are lost.  Exactly-representable rows with real ties (thousands of equal scores around every
+    cut-off), the queries ARE rows of the sampled range (self exclusion inside the sample), every list geometry."""
+    ng, nq, d = 820_000, 1280, 64
+    x = synth.exact_grid(ng, d, 7, 64)
+    for k in (10, 100, 256):
+        geo = _geometry(knn, nq, ng, d, 1, k)
+        assert geo["seed_stride"] >= 1 and geo["seed_units"] * geo["seed_len"] >= 1280, geo   # the mode under test
+        v, i = knn.search(dev(x[:nq]), dev(x), k, metric, self_mode="exclude", precision="bf16")
+        v, i = host(v), host(i)
+        for lo in (0, 1000):
+            ov, oi = oracle.search(x[lo:lo + 24], x, k, metric, "exclude", lo)
+            assert np.array_equal(i[lo:lo + 24], oi), (k, lo, np.argwhere(i[lo:lo + 24] != oi)[:5])
+            assert np.array_equal(v[lo:lo + 24], ov)
+    # keep mode, queries that are not gallery rows, descending-by-row scores inside the sample (every chunk maximum
+    # sits in the chunk's first column) and an all-equal stretch
+    g2 = x.copy()
+    g2[:4096, 0] = (255 - np.arange(4096) // 16).astype(np.float32) / 256.0      # 8 significant bits: exact in bf16
+    g2[4096:6144] = g2[4096]
+    q2 = synth.exact_grid(nq, d, 8, 0)
+    q2[:, 0] = 0.5
+    v, i = knn.search(dev(q2), dev(g2), 100, metric, precision="bf16")
+    ov, oi = oracle.search(q2[600:632], g2, 100, metric)
+    assert np.array_equal(host(i)[600:632], oi) and np.array_equal(host(v)[600:632], ov)
+
+
+def test_small_batch_seeding_keeps_one_maximum_per_unit(knn):
+    """One query block on the TMEM-resident kernel: the pre-pass keeps a single running maximum per (unit, selection
+    thread) -- all the list-maxima seeding ever reads.  Bit-exact with real ties, self rows inside the sample."""
+    ng, nq, d = 3_400_000, 16, 64
+    geo = _geometry(knn, nq, ng, d, 1, 100)
+    assert geo["seed_stride"] == 1 << 30 and geo["qblocks"] == 1, geo
+    x = synth.exact_grid(ng, d, 9, 64)
+    for metric in ("ip", "l2"):
+        v, i = knn.search(dev(x[:nq]), dev(x), 100, metric, self_mode="exclude", precision="bf16")
+        ov, oi = oracle.search(x[:nq], x, 100, metric, "exclude", 0)
+        assert np.array_equal(host(i), oi) and np.array_equal(host(v), ov), metric
+
+
 # ------------------------------------------------------------------------------------------ dense / rank / merge
 @pytest.mark.parametrize("metric,self_mode", [("cosine", "exclude"), ("ip", "minus1"), ("l2", "exclude"), ("l2", "keep")])
 def test_scores_dense_bit_exact(knn, metric, self_mode):
