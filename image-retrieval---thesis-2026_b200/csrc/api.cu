@@ -304,7 +304,7 @@ static void seed_geometry(SearchGeom& g, int64_t ng, int tile, int64_t slots, bo
   // only the best score of every (unit, selection thread) is ever read, so the unit keeps just that -- one running
   // maximum per thread, one key per list, no appends (seed_stride = "the whole unit").
   if (ts_maxima && units * g.groups >= 2 * (int64_t)g.kp && units * g.groups <= 4096)
-    g.seed_stride = 1 << 30;
+    g.seed_stride = kSeedWholeUnit;
 }
 
 }  // namespace knn
@@ -491,7 +491,8 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
       ps.ng = (int64_t)geo.seed_splits * geo.seed_len;
       ps.splits = geo.seed_splits;
       ps.split_len = geo.seed_len;
-      ps.seed_stride = geo.seed_stride;
+      // (whole-unit maxima are written to the maxima table: only with the list-maxima seeding that reads it)
+      ps.seed_stride = (geo.seed_stride == kSeedWholeUnit && !(wl.seed_maxima && ts)) ? 0 : geo.seed_stride;
       const size_t scratch_rows = (size_t)geo.splits * geo.groups * geo.qblocks * kRowsPerUnit;
       ps.lists = p.lists + scratch_rows * (size_t)geo.L;
       ps.counts = p.counts + scratch_rows;
@@ -499,7 +500,7 @@ extern "C" int knn_search(const void* q, const void* g, const float* q_sqnorm, c
               : (dtype == KNN_BF16) ? launch_search_bf16(ps, s) : launch_search_f32(ps, false, s);
       if (rc != KNN_OK) return rc;
       // single query block: hundreds of short lists per row -> seed from the list maxima (list-parallel)
-      rc = wl.seed_maxima ? launch_seed_from_maxima(ps, p.tau_global, s)
+      rc = wl.seed_maxima ? launch_seed_from_maxima(ps, p.tau_global, s, ts && ps.seed_stride == kSeedWholeUnit)
                           : launch_merge_units(ps, 0, nullptr, nullptr, p.tau_global, s);
       if (rc != KNN_OK) return rc;
     }

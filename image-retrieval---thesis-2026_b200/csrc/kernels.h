@@ -34,8 +34,9 @@ struct SearchParams {
   uint32_t* maxima;      // [qblocks*128][splits*groups] best score of every list (threshold seeding from list maxima)
   int32_t* progress;     // [splits][qblocks/2] tile index every CTA pair last published (soft lock-step of the pairs that
                          // stream the same gallery range, pair kernel only); -1 = not started; nullptr = off
-  int seed_stride;       // > 0: threshold-seeding pass in MAXIMA mode (pair kernel): every selection thread appends the
-                         // best score of each run of `seed_stride` of its 32-column chunks instead of selecting
+  int seed_stride;       // > 0: threshold-seeding pass in MAXIMA mode: every selection thread appends the best score of
+                         // each run of `seed_stride` of its 32-column chunks instead of selecting; kSeedWholeUnit
+                         // (TMEM-resident kernel): one maximum per unit, written to `maxima` directly
   float* dense_out;      // dense mode only
   double* stats_out;     // statistics mode only: [splits][qblocks][128][4] = sum, sum of squares, min, max
 };
@@ -58,7 +59,9 @@ int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k
                         int table_cols, const int64_t* qcol, float alpha, float beta, int first_m, int64_t self_offset,
                         int mask_self, float* out_vals, cudaStream_t stream);
 // threshold seeding from list maxima: tau_out[row] = k-th largest of the row's list maxima (needs >= k lists per row)
-int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream);
+// reduced = true: the search kernel already wrote p.maxima (seed_stride == kSeedWholeUnit)
+int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream, bool reduced = false);
+constexpr int kSeedWholeUnit = 1 << 30;
 // order k (value, index) candidates per row best-first, ties by ascending index
 int launch_sort_topk(const float* vals, const int64_t* idx, int64_t nq, int k, int largest, float* out_vals,
                      int64_t* out_idx, cudaStream_t stream);

@@ -616,16 +616,18 @@ int launch_rescore_topk(const float* vals, const int64_t* idx, int64_t nq, int k
   return KNN_OK;
 }
 
-int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream) {
+int launch_seed_from_maxima(const SearchParams& p, uint32_t* tau_out, cudaStream_t stream, bool reduced) {
   if (p.nq == 0) return KNN_OK;
   const int V = p.splits * p.groups;
   if (p.maxima == nullptr || V < p.k || V > 4096) {
     set_error("internal: threshold seeding from list maxima needs k <= lists <= 4096 and scratch (lists=%d k=%d)", V, p.k);
     return KNN_E_INVALID;
   }
-  const int64_t warps = (int64_t)V * p.qblocks * kRowsPerUnit;
-  filter_lists_kernel<true><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
-  KNN_LAUNCHED();
+  if (!reduced) {
+    const int64_t warps = (int64_t)V * p.qblocks * kRowsPerUnit;
+    filter_lists_kernel<true><<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(p);
+    KNN_LAUNCHED();
+  }
   seed_select_kernel<<<(unsigned)p.nq, 256, (size_t)pow2_ge(V) * sizeof(uint32_t), stream>>>(p.maxima, V, p.nq, p.k, tau_out);
   KNN_LAUNCHED();
   return KNN_OK;

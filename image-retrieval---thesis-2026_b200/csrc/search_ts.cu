@@ -308,7 +308,15 @@ search_bf16_ts_kernel(const __grid_constant__ CUtensorMap tmap_g, SearchParams p
       if (seed_stride == 0)
         flush_pending_hits<E, kL2>(st, pend, self_row, p.self_mode, p.k, lane, tau_row, stats_on, e_slow);
     }
-    if (seed_stride > 0 && seed_run.since > 0) seed_flush<kL2>(st, seed_run, row_valid);
+    if (seed_stride == kSeedWholeUnit && p.maxima != nullptr) {
+      // one maximum per (unit, selection thread), written straight into the table seed_select_kernel reads
+      // ([row][splits * 2], order-preserving encoding, 0 = none): no list, no filter_lists launch
+      if (row_valid)
+        p.maxima[(row0 + rloc) * ((int64_t)p.splits * 2) + (sp * 2 + grp)] =
+            seed_run.best > -INFINITY ? f2ord(exact_score<kL2>(seed_run.best) + 0.0f) : 0u;
+    } else if (seed_stride > 0 && seed_run.since > 0) {
+      seed_flush<kL2>(st, seed_run, row_valid);
+    }
     if (stats_on && lane == 0) {
       atomicAdd(cfg.stats + 3, (unsigned long long)(clock64() - e_begin));
       atomicAdd(cfg.stats + 4, (unsigned long long)e_wait);
