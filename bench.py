@@ -471,6 +471,13 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
     }
+    if not exact:   # work decomposition of this rank's search (host arithmetic of the library, knn_search_geometry)
+        geo = (ctypes.c_int64 * 8)()
+        if lib.knn_search_geometry(nq, count, d, 1, k, geo) == 0:
+            line["roofline"]["decomposition"] = {
+                "query_blocks": geo[0], "gallery_splits": geo[1], "lists_per_row": geo[1] * geo[2],
+                "seeding_sample_rows": geo[5] * geo[6],
+                "seeding": ("none" if geo[5] == 0 else "chunk maxima" if geo[7] > 0 else "selecting pre-pass")}
     if exact:
         import importlib
 

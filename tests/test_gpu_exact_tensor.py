@@ -82,6 +82,25 @@ def test_tensor_engine_is_bit_identical_to_the_oracle(knn, tensor_engine, nq, ng
     _check(knn, q, g, k, metric)
 
 
+def test_large_batch_filter_seeds_from_chunk_maxima(knn, tensor_engine):
+    """A large batch over a large gallery: the split filter's pre-pass collects chunk maxima (select.cuh:
+    seed_tile_tmem) like the plain bf16 kernel's.  Bit-identical to the oracle on a slice of the queries."""
+    import ctypes as C
+
+    from b200knn import _lib
+
+    nq, ng, d, k = 1280, 820_000, 64, 50
+    out = (C.c_int64 * 8)()
+    assert _lib.load().knn_search_geometry(nq, ng, 3 * d, 2, 64, out) == 0 and out[7] >= 1, list(out)   # kc = 64 rows
+    rs = np.random.RandomState(17)
+    g = oracle.normalize(rs.standard_normal((ng, d)).astype(np.float32))
+    q = oracle.normalize(g[:nq] + 0.5 * rs.standard_normal((nq, d)).astype(np.float32))
+    for metric in ("cosine", "l2"):
+        v, i = knn.search(dev(q), dev(g), k, metric, precision="fp32")
+        ov, oi = oracle.search(q[100:132], g, k, metric)
+        assert np.array_equal(host(i)[100:132], oi) and np.array_equal(host(v)[100:132], ov), metric
+
+
 def test_self_modes_offsets_and_clustered_data(knn, tensor_engine):
     x, _ = synth.clustered(2000, 128, 3, seed=7, noise=0.8)
     e = oracle.normalize(x)
