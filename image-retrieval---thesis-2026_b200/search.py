@@ -375,14 +375,20 @@ def filter_error_bound(qsq: torch.Tensor, max_gsq: torch.Tensor, d: int, metric:
     return eps
 
 
+_TWO_PRODUCT_MIN_ROWS = 49152
+
+
 def _two_product_filter(nq: int, ng: int, self_mode: str) -> bool:
     """Whether the tensor-core exact engine tries the two-product filter first (KNN_EXACT_PRODUCTS=2|3 forces it):
     queries it cannot prove are GATHERED and re-run through the three-product filter, which needs self_mode "keep" (a
-    gathered batch has no ``query_offset + i`` self rows), and several 256-row query blocks to be worth a second pass."""
+    gathered batch has no ``query_offset + i`` self rows), several 256-row query blocks to be worth a second pass, and a
+    gallery (shard) large enough: dropping a product saves a third of the filter, which scales with the gallery rows,
+    while the wider candidate set costs ~1.1 ms of extra re-scoring per 25 000 queries whatever the gallery -- even at
+    ~42 k rows (25 000 x 14 000 x 1024, the 8-GPU shard of config 3: 6.2 ms with two products, 4.9 ms with three)."""
     forced = os.environ.get("KNN_EXACT_PRODUCTS", "")
     if self_mode != "keep" or forced == "3":
         return False
-    return forced == "2" or nq >= 1024
+    return forced == "2" or (nq >= 1024 and ng >= _TWO_PRODUCT_MIN_ROWS)
 
 
 def _search_exact_tensor(q, qsq, g, gsq, k, metric, self_mode, query_offset, index_base,

@@ -130,3 +130,65 @@ def test_search_geometry_of_the_seeding_pre_pass():
     assert geo(8192, 2_000_000, 512, 0, 100)["seed_stride"] == 0          # fp32 FFMA kernel
     out = (C.c_int64 * 8)()
     assert lib.knn_search_geometry(0, 10, 8, 0, 1, out) == -1 and lib.knn_search_geometry(4, 10, 8, 9, 1, out) == -1
+
+
+def test_search_geometry_invariants_over_random_problems():
+    """Property sweep of the host-side work decomposition: the splits cover the gallery, the seeding sample is a prefix of
+    at most 2 % of it, a maxima-mode list never holds more keys than its capacity, and the workspace query grows with
+    the decomposition it describes."""
+    import random
+
+    from b200knn import _lib
+
+    lib = _lib.load()
+    rnd = random.Random(20261019)
+    names = ("qblocks", "splits", "groups", "split_len", "L", "seed_units", "seed_len", "seed_stride")
+    for _ in range(3000):
+        nq = rnd.choice([1, 7, 64, 128, 129, 300, 1024, 1025, 2048, 5000, 8192, 25000, 40000])
+        ng = int(10 ** rnd.uniform(2, 8.2))
+        d = rnd.choice([8, 64, 256, 512, 768, 1024, 2048])
+        k = rnd.choice([1, 10, 32, 33, 50, 100, 128, 200, 256])
+        dtype = rnd.choice([0, 1])
+        out = (C.c_int64 * 8)()
+        assert lib.knn_search_geometry(nq, ng, d, dtype, k, out) == 0, lib.knn_last_error()
+        g = dict(zip(names, out))
+        tag = (nq, ng, d, k, dtype, g)
+        assert g["qblocks"] * 128 >= nq and g["groups"] in (1, 2), tag
+        assert g["splits"] >= 1 and g["splits"] * g["split_len"] >= ng and (g["splits"] - 1) * g["split_len"] < ng, tag
+        kp = 32
+        while kp < k:
+            kp *= 2
+        assert g["L"] == 2 * kp, tag
+        if g["seed_units"] == 0:
+            assert g["seed_stride"] == 0 and g["seed_len"] == 0, tag
+            continue
+        assert g["seed_units"] * g["seed_len"] <= ng // 50, tag
+        if g["seed_stride"] == 0:
+            continue
+        assert dtype == 1, tag
+        if g["seed_stride"] == 1 << 30:                               # one maximum per (unit, selection thread)
+            assert g["qblocks"] == 1 and 2 * kp <= g["seed_units"] * g["groups"] <= 4096, tag
+            assert g["seed_len"] % 32 == 0 or g["seed_len"] == 224, tag
+        else:
+            assert g["qblocks"] * 128 > 1024 and g["seed_len"] % 256 == 0, tag
+            per_thread = g["seed_len"] // 256 * 8 // g["groups"]
+            keys = -(-per_thread // g["seed_stride"])
+            assert 1 <= keys <= g["L"], tag
+            assert g["seed_units"] * g["groups"] * keys >= 2 * kp, tag
+        assert lib.knn_search_workspace(nq, ng, d, dtype, k) > 0
+
+
+def test_two_product_filter_rule(monkeypatch):
+    """Host logic of the exact engine: the two-product filter is tried first only for keep-mode batches of >= 1024
+    queries over a gallery (shard) large enough that a third of the filter outweighs the wider re-scoring."""
+    from b200knn import search as S
+
+    monkeypatch.delenv("KNN_EXACT_PRODUCTS", raising=False)
+    assert S._two_product_filter(25_000, 112_000, "keep")
+    assert not S._two_product_filter(25_000, 14_000, "keep")         # the 8-GPU shard of config 3
+    assert not S._two_product_filter(512, 112_000, "keep")
+    assert not S._two_product_filter(25_000, 112_000, "exclude")
+    monkeypatch.setenv("KNN_EXACT_PRODUCTS", "2")
+    assert S._two_product_filter(25_000, 14_000, "keep")
+    monkeypatch.setenv("KNN_EXACT_PRODUCTS", "3")
+    assert not S._two_product_filter(25_000, 112_000, "keep")
