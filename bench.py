@@ -339,7 +339,14 @@ def run_workload(name, args, ctx, steps, warmup, primary):
     # runs one step behind); `drain` takes the last one, inside the timed region.
     pending = []
 
+    last_copy = [None]
+
     def take(p, to_host):
+        if to_host and hasattr(p, "to_host"):
+            # pipelined exchange: the device->host copies ride on the side stream behind the merge (copy engine, under
+            # the next local search); `drain` makes the timed stream wait for the last of them
+            last_copy[0] = p.to_host(out_val_host, out_idx_host)
+            return p.vals, p.idx
         v, i = p.result()
         if to_host:
             out_val_host.copy_(v, non_blocking=True)
@@ -366,6 +373,9 @@ def run_workload(name, args, ctx, steps, warmup, primary):
         res = None
         while pending:
             res = take(*pending.pop(0))
+        if last_copy[0] is not None:      # the closing event of the timed region comes after the last host copy
+            torch.cuda.current_stream(dev).wait_event(last_copy[0])
+            last_copy[0] = None
         return res
 
     def barrier():

@@ -110,8 +110,9 @@ class PendingSearch:
     """What :meth:`ShardedFlatIndex.search_async` returns: the result tensors and the event after which they are
     complete (recorded on the side stream of the pipelined exchange; ``None`` = complete in stream order already)."""
 
-    def __init__(self, vals: torch.Tensor, idx: torch.Tensor, done: Optional[torch.cuda.Event] = None):
-        self.vals, self.idx, self.done = vals, idx, done
+    def __init__(self, vals: torch.Tensor, idx: torch.Tensor, done: Optional[torch.cuda.Event] = None,
+                 stream: Optional[torch.cuda.Stream] = None):
+        self.vals, self.idx, self.done, self.stream = vals, idx, done, stream
 
     def result(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(distances, indices), safe to use on the CURRENT stream (which is made to wait for the merge)."""
@@ -122,6 +123,21 @@ class PendingSearch:
             self.idx.record_stream(cur)
             self.done = None
         return self.vals, self.idx
+
+    def to_host(self, out_vals: torch.Tensor, out_idx: torch.Tensor) -> torch.cuda.Event:
+        """Copy the result into (pinned) host tensors WITHOUT involving the current stream: the copies are enqueued on
+        the stream that produces the result -- the side stream of the pipelined exchange, right behind the merge -- so
+        they run on the copy engine under the next local search instead of between two searches.  Returns the event
+        after which the host tensors are complete (``event.synchronize()``, or ``stream.wait_event(event)``, before
+        reading them)."""
+        dev = self.vals.device
+        s = self.stream if (self.done is not None and self.stream is not None) else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(s):
+            out_vals.copy_(self.vals, non_blocking=True)
+            out_idx.copy_(self.idx, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        return ev
 
 
 class ShardedFlatIndex:
@@ -301,7 +317,7 @@ class ShardedFlatIndex:
             self._prof.append(marks)
             if len(self._prof) > 64:
                 self._prof.pop(0)
-        return PendingSearch(vals, idx, done)
+        return PendingSearch(vals, idx, done, self._side)
 
     def search_host_async(self, queries_host: torch.Tensor, k: int, *, exclude_self: bool = False,
                           self_mode: Optional[str] = None, query_offset: int = 0) -> PendingSearch:

@@ -85,6 +85,20 @@ def _worker(rank, world, port, out_dir):
         v, i = p.result()
         if not (torch.equal(i, want[which][1]) and torch.equal(v, want[which][0])):
             failures.append(("pipelined-tail", which, int((i != want[which][1]).sum())))
+    # results copied to the host on the side stream (PendingSearch.to_host), the next searches already enqueued
+    host_bufs = [(torch.empty((300, 100), dtype=torch.float32).pin_memory(),
+                  torch.empty((300, 100), dtype=torch.int64).pin_memory()) for _ in range(6)]
+    copies = []
+    for step in range(6):
+        if lag.random() < 0.5:
+            torch.cuda._sleep(int(lag.random() * 3e6))
+        p = sh.search_async(qa if step & 1 == 0 else qb, 100)
+        copies.append((step & 1, p, p.to_host(*host_bufs[step])))
+    for step, (which, p, ev) in enumerate(copies):
+        ev.synchronize()
+        hv, hi = host_bufs[step]
+        if not (torch.equal(hi, want[which][1].cpu()) and torch.equal(hv, want[which][0].cpu())):
+            failures.append(("pipelined-to-host", step, which))
     v, i = sh.search_host(qb.cpu().pin_memory(), 100)         # the synchronous entry points on a pipelined index
     if not (torch.equal(i, want[1][1]) and torch.equal(v, want[1][0])):
         failures.append(("pipelined", "search_host"))
