@@ -181,8 +181,9 @@ def test_search_geometry_invariants_over_random_problems():
 def test_two_product_filter_rule(monkeypatch):
     """Host logic of the exact engine: the two-product filter is tried first only for keep-mode batches of >= 1024
     queries over a gallery (shard) large enough that a third of the filter outweighs the wider re-scoring."""
-    from b200knn import search as S
+    import importlib
 
+    S = importlib.import_module("b200knn.search")        # (`b200knn.search` the attribute is the function)
     monkeypatch.delenv("KNN_EXACT_PRODUCTS", raising=False)
     assert S._two_product_filter(25_000, 112_000, "keep")
     assert not S._two_product_filter(25_000, 14_000, "keep")         # the 8-GPU shard of config 3
