@@ -71,6 +71,12 @@ class ComparisonConfig:
     search_batch_size: int = 10
 
 
+def compare_collection_coverage(conv_adapter, dino_adapter) -> Dict[str, List[str]]:
+    """``image_path`` coverage of the two collections (retrieval_analysis/milvus_adapter.py:309-320)."""
+    cp, dp = set(conv_adapter.list_image_paths()), set(dino_adapter.list_image_paths())
+    return {"conv_only": sorted(cp - dp), "dino_only": sorted(dp - cp), "present_in_both": sorted(cp & dp)}
+
+
 def filter_present_queries(queries, coverage: Dict[str, List[str]]) -> Dict[str, List[QueryRecord]]:
     """milvus_adapter.py:321-336."""
     present = set(coverage["present_in_both"])

@@ -107,9 +107,11 @@ def flatten_query_result(result: Mapping[str, Any]) -> Dict[str, Any]:
 
 
 def write_csv(path: str, rows: Sequence[Mapping[str, Any]]) -> str:
-    """export_utils.py:22-42: header = union of the row keys in first-seen order."""
+    """export_utils.py:22-42: header = union of the row keys in first-seen order (no rows: a file with an empty header
+    line)."""
     out = Path(path)
     out.parent.mkdir(parents=True, exist_ok=True)
+    rows = list(rows)
     fieldnames: List[str] = []
     for row in rows:
         for key in row.keys():
@@ -127,3 +129,34 @@ def save_fused_embeddings(path: str, image_paths: Sequence[str], labels: Sequenc
     np.savez_compressed(path, image_paths=np.asarray(image_paths), labels=np.asarray(labels),
                         embeddings=np.asarray(_np(embeddings), dtype=np.float32))
     return path
+
+
+COMPARISON_GROUPS = ("both_correct", "both_wrong", "dino_correct_conv_wrong", "conv_correct_dino_wrong")
+
+
+def export_analysis(payload: Mapping[str, Any], output_dir) -> List[str]:
+    """Files of one dual-collection comparison (retrieval_analysis/run_analysis.py:67-85): the whole ``compare_models``
+    payload as ``comparison_results.json``, its per-query rows flattened as ``comparison_results.csv`` and one
+    ``group_<name>.csv`` per comparison group (written even when the group is empty).  -> the paths written."""
+    root = Path(output_dir)
+    written = [write_json(str(root / "comparison_results.json"), payload)]
+    flat = [(row["assigned_group"], flatten_query_result(row)) for row in payload["results"]]
+    written.append(write_csv(str(root / "comparison_results.csv"), [r for _, r in flat]))
+    for group in COMPARISON_GROUPS:
+        written.append(write_csv(str(root / f"group_{group}.csv"), [r for g, r in flat if g == group]))
+    return written
+
+
+def comparison_summary_text(payload: Mapping[str, Any]) -> str:
+    """What the runner prints after a comparison (run_analysis.py:88-108), as one string."""
+    cov, summ = payload["coverage"], payload["summary"]
+    lines = ["Coverage:", f"  Present in ConvNeXt only: {len(cov['present_in_conv_only'])}",
+             f"  Present in DINO only: {len(cov['present_in_dino_only'])}",
+             f"  Present in both: {len(cov['present_in_both'])}", "Summary:"]
+    lines += [f"  {key}: {summ[key]}" for key in COMPARISON_GROUPS + ("evaluated_queries",)]
+    lines += [f"  missing_queries: {len(payload['missing_queries'])}", f"  errors: {len(payload['errors'])}"]
+    return "\n".join(lines) + "\n"
+
+
+def print_summary(payload: Mapping[str, Any]) -> None:
+    print(comparison_summary_text(payload), end="")
