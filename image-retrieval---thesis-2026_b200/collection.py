@@ -18,6 +18,7 @@ the similarity (larger = closer); for L2 it is the Euclidean distance and ``simi
 from __future__ import annotations
 
 import json
+import os
 import re
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional, Sequence
@@ -419,6 +420,66 @@ class LocalRetriever:
     def batch_search(self, query_image_paths, top_k: int = 10, search_params=None):
         """milvus_retrieval.py:122-140."""
         return [self.search(q, top_k, search_params)[0] for q in query_image_paths]
+
+
+class PathMapper:
+    """Stored (Kaggle) image paths -> paths on the local machine (milvus/path_mapper.py:10-107): a hit's ``image_path`` is
+    re-rooted by FILE NAME under ``local_base_path``."""
+
+    def __init__(self, kaggle_prefix: str = "/kaggle/input", local_base_path: Optional[str] = None):
+        self.kaggle_prefix = kaggle_prefix
+        self.local_base_path = local_base_path
+
+    def extract_filename(self, kaggle_path: str) -> str:
+        return os.path.basename(kaggle_path)
+
+    def extract_relative_path(self, kaggle_path: str) -> str:
+        """What follows ``.../input/<dataset>/``; the file name when the path has no ``input`` component."""
+        parts = kaggle_path.split("/")
+        if "input" in parts:
+            return "/".join(parts[parts.index("input") + 2:])
+        return self.extract_filename(kaggle_path)
+
+    def remap_path(self, kaggle_path: str, local_base_path: Optional[str] = None) -> str:
+        base = local_base_path or self.local_base_path
+        if not base:
+            raise ValueError("local_base_path must be provided")
+        return os.path.join(base, self.extract_filename(kaggle_path))
+
+    def verify_path(self, kaggle_path: str, local_base_path: Optional[str] = None):
+        remapped = self.remap_path(kaggle_path, local_base_path)
+        return os.path.exists(remapped), remapped
+
+    def batch_remap(self, kaggle_paths, local_base_path: Optional[str] = None) -> List[str]:
+        return [self.remap_path(p, local_base_path) for p in kaggle_paths]
+
+
+class LocalRetrieverPatched(LocalRetriever):
+    """``MilvusRetrieverPatched`` (milvus/milvus_retrieval_patched.py:9-133): the same search, with the ``image_path`` of
+    every hit that starts with ``/kaggle/`` re-rooted under ``local_data_base_path`` (the reference also prints each
+    remapped pair; this one does not)."""
+
+    def __init__(self, collection: LocalCollection, embed_fn: Optional[Callable[[Any], torch.Tensor]] = None,
+                 local_data_base_path: Optional[str] = None, enable_path_mapping: bool = True):
+        super().__init__(collection, embed_fn)
+        self.enable_path_mapping = enable_path_mapping
+        self.path_mapper = PathMapper(local_base_path=local_data_base_path) \
+            if (enable_path_mapping and local_data_base_path) else None
+
+    def _remap_image_path(self, kaggle_path: str) -> str:
+        if self.path_mapper is None or not kaggle_path.startswith("/kaggle/"):
+            return kaggle_path
+        return self.path_mapper.remap_path(kaggle_path)
+
+    def _remap_results(self, results: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+        for r in results:
+            r["image_path"] = self._remap_image_path(r["image_path"])
+        return results
+
+    def search(self, query_image_path, top_k: int = 10, search_params: Optional[Mapping[str, Any]] = None,
+               metric_type: str = "COSINE"):
+        results, query_embedding = super().search(query_image_path, top_k, search_params, metric_type)
+        return self._remap_results(results), query_embedding
 
 
 # ----------------------------------------------------------------------------------------------------------------
