@@ -16,11 +16,12 @@ from . import fullrank
 from . import pairwise
 from . import sources
 from . import nih
+from . import chestmir
 from .sharded import ShardedFlatIndex
 
 __all__ = [
     "KnnError", "LIB_PATH", "load_library", "FlatIndex", "ShardedFlatIndex", "merge_topk", "normalize",
     "merge_topk_parts", "pack_bits", "rank_rows", "row_sqnorm", "scores_dense", "search", "search_hamming",
     "split_bf16x3", "unpack_bits_pm1", "metrics", "fusion", "collection", "formats", "analysis", "fullrank", "pairwise",
-    "sources", "nih",
+    "sources", "nih", "chestmir",
 ]
