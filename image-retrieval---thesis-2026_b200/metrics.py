@@ -11,7 +11,7 @@ Two entry styles per metric family:
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -421,6 +421,44 @@ def evaluate_results_from_topk(vals: torch.Tensor, indices: torch.Tensor, qlabel
         metrics[f"P@{k}"] = float(np.mean(p) * 100.0) if len(p) else 0.0
         metrics[f"R@{k}"] = float(np.mean(r) * 100.0) if len(r) else 0.0
     return metrics
+
+
+def hits_to_arrays(items: Sequence[Mapping]):
+    """The hits JSON of query_nih_zilliz.py:58-72 (``formats.nih_query_results``) as arrays: scores fp32 [Q, K], hit
+    positions int64 [Q, K] (= rows of the label table below), query multi-hots fp32 [Q, C] and the multi-hots of all
+    hits fp32 [Q * K, C].  Every query must carry the same number of hits (what ``search_collection(top_k)`` returns)."""
+    nq = len(items)
+    k = len(items[0]["results"]) if nq else 0
+    for it in items:
+        if len(it["results"]) != k:
+            raise ValueError(f"evaluate_results on the device needs the same number of hits for every query "
+                             f"(got {len(it['results'])} and {k})")
+    qlab = np.asarray([it["query_label_vector"] for it in items], dtype=np.float32).reshape(nq, -1)
+    vals = np.asarray([[h["score"] for h in it["results"]] for it in items], dtype=np.float32).reshape(nq, k)
+    glab = np.asarray([h["label_vector"] for it in items for h in it["results"]], dtype=np.float32).reshape(nq * k, -1)
+    idx = np.arange(nq * k, dtype=np.int64).reshape(nq, k)
+    return vals, idx, qlab, glab
+
+
+def evaluate_results(items: Sequence[Mapping], jaccard_threshold: float, ks: Sequence[int], device=None) -> Dict[str, float]:
+    """Reference signature (evaluate_nih_zilliz.py:34-64): ``items`` is the hits JSON -- one entry per query with its
+    ``query_label_vector`` and ``results`` (each hit: ``score``, ``label_vector``).  Same metric dictionary; the work runs
+    in :func:`evaluate_results_from_topk` on the device."""
+    ks = [int(k) for k in ks]
+    if not items or not len(items[0]["results"]):
+        for it in items:
+            if len(it["results"]):
+                raise ValueError("evaluate_results on the device needs the same number of hits for every query")
+        # no query, or no hit for any query: every list the reference averages is empty or all zero
+        out = {"mAP": 0.0, "num_queries": float(len(items)), "num_valid_ap_queries": 0.0}
+        for k in ks:
+            out[f"P@{k}"] = 0.0
+            out[f"R@{k}"] = 0.0
+        return out
+    vals, idx, qlab, glab = hits_to_arrays(items)
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    to = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    return evaluate_results_from_topk(to(vals), to(idx), to(qlab), to(glab), jaccard_threshold, ks)
 
 
 def multilabel_hit_rate_from_topk(indices: torch.Tensor, qlabels_multihot: torch.Tensor,
