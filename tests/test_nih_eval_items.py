@@ -68,3 +68,13 @@ def test_hand_over_to_the_device_function(M, gold, monkeypatch):
     want = M.hits_to_arrays(gold["items"])
     for got, w in zip((seen["vals"], seen["idx"], seen["qlab"], seen["glab"]), want):
         assert isinstance(got, torch.Tensor) and np.array_equal(got.numpy(), w)
+
+
+@pytest.mark.gpu
+def test_device_result_equals_the_real_reference_function(M, gold):
+    """The whole entry on a B200: hits JSON in, the REAL ``evaluate_results``' metric dictionary out (keys in its order)."""
+    for thr, ks, key in ((gold["threshold"], gold["ks"], "metrics"), (0.0, [1, 3], "metrics_thr_0")):
+        got = M.evaluate_results(gold["items"], thr, ks)
+        assert list(got) == list(gold[key])
+        for name, want in gold[key].items():
+            assert abs(got[name] - want) < 1e-9, (key, name, got[name], want)
