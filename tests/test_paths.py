@@ -40,3 +40,24 @@ def test_patched_retriever_re_roots_only_kaggle_paths(tmp_path):
         assert off.path_mapper is None
         assert [h["image_path"] for h in off._remap_results(hits())] == [h["image_path"] for h in hits()]
     assert issubclass(C.LocalRetrieverPatched, C.LocalRetriever)
+
+
+@pytest.mark.gpu
+def test_patched_retriever_search_on_the_device():
+    """Same hits as the plain retriever, stored ``/kaggle/`` paths re-rooted under the local base (verified on a B200)."""
+    import numpy as np
+
+    C = importlib.import_module("b200knn.collection")
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((50, 16)).astype(np.float32)
+    paths = [f"/kaggle/input/ds/train/img_{i}.png" if i % 2 == 0 else f"/data/local/img_{i}.png" for i in range(50)]
+    coll = C.LocalCollection("c", 16, "COSINE")
+    coll.insert([{"image_path": p, "label": f"l{i % 3}", "embedding": v} for i, (p, v) in enumerate(zip(paths, x))])
+    plain, _ = C.LocalRetriever(coll).search(x[4], top_k=6)
+    patched, _ = C.LocalRetrieverPatched(coll, local_data_base_path="/mnt/data").search(x[4], top_k=6)
+    assert [h["id"] for h in plain] == [h["id"] for h in patched] and plain[0]["id"] == 4
+    for a, b in zip(plain, patched):
+        want = "/mnt/data/" + a["image_path"].rsplit("/", 1)[1] if a["image_path"].startswith("/kaggle/") else a["image_path"]
+        assert b["image_path"] == want and b["similarity"] == a["similarity"] and b["label"] == a["label"]
+    off, _ = C.LocalRetrieverPatched(coll, local_data_base_path="/mnt/data", enable_path_mapping=False).search(x[4], top_k=6)
+    assert off == plain
